@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""bench.py — the KNN hot path (Fit = all-pairs similarity, then full test-set Predict) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU algorithm
+
+One "step" = one pass of the hot path over one synthetic rating matrix of BASELINE.json configs[1]
+(KNNWithMeans, item-based Pearson, k=40, MovieLens-1M shape 6040 x 3706 with 1,000,000 training
+ratings; the test set is a further 200,000 held-out pairs of the same generator):
+    Fit(train)    -> dense N x N float64 similarity matrix resident in HBM (N = 3706 items)
+    Predict(test) -> 200,000 predictions
+metric = similarity pairs/s = N(N-1)/2 unordered left-row pairs / step time (Fit + Predict);
+predictions/s over the same step is reported beside it.  `value` is timed with CUDA events with
+every input already resident in HBM; `e2e` is the same step through the public API with HOST
+buffers (pinned), host<->device copies inside the timed region.
+
+N > 1 (torchrun, one rank per GPU): the path partitions into independent units, so rank r
+processes its own rating matrix of the named shape (a cross-validation fold per GPU, exactly
+how the reference parallelises, core/eval.go:28-35) — no data-path collective, scaling "weak".
+`--shard-rows` instead row-shards ONE matrix across the ranks and assembles the neighbour lists
+with an NCCL all-gather (scaling "strong"; meant for the ML-20M shapes, see profiles/).
+
+The reference arm times the CPU restatement of the Go algorithm (oracle/, the reference itself
+is Go and no Go toolchain exists in the image) on the box's host cores: Fit with nJobs = all
+cores exactly as core/knn.go:192-216, Predict as the reference's serial loop (core/data.go:98-105).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (users, items, train nnz, test nnz, sim, knn_type, user_based, k)
+    "ml1m_item_pearson_k40": (6040, 3706, 1_000_000, 200_000, "pearson", "centered", False, 40),
+    "ml100k_user_cosine_k40": (943, 1682, 80_000, 20_000, "cosine", "basic", True, 40),
+    "ml20m_item_pearson_k40": (138_493, 26_744, 20_000_000, 4_000_000, "pearson", "centered", False, 40),
+    "ml20m_user_msd_k100": (138_493, 26_744, 20_000_000, 0, "msd", "basic", True, 100),
+    "netflix_item_cosine_k50": (480_189, 17_770, 100_000_000, 20_000_000, "cosine", "basic", False, 50),
+}
+DEFAULT_WORKLOAD = "ml1m_item_pearson_k40"
+SEED = 0x5EED0000 + 1  # config index 1
+
+
+def make_data(workload, fold=0):
+    import recommend_sys_b200 as rs
+
+    users, items, nnz, n_test, *_ = WORKLOADS[workload]
+    d = rs.core.synth_ratings(users, items, nnz + n_test, SEED + 1000 * fold)
+    test = d.SubSet(np.arange(0, n_test))
+    train = rs.NewTrainSet(d.SubSet(np.arange(n_test, d.Length())))
+    return train, test
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [x for x in sm if x >= 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return float(j["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def cpu_reference_step(ob, ots, test, sim, knn_type, user_based, k, cores, rows=None, n_pred=None):
+    """One step of the reference's CPU algorithm (restated in oracle/): returns (seconds_fit,
+    seconds_predict, rows_fitted, n_predicted)."""
+    knn = ob.KNN(sim=sim, knn_type=knn_type, user_based=user_based, k=k, n_jobs=cores, tie_policy="go")
+    t0 = time.perf_counter()
+    knn.fit(ots, rows=rows)
+    t1 = time.perf_counter()
+    u, i = test.Users, test.Items
+    if rows is not None:
+        inner = (ots_inner(ots, user_based))
+        left_of_test = inner(u if user_based else i)
+        sel = np.where((left_of_test >= rows[0]) & (left_of_test < rows[1]))[0]
+        u, i = u[sel], i[sel]
+    if n_pred is not None:
+        u, i = u[:n_pred], i[:n_pred]
+    t2 = time.perf_counter()
+    knn.predict_batch(u, i, n_threads=1)  # the reference's loop is serial (core/data.go:98-105)
+    t3 = time.perf_counter()
+    return t1 - t0, t3 - t2, (knn.n if rows is None else rows[1] - rows[0]), len(u)
+
+
+def ots_inner(ots, user_based):
+    from oracle import binding as ob
+
+    L = ob.lib()
+    conv = L.or_trainset_convert_user if user_based else L.or_trainset_convert_item
+    return lambda raw: np.array([conv(ots.h, int(x)) for x in raw], dtype=np.int64)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (restated)."""
+    if rank != 0:
+        return
+    from oracle import binding as ob
+
+    users, items, nnz, n_test, sim, knn_type, user_based, k = WORKLOADS[args.workload]
+    train, test = make_data(args.workload)
+    ots = ob.TrainSet(train.Users, train.Items, train.Ratings)
+    cores = os.cpu_count() or 1
+    n = train.UserCount if user_based else train.ItemCount
+    pairs_full = n * (n - 1) / 2
+    budget_s = 200.0
+    # probe: a 64-row slab tells how long a full step would take
+    tf, tp, rows_done, npred = cpu_reference_step(ob, ots, test, sim, knn_type, user_based, k, cores,
+                                                  rows=(0, min(64, n)), n_pred=2000)
+    est_full = tf * (n / max(1, rows_done)) * 0.55 + (tp / max(1, npred)) * test.Length()
+    total_steps = args.steps + args.warmup
+    if est_full * total_steps <= budget_s:
+        rows, n_pred, sample = None, None, f"full workload: Fit all {n} rows + {test.Length()} serial predictions"
+    else:
+        frac = budget_s / (est_full * total_steps)
+        nrows = max(64, int(n * frac))
+        rows = (0, min(n, nrows))
+        n_pred = max(1000, int(test.Length() * frac))
+        sample = (f"slab of {rows[1]} of {n} left rows x all {n} (pairs/s from the slab) + first {n_pred} "
+                  f"of the slab's test pairs, serial")
+    times = []
+    for s in range(total_steps):
+        tf, tp, rows_done, npred = cpu_reference_step(ob, ots, test, sim, knn_type, user_based, k, cores, rows=rows,
+                                                      n_pred=n_pred)
+        if s >= args.warmup:
+            times.append((tf, tp, rows_done, npred))
+    tf = sum(t[0] for t in times) / len(times)
+    tp = sum(t[1] for t in times) / len(times)
+    rows_done, npred = times[0][2], times[0][3]
+    if rows is None:
+        pairs = pairs_full
+        step_s = tf + tp
+    else:
+        # the slab computes rows_done x (n-1) ordered pairs; a full Fit computes every unordered
+        # pair once (core/knn.go:203 skips filled cells), i.e. n/rows_done/2 slabs' worth
+        pairs = pairs_full
+        step_s = tf * (n / rows_done) * 0.5 + (tp / max(1, npred)) * test.Length()
+    value = pairs / step_s
+    line = {
+        "impl": "reference", "metric": "similarity_pairs_per_sec", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "predictions_per_sec": test.Length() / step_s,
+        "fit_ms": tf * 1e3, "predict_ms": tp * 1e3,
+        "config": {"workload": args.workload, "shape": f"{users}x{items}", "train_ratings": train.Length(),
+                   "test_pairs": test.Length(), "sim": sim, "knn_type": knn_type, "user_based": user_based, "k": k,
+                   "tie_policy": "go (pdqsort port)"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def pinned_like(a):
+    """A numpy view over page-locked host memory holding a copy of `a`."""
+    import torch
+
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    _KEEP.append(t)
+    return t.numpy()
+
+
+_KEEP = []
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import recommend_sys_b200 as rs
+    from recommend_sys_b200.shard import allgather_topk, shard_rows
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    users, items, nnz, n_test, sim, knn_type, user_based, k = WORKLOADS[args.workload]
+    shard = args.shard_rows and world > 1
+    train, test = make_data(args.workload, fold=0 if shard else rank)
+    n_left = train.UserCount if user_based else train.ItemCount
+    n_right = train.ItemCount if user_based else train.UserCount
+    left = train.innerUsers if user_based else train.innerItems
+    right = train.innerItems if user_based else train.innerUsers
+    t_left_raw = test.Users if user_based else test.Items
+    t_right_raw = test.Items if user_based else test.Users
+    t_left = (train.convert_users if user_based else train.convert_items)(t_left_raw)
+    t_right = (train.convert_items if user_based else train.convert_users)(t_right_raw)
+    rb, re = shard_rows(n_left, world, rank) if shard else (0, 0)
+    if shard and n_test:
+        mine = (t_left >= rb) & (t_left < re)
+        t_left, t_right = t_left[mine], t_right[mine]
+    n_pred = len(t_left)
+
+    stream = torch.cuda.current_stream()
+    h = rs.core._Handle(sim=sim, knn_type=knn_type, k=k, device=local_rank, row_begin=rb, row_end=re,
+                        store="topk" if (shard and not n_test) else "matrix", topk=k,
+                        pearson_mode=args.pearson_mode, sim_path=args.sim_path)
+    h.set_stream(stream.cuda_stream)
+
+    d_left = torch.from_numpy(left).to(dev)
+    d_right = torch.from_numpy(right).to(dev)
+    d_rating = torch.from_numpy(train.Ratings).to(dev)
+    d_tl = torch.from_numpy(t_left).to(dev) if n_pred else None
+    d_tr = torch.from_numpy(t_right).to(dev) if n_pred else None
+    d_out = torch.empty(max(1, n_pred), dtype=torch.float64, device=dev)
+    rows_local = (re - rb) if shard else n_left
+    d_tk_i = torch.empty((rows_local, k), dtype=torch.int32, device=dev) if shard else None
+    d_tk_s = torch.empty((rows_local, k), dtype=torch.float64, device=dev) if shard else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_device():
+        h.fit_device(d_left.data_ptr(), d_right.data_ptr(), d_rating.data_ptr(), len(left), n_left, n_right,
+                     train.GlobalMean)
+        if n_pred:
+            h.predict_batch_device(d_tl.data_ptr(), d_tr.data_ptr(), n_pred, d_out.data_ptr())
+        if shard:
+            h.topk_device(k, d_tk_i.data_ptr(), d_tk_s.data_ptr())
+            allgather_topk(d_tk_i, d_tk_s, n_left, k)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+        flush.fill_(1)
+    barrier()
+    h.profile_reset()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s in range(args.steps):
+        ev[s][0].record(stream)
+        step_device()
+        ev[s][1].record(stream)
+        flush.fill_(s & 0xff)  # L2 flush between timed iterations (outside the event pairs)
+    barrier()
+    clock_info = clocks.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    prof = h.profile()
+
+    # ---- e2e: public API, host (pinned) buffers in, host predictions out ----
+    train.innerUsers = pinned_like(train.innerUsers)
+    train.innerItems = pinned_like(train.innerItems)
+    train.Ratings = pinned_like(train.Ratings)
+    ctor = {"basic": rs.NewKNN, "centered": rs.NewKNNWithMean, "zscore": rs.NewKNNWithZScore,
+            "baseline": rs.NewKNNBaseLine}[knn_type]
+    sim_obj = {"cosine": rs.Cosine, "msd": rs.MSD, "pearson": rs.Pearson, "pearson_baseline": rs.PearsonBaseline}[sim]
+    params = {"sim": sim_obj, "userBased": user_based, "k": k, "device": local_rank,
+              "pearsonMode": args.pearson_mode, "simPath": args.sim_path}
+    if shard:
+        params.update({"rowBegin": rb, "rowEnd": re})
+    e2e_test = test
+    if shard and n_test:
+        e2e_test = test.SubSet(np.where(mine)[0])
+
+    def step_e2e():
+        est = ctor(rs.Parameters(params))
+        est.Fit(train)
+        out = e2e_test.Predict(est) if n_test else None
+        est.Close()
+        return out
+
+    e2e_steps = max(1, min(args.steps, 5))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+
+    # ---- reduce over ranks: max time, summed units ----
+    pairs_rank = n_left * (n_left - 1) / 2 if not shard else (re - rb) * (n_left - 1) / 2.0
+    red = torch.tensor([total_ms, e2e_s, prof["sim_kernel_ms"], prof["predict_kernel_ms"]], dtype=torch.float64,
+                       device=dev)
+    units = torch.tensor([pairs_rank, float(n_pred)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(units, op=dist.ReduceOp.SUM)
+    total_ms, e2e_s, sim_ms, pred_ms = red.tolist()
+    pairs_all, preds_all = units.tolist()
+    if rank != 0:
+        h.close()
+        return
+
+    ms_per_step = total_ms / args.steps
+    value = pairs_all / (ms_per_step / 1e3)
+    hbm_peak, peak_src = load_peaks()
+    # dominant kernel = the similarity kernel.  Algorithmic bytes per launch:
+    # one read of the left CSR (4 B id + 8 B rating per entry) + 8 B per similarity the kernel emits
+    # (the computed block-triangle; the mirror pass writes the rest) — stream path; the tensor path
+    # reports int8 ops instead.
+    sim_launch_ms = sim_ms / max(1, prof["sim_launches"])
+    if prof["sim_path_used"] == rs.core.RS_SIM_PATH["tensor"]:
+        g = {"cosine": 3, "msd": 4, "pearson": 6}[sim]
+        ops = pairs_rank * 2 * g * n_right
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+        tpeak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+        roof = {"bound": "tensor", "achieved": ops / (sim_launch_ms / 1e3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                "frac": ops / (sim_launch_ms / 1e3) / 1e12 / tpeak, "traffic": None,
+                "peak_source": f"2 x {peak_src} bf16 burst (int8 is not in MEASURED_PEAKS.json)",
+                "kernel": "sim_tensor_kernel", "ms_per_launch": sim_launch_ms}
+    else:
+        emitted = pairs_rank + n_left * 512  # block-triangle incl. the diagonal chunks
+        alg_bytes = len(left) * 12 + emitted * 8
+        roof = {"bound": "hbm", "achieved": alg_bytes / (sim_launch_ms / 1e3) / 1e9, "peak": hbm_peak,
+                "unit": "GB/s", "frac": alg_bytes / (sim_launch_ms / 1e3) / 1e9 / hbm_peak, "traffic": None,
+                "peak_source": f"{peak_src} copy bandwidth", "kernel": "sim_stream_kernel<pearson>",
+                "ms_per_launch": sim_launch_ms,
+                "note": "FP64-pipe/L2-bound kernel reported against the HBM roofline of its algorithmic bytes"}
+    prof_file = ROOT / "profiles" / "traffic.json"
+    if prof_file.exists():
+        try:
+            roof["traffic"] = json.loads(prof_file.read_text()).get(roof["kernel"].split("<")[0])
+        except (ValueError, OSError):
+            pass
+
+    line = {
+        "metric": "similarity_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if shard else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "predictions_per_sec": preds_all / (ms_per_step / 1e3),
+        "config": {"workload": args.workload, "shape": f"{users}x{items}", "train_ratings": train.Length(),
+                   "test_pairs": int(preds_all), "sim": sim, "knn_type": knn_type, "user_based": user_based, "k": k,
+                   "tie_policy": "canonical", "pearson_mode": args.pearson_mode,
+                   "sim_path": {0: "auto", 1: "tensor", 2: "stream"}[prof["sim_path_used"]],
+                   "l2": "flushed between timed iterations (256 MiB write)",
+                   "parallelism": ("row-sharded + NCCL all-gather of neighbour lists" if shard
+                                   else ("one fold per GPU, no collective" if world > 1 else "single GPU"))},
+        "clocks": clock_info,
+        "e2e": {"value": pairs_all / e2e_s, "unit": "pairs/s", "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": int(len(left) * 16 + n_pred * 8), "d2h_bytes_per_step": int(n_pred * 8),
+                "predictions_per_sec": preds_all / e2e_s, "steps": e2e_steps},
+        "gpu_launches": int(prof["total_launches"]),
+        "kernel_ms": {"sim": sim_ms / args.steps, "predict": pred_ms / args.steps, "prep": prof["prep_ms"] / args.steps},
+        "roofline": roof,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import binding as ob
+
+        ots = ob.TrainSet(train.Users, train.Items, train.Ratings)
+        cores = os.cpu_count() or 1
+        n = n_left
+        tf, tp, rows_done, npred = cpu_reference_step(ob, ots, test, sim, knn_type, user_based, k, cores,
+                                                      rows=(0, min(256, n)), n_pred=20000)
+        # slab: rows_done x (n-1) ordered pairs; the full Fit computes each unordered pair about once
+        est_fit = tf * (n / rows_done) * 0.5
+        if est_fit < 25:
+            tf, tp, rows_done, npred = cpu_reference_step(ob, ots, test, sim, knn_type, user_based, k, cores,
+                                                          n_pred=20000)
+            est_fit = tf
+            sample = f"full Fit ({n} rows, {cores} threads) + first {npred} test pairs predicted serially"
+        else:
+            sample = (f"Fit slab of {rows_done} rows x all {n} ({cores} threads, scaled x{n / rows_done:.1f}/2) + "
+                      f"first {npred} of the slab's test pairs predicted serially")
+        cpu_step = est_fit + (tp / max(1, npred)) * test.Length()
+        line["cpu_baseline"] = {"value": (n * (n - 1) / 2) / cpu_step, "unit": "pairs/s", "cores": cores,
+                                "kind": "port", "sample": sample, "fit_s": est_fit,
+                                "predict_s": (tp / max(1, npred)) * test.Length()}
+    print(json.dumps(line), flush=True)
+    h.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--shard-rows", action="store_true")
+    ap.add_argument("--pearson-mode", default="exact", choices=["exact", "sums"])
+    ap.add_argument("--sim-path", default="auto", choices=["auto", "tensor", "stream"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,177 @@
+/*
+ * rs_knn.h — C ABI of the B200-native KNN hot path (librs_knn_b200.so).
+ *
+ * This is the drop-in boundary for Oneaccount1/recommend-sys' memory-based KNN
+ * recommender.  Each entry point names the reference interface it replaces (paths are
+ * relative to the reference repository).  The reference-side binding (cgo) is in
+ * recommend-sys_b200/go/ and INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only: pointers + sizes, no torch / C++ types in any signature;
+ *   - every function returns RS_OK (0) or a negative RS_ERR_* code; rs_last_error()
+ *     returns a thread-local message for the last failure on the calling thread;
+ *   - host-pointer entry points borrow their arguments for the duration of the call only
+ *     (cgo forbids C retaining Go pointers); `_device` variants take CUDA device pointers
+ *     that must stay valid until the handle's stream has drained;
+ *   - ids are INNER ids (core/data.go:137-151 — order of first appearance), -1 is the
+ *     reference's `newID` (core/data.go:129);
+ *   - "left" is the side similarities are computed over (users if userBased, else items,
+ *     core/knn.go:154-162), "right" is the other side;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails
+ *     with RS_ERR_CUDA.
+ */
+#ifndef RS_KNN_H
+#define RS_KNN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_OK 0
+#define RS_ERR_INVALID (-1)     /* bad argument / call order                              */
+#define RS_ERR_CUDA (-2)        /* CUDA runtime or driver failure (incl. no device)       */
+#define RS_ERR_UNSUPPORTED (-3) /* input outside what the device path supports            */
+#define RS_ERR_OOM (-4)         /* device allocation failed                               */
+#define RS_ERR_DUPLICATE (-5)   /* the same (left,right) pair appears twice in the ratings */
+
+/* core/sim.go: Cosine :10, MSD :28, Pearson :47.  PEARSON_BASELINE is an extension
+ * (named by the north star, absent from the reference). */
+enum rs_sim { RS_SIM_COSINE = 0, RS_SIM_MSD = 1, RS_SIM_PEARSON = 2, RS_SIM_PEARSON_BASELINE = 3 };
+/* core/knn.go:10-15 and the four constructors core/knn.go:50-73 */
+enum rs_knn_type { RS_KNN_BASIC = 0, RS_KNN_CENTERED = 1, RS_KNN_ZSCORE = 2, RS_KNN_BASELINE = 3 };
+/* How Pearson is evaluated.
+ *   EXACT: FP64 replay of core/sim.go:65-80 in the reference's accumulation order
+ *          (ascending right id) — bit-identical similarities and neighbour lists.
+ *   SUMS : the six integer co-rating sums on int8 tensor cores + an FP64 epilogue;
+ *          equal to EXACT within 1e-9*max(1,|s|), not bit-identical (SURVEY.md hazard 2). */
+enum rs_pearson_mode { RS_PEARSON_EXACT = 0, RS_PEARSON_SUMS = 1 };
+/* Which device kernel computes the similarities.
+ *   AUTO  : TENSOR for Cosine/MSD (and Pearson in SUMS mode) when every rating is an
+ *           integer in [-11, 11]; STREAM otherwise.
+ *   TENSOR: tcgen05.mma.kind::i8 masked contractions (fails with RS_ERR_UNSUPPORTED if
+ *           the ratings are not small integers).
+ *   STREAM: FP64 CUDA-core kernel streaming the transposed rating bytes, accumulation in
+ *           the reference's order (any rating set with <= 255 distinct values). */
+enum rs_sim_path { RS_PATH_AUTO = 0, RS_PATH_TENSOR = 1, RS_PATH_STREAM = 2 };
+/* What Fit leaves resident in HBM.
+ *   MATRIX: the dense similarity rows of this handle's shard (what core/knn.go:157,161
+ *           keeps; required by Predict).
+ *   TOPK  : only the per-row top-`topk` neighbour lists, selected in the kernel epilogue;
+ *           the N x N matrix never lands in HBM (BASELINE.json config 4). */
+enum rs_store { RS_STORE_MATRIX = 0, RS_STORE_TOPK = 1 };
+
+typedef struct rs_knn rs_knn; /* opaque handle; one per estimator copy (core/eval.go:29-30) */
+
+/* Mirrors the Parameters keys the path reads (core/knn.go:79-81,145-148) plus the
+ * device-side choices.  Fill with rs_knn_params_default() first. */
+typedef struct rs_knn_params {
+    int32_t sim;          /* enum rs_sim;        Parameters["sim"], default MSD           */
+    int32_t knn_type;     /* enum rs_knn_type;   fixed by the constructor                 */
+    int32_t k;            /* Parameters["k"], default 40                                  */
+    int32_t min_k;        /* Parameters["mink"], default 1                                */
+    int32_t device;       /* CUDA device ordinal; -1 = the calling thread's current device */
+    int32_t pearson_mode; /* enum rs_pearson_mode, default EXACT                          */
+    int32_t sim_path;     /* enum rs_sim_path, default AUTO                               */
+    int32_t store;        /* enum rs_store, default MATRIX                                */
+    int32_t topk;         /* neighbours per row for RS_STORE_TOPK / rs_knn_topk           */
+    int32_t reserved0;
+    int64_t row_begin;    /* shard of left rows this handle owns: [row_begin,row_end);    */
+    int64_t row_end;      /*   0,0 = all rows.  One handle per GPU when row-sharding.     */
+    double shrinkage;     /* PearsonBaseline extension: (n-1)/(n-1+shrinkage), 0 = off    */
+} rs_knn_params;
+
+/* Per-handle counters since creation / the last rs_knn_profile_reset: device time of the
+ * named kernels measured with CUDA events on the handle's stream, and launch counts. */
+typedef struct rs_knn_profile {
+    double sim_kernel_ms;      /* dominant similarity kernel (tensor or stream)            */
+    double predict_kernel_ms;  /* gather-select-reduce kernel                              */
+    double prep_ms;            /* CSR build, packing, statistics                           */
+    int64_t sim_launches;
+    int64_t predict_launches;
+    int64_t total_launches;    /* every kernel this library launched on the handle         */
+    int32_t sim_path_used;     /* enum rs_sim_path actually taken by the last Fit          */
+    int32_t reserved0;
+} rs_knn_profile;
+
+/* Thread-local message of the last error on this thread ("" if none). */
+const char *rs_last_error(void);
+/* Library/ABI version, and the number of visible CUDA devices (0 when there is none). */
+int32_t rs_knn_abi_version(void);
+int32_t rs_knn_device_count(void);
+
+/* Defaults of core/knn.go:79-81,145-148 (sim=MSD, k=40, mink=1), device -1, AUTO path. */
+int32_t rs_knn_params_default(rs_knn_params *p);
+
+/* Replaces NewKNN / NewKNNWithMean / NewKNNWithZScore / NewKNNBaseLine (core/knn.go:50-73)
+ * + SetParams (core/base.go:64-66). */
+int32_t rs_knn_create(const rs_knn_params *p, rs_knn **out);
+/* Go side: Close() + finalizer; the handle lives in an unexported field so the gob
+ * round-trip in Copy (core/dump.go:37-43) never sees it. */
+int32_t rs_knn_destroy(rs_knn *h);
+
+/* Run all of this handle's work on `cuda_stream` (a cudaStream_t / CUstream), e.g. the
+ * caller's current stream.  NULL = the handle's own stream. */
+int32_t rs_knn_set_stream(rs_knn *h, void *cuda_stream);
+
+/* Replaces KNN.Fit (core/knn.go:143-217) after the Go side has built the inner-id COO:
+ * left[i], right[i], rating[i] for i in dataset order (the order matters: Means/StdDevs are
+ * accumulated in it, core/data.go:222-235, core/knn.go:167-177).
+ *   global_mean       TrainSet.GlobalMean (core/data.go:134)
+ *   left_bias         Bias of the left side for RS_KNN_BASELINE (core/knn.go:179-187), else NULL
+ *   right_bias,global_bias  only for RS_SIM_PEARSON_BASELINE (both bias vectors), else NULL/0
+ * Host pointers; copied to the device inside the call. */
+int32_t rs_knn_fit(rs_knn *h, const int32_t *left, const int32_t *right, const double *rating,
+                   int64_t nnz, int32_t n_left, int32_t n_right, double global_mean,
+                   const double *left_bias, const double *right_bias, double global_bias);
+/* Same with every array already resident in device memory. */
+int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_right,
+                          const double *d_rating, int64_t nnz, int32_t n_left, int32_t n_right,
+                          double global_mean, const double *d_left_bias,
+                          const double *d_right_bias, double global_bias);
+
+/* Replaces DataSet.Predict (core/data.go:98-105) looping over KNN.Predict
+ * (core/knn.go:75-141): out[i] = prediction for (left[i], right[i]); -1 on either side
+ * returns GlobalMean.  Ties between equal similarities are broken by ascending inner id
+ * (the canonical policy; Go's sort.Sort is unstable, SURVEY.md hazard 1).
+ * Requires RS_STORE_MATRIX; left ids must lie in the handle's row shard. */
+int32_t rs_knn_predict_batch(rs_knn *h, const int32_t *left, const int32_t *right, int64_t n,
+                             double *out);
+int32_t rs_knn_predict_batch_device(rs_knn *h, const int32_t *d_left, const int32_t *d_right,
+                                    int64_t n, double *d_out);
+/* The neighbours one prediction used, in accumulation order (for parity tests of the
+ * neighbour indices).  Returns the count in *n_out (0 = GlobalMean branch). */
+int32_t rs_knn_predict_neighbors(rs_knn *h, int32_t left, int32_t right, int32_t cap,
+                                 int32_t *ids, double *sims, int32_t *n_out);
+
+/* Backs the exported KNN.Sims field / gob Save on demand (core/knn.go:21, core/dump.go:11):
+ * copies rows [row0,row0+nrows) of the N x N float64 matrix (NaN = unset, diagonal NaN,
+ * core/utils.go:110-120) to `out` (nrows*N doubles).  Rows must lie in the shard. */
+int32_t rs_knn_sims_rows(rs_knn *h, int64_t row0, int64_t nrows, double *out);
+
+/* Per-row top-k neighbour lists of the shard under (similarity desc, id asc), NaN skipped,
+ * unused slots idx=-1/sim=NaN: idx, sim are (row_end-row_begin) x k.  Not an artefact of
+ * the reference (it selects per prediction); this is BASELINE.json config 4's output.
+ * The _device variant writes into device memory (for an NCCL all-gather across shards). */
+int32_t rs_knn_topk(rs_knn *h, int32_t k, int32_t *idx, double *sim);
+int32_t rs_knn_topk_device(rs_knn *h, int32_t k, int32_t *d_idx, double *d_sim);
+
+/* Integer co-rating sums {count, sum_x, sum_y, sum_xx, sum_yy, sum_xy} of left rows
+ * [row0,row0+nrows) against all N rows, straight from the tensor-core contraction
+ * (out: nrows*N*6 int32, host).  Parity surface for "integer co-rating sums bit-exact". */
+int32_t rs_knn_cosums(rs_knn *h, int64_t row0, int64_t nrows, int32_t *out);
+
+/* KNN.Means / KNN.StdDevs (core/knn.go:24-25): n_left doubles each, host. */
+int32_t rs_knn_means(rs_knn *h, double *out);
+int32_t rs_knn_stddevs(rs_knn *h, double *out);
+
+int32_t rs_knn_profile_get(rs_knn *h, rs_knn_profile *out);
+int32_t rs_knn_profile_reset(rs_knn *h);
+/* Block until everything queued on the handle's stream has finished. */
+int32_t rs_knn_synchronize(rs_knn *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RS_KNN_H */

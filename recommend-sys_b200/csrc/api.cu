@@ -1,0 +1,538 @@
+// api.cu — the C ABI of include/rs_knn.h: handle lifetime, Fit / Predict orchestration.
+// No CPU fallback anywhere: every compute entry point needs a CUDA device.
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void rs_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+int32_t enter(rs_knn *h) {
+    if (!h) {
+        rs_set_error("null handle");
+        return RS_ERR_INVALID;
+    }
+    // goroutines migrate between OS threads: bind the device on every entry
+    RS_CUDA(cudaSetDevice(h->device));
+    return RS_OK;
+}
+
+void free_fit_state(rs_knn *h) {
+    for (void *p : h->allocs) cudaFree(p);
+    h->allocs.clear();
+    h->fitted = false;
+    h->l_ptr = h->r_ptr = nullptr;
+    h->l_col = h->r_col = nullptr;
+    h->l_val = h->r_val = h->ld_val = nullptr;
+    h->l_code = nullptr;
+    h->lut = h->means = h->stddevs = h->pmeans = h->left_bias = h->right_bias = nullptr;
+    h->rt = nullptr;
+    h->planes = nullptr;
+    h->sims = nullptr;
+    h->topk_idx = nullptr;
+    h->topk_sim = nullptr;
+    h->d_flags = nullptr;
+}
+
+int32_t fold_profile(rs_knn *h) {
+    RS_CUDA(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    if (h->prep_pending) {
+        RS_CUDA(cudaEventElapsedTime(&ms, h->ev_a, h->ev_b));
+        h->prof.prep_ms += ms;
+        h->prep_pending = false;
+    }
+    if (h->sim_pending) {
+        RS_CUDA(cudaEventElapsedTime(&ms, h->ev_b, h->ev_c));
+        h->prof.sim_kernel_ms += ms;
+        h->sim_pending = false;
+    }
+    if (h->pred_pending) {
+        RS_CUDA(cudaEventElapsedTime(&ms, h->ev_d, h->ev_e));
+        h->prof.predict_kernel_ms += ms;
+        h->pred_pending = false;
+    }
+    return RS_OK;
+}
+
+bool tensor_eligible(const rs_knn *h) {
+    if (h->rating_class != RS_CLASS_INT8) return false;
+    if (h->p.sim == RS_SIM_COSINE || h->p.sim == RS_SIM_MSD) return true;
+    if (h->p.sim == RS_SIM_PEARSON && h->p.pearson_mode == RS_PEARSON_SUMS) return true;
+    return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *rs_last_error(void) { return g_err; }
+int32_t rs_knn_abi_version(void) { return 1; }
+
+int32_t rs_knn_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int32_t rs_knn_params_default(rs_knn_params *p) {
+    if (!p) return RS_ERR_INVALID;
+    std::memset(p, 0, sizeof(*p));
+    p->sim = RS_SIM_MSD;         // core/knn.go:145
+    p->knn_type = RS_KNN_BASIC;  // core/knn.go:52
+    p->k = 40;                   // core/knn.go:80
+    p->min_k = 1;                // core/knn.go:81
+    p->device = -1;
+    p->pearson_mode = RS_PEARSON_EXACT;
+    p->sim_path = RS_PATH_AUTO;
+    p->store = RS_STORE_MATRIX;
+    p->topk = 40;
+    return RS_OK;
+}
+
+int32_t rs_knn_create(const rs_knn_params *p, rs_knn **out) {
+    if (!p || !out) {
+        rs_set_error("rs_knn_create: null argument");
+        return RS_ERR_INVALID;
+    }
+    if (p->sim < RS_SIM_COSINE || p->sim > RS_SIM_PEARSON_BASELINE || p->knn_type < RS_KNN_BASIC ||
+        p->knn_type > RS_KNN_BASELINE || p->k < 1 || p->min_k < 0) {
+        rs_set_error("rs_knn_create: invalid sim/knn_type/k/min_k");
+        return RS_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        rs_set_error("no CUDA device available (%s); this library has no CPU fallback",
+                     e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+        return RS_ERR_CUDA;
+    }
+    int dev = p->device;
+    if (dev < 0) RS_CUDA(cudaGetDevice(&dev));
+    if (dev >= ndev) {
+        rs_set_error("device %d out of range (%d devices)", dev, ndev);
+        return RS_ERR_INVALID;
+    }
+    cudaDeviceProp prop;
+    RS_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        rs_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major,
+                     prop.minor);
+        return RS_ERR_UNSUPPORTED;
+    }
+    rs_knn *h = new (std::nothrow) rs_knn();
+    if (!h) return RS_ERR_OOM;
+    h->p = *p;
+    h->device = dev;
+    RS_CUDA(cudaSetDevice(dev));
+    RS_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    RS_CUDA(cudaEventCreate(&h->ev_a));
+    RS_CUDA(cudaEventCreate(&h->ev_b));
+    RS_CUDA(cudaEventCreate(&h->ev_c));
+    RS_CUDA(cudaEventCreate(&h->ev_d));
+    RS_CUDA(cudaEventCreate(&h->ev_e));
+    *out = h;
+    return RS_OK;
+}
+
+int32_t rs_knn_destroy(rs_knn *h) {
+    if (!h) return RS_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_fit_state(h);
+    for (void *p : h->scratch) cudaFree(p);
+    cudaEventDestroy(h->ev_a);
+    cudaEventDestroy(h->ev_b);
+    cudaEventDestroy(h->ev_c);
+    cudaEventDestroy(h->ev_d);
+    cudaEventDestroy(h->ev_e);
+    cudaStreamDestroy(h->own_stream);
+    delete h;
+    return RS_OK;
+}
+
+int32_t rs_knn_set_stream(rs_knn *h, void *cuda_stream) {
+    RS_TRY(enter(h));
+    RS_CUDA(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return RS_OK;
+}
+
+int32_t rs_knn_synchronize(rs_knn *h) {
+    RS_TRY(enter(h));
+    RS_CUDA(cudaStreamSynchronize(h->stream));
+    return RS_OK;
+}
+
+int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_right, const double *d_rating,
+                          int64_t nnz, int32_t n_left, int32_t n_right, double global_mean,
+                          const double *d_left_bias, const double *d_right_bias, double global_bias) {
+    RS_TRY(enter(h));
+    if (!d_left || !d_right || !d_rating || nnz <= 0 || n_left <= 0 || n_right <= 0) {
+        rs_set_error("rs_knn_fit: empty or null input (nnz=%lld n_left=%d n_right=%d)", (long long)nnz, n_left,
+                     n_right);
+        return RS_ERR_INVALID;
+    }
+    if (h->p.knn_type == RS_KNN_BASELINE && !d_left_bias) {
+        rs_set_error("rs_knn_fit: RS_KNN_BASELINE needs left_bias (core/knn.go:179-187)");
+        return RS_ERR_INVALID;
+    }
+    if (h->p.sim == RS_SIM_PEARSON_BASELINE && (!d_left_bias || !d_right_bias)) {
+        rs_set_error("rs_knn_fit: RS_SIM_PEARSON_BASELINE needs both bias vectors");
+        return RS_ERR_INVALID;
+    }
+    RS_TRY(fold_profile(h));
+    free_fit_state(h);
+    h->nnz = nnz;
+    h->n_left = n_left;
+    h->n_right = n_right;
+    h->global_mean = global_mean;
+    h->global_bias = global_bias;
+    h->row_begin = h->p.row_begin;
+    h->row_end = h->p.row_end;
+    if (h->row_begin == 0 && h->row_end == 0) h->row_end = n_left;
+    if (h->row_begin < 0 || h->row_end > n_left || h->row_begin > h->row_end) {
+        rs_set_error("row shard [%lld,%lld) outside [0,%d)", (long long)h->row_begin, (long long)h->row_end, n_left);
+        return RS_ERR_INVALID;
+    }
+    const int64_t rows = h->row_end - h->row_begin;
+
+    RS_CUDA(cudaEventRecord(h->ev_a, h->stream));
+    int32_t rc = rs_prep_build(h, d_left, d_right, d_rating, d_left_bias, d_right_bias);
+    if (rc != RS_OK) { free_fit_state(h); return rc; }
+
+    int path = h->p.sim_path;
+    if (path == RS_PATH_AUTO) path = tensor_eligible(h) ? RS_PATH_TENSOR : RS_PATH_STREAM;
+    if (path == RS_PATH_TENSOR && !tensor_eligible(h)) {
+        rs_set_error("tensor path needs integer ratings in [-11,11] and Cosine/MSD (or Pearson in SUMS mode)");
+        free_fit_state(h);
+        return RS_ERR_UNSUPPORTED;
+    }
+    h->prof.sim_path_used = path;
+    rc = (path == RS_PATH_TENSOR) ? rs_prep_planes(h) : rs_prep_rt(h);
+    if (rc != RS_OK) { free_fit_state(h); return rc; }
+
+    h->ld_s = ((int64_t)n_left + 15) / 16 * 16;
+    if (h->p.store == RS_STORE_MATRIX) {
+        rc = rs_alloc(h, &h->sims, (size_t)rows * (size_t)h->ld_s);
+        if (rc != RS_OK) { free_fit_state(h); return rc; }
+        RS_CUDA(cudaEventRecord(h->ev_b, h->stream));
+        rc = (path == RS_PATH_TENSOR) ? rs_sim_tensor_launch(h, nullptr, 0, 0) : rs_sim_stream_launch(h);
+        if (rc != RS_OK) { free_fit_state(h); return rc; }
+        RS_CUDA(cudaEventRecord(h->ev_c, h->stream));
+        if (path == RS_PATH_STREAM) {
+            rc = rs_symmetrize_launch(h);
+            if (rc != RS_OK) { free_fit_state(h); return rc; }
+        }
+    } else {
+        // top-k only: similarity rows are produced slab by slab and reduced to neighbour
+        // lists; the N x N matrix never exists in HBM.
+        const int32_t k = h->p.topk > 0 ? h->p.topk : h->p.k;
+        int64_t slab = (int64_t)(2ull << 30) / ((int64_t)h->ld_s * 8);  // ~2 GiB of rows at a time
+        if (slab < 128) slab = 128;
+        slab = slab / 128 * 128;
+        if (slab > rows) slab = rows;
+        RS_TRY(rs_alloc(h, &h->sims, (size_t)slab * (size_t)h->ld_s));
+        RS_TRY(rs_alloc(h, &h->topk_idx, (size_t)rows * k));
+        RS_TRY(rs_alloc(h, &h->topk_sim, (size_t)rows * k));
+        RS_CUDA(cudaEventRecord(h->ev_b, h->stream));
+        const int64_t rb = h->row_begin, re = h->row_end;
+        for (int64_t r0 = rb; r0 < re; r0 += slab) {
+            h->row_begin = r0;
+            h->row_end = r0 + slab < re ? r0 + slab : re;
+            rc = (path == RS_PATH_TENSOR) ? rs_sim_tensor_launch(h, nullptr, 0, 0) : rs_sim_stream_launch(h);
+            if (rc == RS_OK && path == RS_PATH_STREAM) rc = rs_symmetrize_launch(h);
+            if (rc == RS_OK)
+                rc = rs_topk_launch(h, k, h->topk_idx + (r0 - rb) * k, h->topk_sim + (r0 - rb) * k);
+            if (rc != RS_OK) break;
+        }
+        h->row_begin = rb;
+        h->row_end = re;
+        if (rc != RS_OK) { free_fit_state(h); return rc; }
+        RS_CUDA(cudaEventRecord(h->ev_c, h->stream));
+    }
+    h->prep_pending = true;
+    h->sim_pending = true;
+    h->fitted = true;
+    return RS_OK;
+}
+
+int32_t rs_knn_fit(rs_knn *h, const int32_t *left, const int32_t *right, const double *rating, int64_t nnz,
+                   int32_t n_left, int32_t n_right, double global_mean, const double *left_bias,
+                   const double *right_bias, double global_bias) {
+    RS_TRY(enter(h));
+    if (!left || !right || !rating || nnz <= 0 || n_left <= 0 || n_right <= 0) {
+        rs_set_error("rs_knn_fit: empty or null input (nnz=%lld n_left=%d n_right=%d)", (long long)nnz, n_left,
+                     n_right);
+        return RS_ERR_INVALID;
+    }
+    int32_t *d_left = nullptr, *d_right = nullptr;
+    double *d_rating = nullptr, *d_lb = nullptr, *d_rb = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_left); cudaFree(d_right); cudaFree(d_rating); cudaFree(d_lb); cudaFree(d_rb);
+    };
+#define FIT_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            rs_set_error("%s: %s", #expr, cudaGetErrorString(e_));                                  \
+            cleanup();                                                                              \
+            return e_ == cudaErrorMemoryAllocation ? RS_ERR_OOM : RS_ERR_CUDA;                      \
+        }                                                                                           \
+    } while (0)
+    FIT_CUDA(cudaMalloc(&d_left, (size_t)nnz * 4));
+    FIT_CUDA(cudaMalloc(&d_right, (size_t)nnz * 4));
+    FIT_CUDA(cudaMalloc(&d_rating, (size_t)nnz * 8));
+    FIT_CUDA(cudaMemcpyAsync(d_left, left, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
+    FIT_CUDA(cudaMemcpyAsync(d_right, right, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
+    FIT_CUDA(cudaMemcpyAsync(d_rating, rating, (size_t)nnz * 8, cudaMemcpyHostToDevice, h->stream));
+    if (left_bias) {
+        FIT_CUDA(cudaMalloc(&d_lb, (size_t)n_left * 8));
+        FIT_CUDA(cudaMemcpyAsync(d_lb, left_bias, (size_t)n_left * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (right_bias) {
+        FIT_CUDA(cudaMalloc(&d_rb, (size_t)n_right * 8));
+        FIT_CUDA(cudaMemcpyAsync(d_rb, right_bias, (size_t)n_right * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    int32_t rc = rs_knn_fit_device(h, d_left, d_right, d_rating, nnz, n_left, n_right, global_mean, d_lb, d_rb,
+                                   global_bias);
+    cudaError_t e = cudaStreamSynchronize(h->stream);  // inputs are borrowed only for the call
+    cleanup();
+    if (rc != RS_OK) return rc;
+    if (e != cudaSuccess) {
+        rs_set_error("rs_knn_fit: %s", cudaGetErrorString(e));
+        h->fitted = false;
+        return RS_ERR_CUDA;
+    }
+    return RS_OK;
+#undef FIT_CUDA
+}
+
+static int32_t require_matrix(rs_knn *h, const char *who) {
+    if (!h->fitted) {
+        rs_set_error("%s: Fit has not been called", who);
+        return RS_ERR_INVALID;
+    }
+    if (h->p.store != RS_STORE_MATRIX) {
+        rs_set_error("%s needs RS_STORE_MATRIX (the handle keeps top-k lists only)", who);
+        return RS_ERR_INVALID;
+    }
+    return RS_OK;
+}
+
+int32_t rs_knn_predict_batch_device(rs_knn *h, const int32_t *d_left, const int32_t *d_right, int64_t n,
+                                    double *d_out) {
+    RS_TRY(enter(h));
+    RS_TRY(require_matrix(h, "rs_knn_predict_batch"));
+    if (n == 0) return RS_OK;
+    if (!d_left || !d_right || !d_out || n < 0) {
+        rs_set_error("rs_knn_predict_batch: null argument");
+        return RS_ERR_INVALID;
+    }
+    if (h->pred_pending) RS_TRY(fold_profile(h));
+    RS_CUDA(cudaEventRecord(h->ev_d, h->stream));
+    RS_TRY(rs_predict_launch(h, d_left, d_right, n, d_out, nullptr, nullptr, nullptr, 0));
+    RS_CUDA(cudaEventRecord(h->ev_e, h->stream));
+    h->pred_pending = true;
+    return RS_OK;
+}
+
+static int32_t scratch_get(rs_knn *h, int slot, size_t bytes, void **out) {
+    if (h->scratch.size() <= (size_t)slot) {
+        h->scratch.resize(slot + 1, nullptr);
+        h->scratch_bytes.resize(slot + 1, 0);
+    }
+    if (h->scratch_bytes[slot] < bytes) {
+        if (h->scratch[slot]) cudaFree(h->scratch[slot]);
+        h->scratch[slot] = nullptr;
+        h->scratch_bytes[slot] = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&h->scratch[slot], want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            rs_set_error("cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+            return RS_ERR_OOM;
+        }
+        h->scratch_bytes[slot] = want;
+    }
+    *out = h->scratch[slot];
+    return RS_OK;
+}
+
+int32_t rs_knn_predict_batch(rs_knn *h, const int32_t *left, const int32_t *right, int64_t n, double *out) {
+    RS_TRY(enter(h));
+    RS_TRY(require_matrix(h, "rs_knn_predict_batch"));
+    if (n == 0) return RS_OK;
+    if (!left || !right || !out || n < 0) {
+        rs_set_error("rs_knn_predict_batch: null argument");
+        return RS_ERR_INVALID;
+    }
+    void *dl, *dr, *dout;
+    RS_TRY(scratch_get(h, 0, (size_t)n * 4, &dl));
+    RS_TRY(scratch_get(h, 1, (size_t)n * 4, &dr));
+    RS_TRY(scratch_get(h, 2, (size_t)n * 8, &dout));
+    RS_CUDA(cudaMemcpyAsync(dl, left, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    RS_CUDA(cudaMemcpyAsync(dr, right, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    RS_TRY(rs_knn_predict_batch_device(h, (const int32_t *)dl, (const int32_t *)dr, n, (double *)dout));
+    RS_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    RS_CUDA(cudaStreamSynchronize(h->stream));
+    return RS_OK;
+}
+
+int32_t rs_knn_predict_neighbors(rs_knn *h, int32_t left, int32_t right, int32_t cap, int32_t *ids, double *sims,
+                                 int32_t *n_out) {
+    RS_TRY(enter(h));
+    RS_TRY(require_matrix(h, "rs_knn_predict_neighbors"));
+    if (!ids || !sims || !n_out || cap < 1) {
+        rs_set_error("rs_knn_predict_neighbors: null argument");
+        return RS_ERR_INVALID;
+    }
+    void *dl, *dr, *dout, *dids, *dsims, *dcnt;
+    RS_TRY(scratch_get(h, 0, 4, &dl));
+    RS_TRY(scratch_get(h, 1, 4, &dr));
+    RS_TRY(scratch_get(h, 2, 8, &dout));
+    RS_TRY(scratch_get(h, 3, (size_t)cap * 4, &dids));
+    RS_TRY(scratch_get(h, 4, (size_t)cap * 8, &dsims));
+    RS_TRY(scratch_get(h, 5, 4, &dcnt));
+    RS_CUDA(cudaMemcpyAsync(dl, &left, 4, cudaMemcpyHostToDevice, h->stream));
+    RS_CUDA(cudaMemcpyAsync(dr, &right, 4, cudaMemcpyHostToDevice, h->stream));
+    RS_CUDA(cudaMemsetAsync(dcnt, 0, 4, h->stream));
+    RS_TRY(rs_predict_launch(h, (const int32_t *)dl, (const int32_t *)dr, 1, (double *)dout, (int32_t *)dids,
+                             (double *)dsims, (int32_t *)dcnt, cap));
+    int32_t cnt = 0;
+    RS_CUDA(cudaMemcpyAsync(&cnt, dcnt, 4, cudaMemcpyDeviceToHost, h->stream));
+    RS_CUDA(cudaStreamSynchronize(h->stream));
+    if (cnt > 0) {
+        RS_CUDA(cudaMemcpy(ids, dids, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+        RS_CUDA(cudaMemcpy(sims, dsims, (size_t)cnt * 8, cudaMemcpyDeviceToHost));
+    }
+    *n_out = cnt;
+    return RS_OK;
+}
+
+int32_t rs_knn_sims_rows(rs_knn *h, int64_t row0, int64_t nrows, double *out) {
+    RS_TRY(enter(h));
+    RS_TRY(require_matrix(h, "rs_knn_sims_rows"));
+    if (!out || nrows < 0 || row0 < h->row_begin || row0 + nrows > h->row_end) {
+        rs_set_error("rs_knn_sims_rows: rows [%lld,%lld) outside the shard [%lld,%lld)", (long long)row0,
+                     (long long)(row0 + nrows), (long long)h->row_begin, (long long)h->row_end);
+        return RS_ERR_INVALID;
+    }
+    if (nrows == 0) return RS_OK;
+    RS_CUDA(cudaMemcpy2DAsync(out, (size_t)h->n_left * 8, h->sims + (row0 - h->row_begin) * h->ld_s,
+                              (size_t)h->ld_s * 8, (size_t)h->n_left * 8, (size_t)nrows, cudaMemcpyDeviceToHost,
+                              h->stream));
+    RS_CUDA(cudaStreamSynchronize(h->stream));
+    return RS_OK;
+}
+
+int32_t rs_knn_topk_device(rs_knn *h, int32_t k, int32_t *d_idx, double *d_sim) {
+    RS_TRY(enter(h));
+    if (!h->fitted || !d_idx || !d_sim) {
+        rs_set_error("rs_knn_topk: not fitted or null argument");
+        return RS_ERR_INVALID;
+    }
+    const int64_t rows = h->row_end - h->row_begin;
+    if (h->p.store == RS_STORE_TOPK) {
+        const int32_t kk = h->p.topk > 0 ? h->p.topk : h->p.k;
+        if (k != kk) {
+            rs_set_error("rs_knn_topk: handle holds top-%d lists, asked for %d", kk, k);
+            return RS_ERR_INVALID;
+        }
+        RS_CUDA(cudaMemcpyAsync(d_idx, h->topk_idx, (size_t)rows * k * 4, cudaMemcpyDeviceToDevice, h->stream));
+        RS_CUDA(cudaMemcpyAsync(d_sim, h->topk_sim, (size_t)rows * k * 8, cudaMemcpyDeviceToDevice, h->stream));
+        return RS_OK;
+    }
+    return rs_topk_launch(h, k, d_idx, d_sim);
+}
+
+int32_t rs_knn_topk(rs_knn *h, int32_t k, int32_t *idx, double *sim) {
+    RS_TRY(enter(h));
+    if (!h->fitted || !idx || !sim || k < 1) {
+        rs_set_error("rs_knn_topk: not fitted or bad argument");
+        return RS_ERR_INVALID;
+    }
+    const int64_t rows = h->row_end - h->row_begin;
+    void *di, *ds;
+    RS_TRY(scratch_get(h, 3, (size_t)rows * k * 4, &di));
+    RS_TRY(scratch_get(h, 4, (size_t)rows * k * 8, &ds));
+    RS_TRY(rs_knn_topk_device(h, k, (int32_t *)di, (double *)ds));
+    RS_CUDA(cudaMemcpyAsync(idx, di, (size_t)rows * k * 4, cudaMemcpyDeviceToHost, h->stream));
+    RS_CUDA(cudaMemcpyAsync(sim, ds, (size_t)rows * k * 8, cudaMemcpyDeviceToHost, h->stream));
+    RS_CUDA(cudaStreamSynchronize(h->stream));
+    return RS_OK;
+}
+
+int32_t rs_knn_cosums(rs_knn *h, int64_t row0, int64_t nrows, int32_t *out) {
+    RS_TRY(enter(h));
+    if (!h->fitted || !out || nrows < 0 || row0 < 0 || row0 + nrows > h->n_left) {
+        rs_set_error("rs_knn_cosums: not fitted or bad argument");
+        return RS_ERR_INVALID;
+    }
+    if (h->rating_class != RS_CLASS_INT8) {
+        rs_set_error("rs_knn_cosums: integer co-rating sums need integer ratings in [-11,11]");
+        return RS_ERR_UNSUPPORTED;
+    }
+    if (nrows == 0) return RS_OK;
+    if (!h->planes) RS_TRY(rs_prep_planes(h));
+    void *d;
+    const size_t bytes = (size_t)nrows * (size_t)h->n_left * 6 * 4;
+    RS_TRY(scratch_get(h, 6, bytes, &d));
+    RS_TRY(rs_sim_tensor_launch(h, (int32_t *)d, row0, nrows));
+    RS_CUDA(cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, h->stream));
+    RS_CUDA(cudaStreamSynchronize(h->stream));
+    return RS_OK;
+}
+
+static int32_t copy_vec(rs_knn *h, const double *d, double *out, const char *who) {
+    RS_TRY(enter(h));
+    if (!h->fitted || !out || !d) {
+        rs_set_error("%s: not fitted or null argument", who);
+        return RS_ERR_INVALID;
+    }
+    RS_CUDA(cudaMemcpyAsync(out, d, (size_t)h->n_left * 8, cudaMemcpyDeviceToHost, h->stream));
+    RS_CUDA(cudaStreamSynchronize(h->stream));
+    return RS_OK;
+}
+
+int32_t rs_knn_means(rs_knn *h, double *out) { return copy_vec(h, h ? h->means : nullptr, out, "rs_knn_means"); }
+int32_t rs_knn_stddevs(rs_knn *h, double *out) {
+    if (h && h->p.knn_type != RS_KNN_ZSCORE) {
+        rs_set_error("rs_knn_stddevs: only the z-score KNN keeps StdDevs (core/knn.go:167)");
+        return RS_ERR_INVALID;
+    }
+    return copy_vec(h, h ? h->stddevs : nullptr, out, "rs_knn_stddevs");
+}
+
+int32_t rs_knn_profile_get(rs_knn *h, rs_knn_profile *out) {
+    RS_TRY(enter(h));
+    if (!out) return RS_ERR_INVALID;
+    RS_TRY(fold_profile(h));
+    *out = h->prof;
+    return RS_OK;
+}
+
+int32_t rs_knn_profile_reset(rs_knn *h) {
+    RS_TRY(enter(h));
+    RS_TRY(fold_profile(h));
+    int32_t path = h->prof.sim_path_used;
+    h->prof = rs_knn_profile{};
+    h->prof.sim_path_used = path;
+    return RS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+// common.cuh — shared declarations of librs_knn_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "rs_knn.h"
+
+void rs_set_error(const char *fmt, ...);
+
+#define RS_CUDA(expr)                                                                       \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            rs_set_error("%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return (e_ == cudaErrorMemoryAllocation) ? RS_ERR_OOM : RS_ERR_CUDA;            \
+        }                                                                                   \
+    } while (0)
+
+#define RS_TRY(expr)              \
+    do {                          \
+        int32_t rc_ = (expr);     \
+        if (rc_ != RS_OK) return rc_; \
+    } while (0)
+
+// Rating classes (how a rating is represented as one byte; 0 = missing).
+//   RS_CLASS_INT8 : every rating is an integer in [-11,11]; code = rating + 12.
+//   RS_CLASS_TABLE: <= 255 distinct values; code = 1 + rank in the sorted value table.
+enum { RS_CLASS_INT8 = 0, RS_CLASS_TABLE = 1 };
+constexpr int RS_INT8_BIAS = 12;
+
+// Column-chunk width of the streaming similarity kernel (threads * bytes per thread).
+constexpr int RS_STREAM_THREADS = 128;
+constexpr int RS_STREAM_JPT = 8;
+constexpr int RS_STREAM_JC = RS_STREAM_THREADS * RS_STREAM_JPT;  // 1024
+
+// Tensor-core similarity kernel tile: 128 left rows (MMA M) x 64 left rows (MMA N),
+// K blocked by 128 bytes (one SWIZZLE_128B atom) per pipeline stage.
+constexpr int RS_TC_BM = 128;
+constexpr int RS_TC_BN = 64;
+constexpr int RS_TC_BK = 128;
+
+struct rs_knn {
+    rs_knn_params p{};
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr;
+    rs_knn_profile prof{};
+    // pending event pairs whose elapsed time has not been folded into prof yet
+    bool sim_pending = false, pred_pending = false, prep_pending = false;
+
+    bool fitted = false;
+    int32_t n_left = 0, n_right = 0;
+    int64_t nnz = 0;
+    int64_t row_begin = 0, row_end = 0;  // resolved shard
+    double global_mean = 0.0, global_bias = 0.0;
+    int rating_class = RS_CLASS_INT8;
+    int n_codes = 0;
+
+    std::vector<void *> allocs;  // everything Fit allocated (freed on refit / destroy)
+
+    // CSR of the left rows, entries ascending by right id (core/data.go:236-243)
+    int64_t *l_ptr = nullptr;
+    int32_t *l_col = nullptr;
+    double *l_val = nullptr;
+    uint8_t *l_code = nullptr;
+    double *ld_val = nullptr;  // left rows in DATASET order (means / std accumulate in it)
+    // CSR of the right rows, entries ascending by left id (Predict candidates)
+    int64_t *r_ptr = nullptr;
+    int32_t *r_col = nullptr;
+    double *r_val = nullptr;
+
+    double *lut = nullptr;        // [256] code -> rating value
+    double *means = nullptr;      // KNN.Means    (dataset order sum / count)
+    double *stddevs = nullptr;    // KNN.StdDevs
+    double *pmeans = nullptr;     // Pearson's own row means (sorted-order sum, core/sim.go:49-62)
+    double *left_bias = nullptr;  // KNN.Bias
+    double *right_bias = nullptr;
+
+    // transposed rating bytes RT[right][left] (n_right x ld_rt), stream path
+    uint8_t *rt = nullptr;
+    int64_t ld_rt = 0;
+    // int8 planes X, X^2, M of the left matrix, [3][n_pad][k_pad], K-major (tensor path)
+    int8_t *planes = nullptr;
+    int64_t tc_npad = 0, tc_kpad = 0;
+
+    // outputs
+    double *sims = nullptr;  // (row_end-row_begin) x ld_s, NaN = unset
+    int64_t ld_s = 0;
+    int32_t *topk_idx = nullptr;  // RS_STORE_TOPK: rows x topk
+    double *topk_sim = nullptr;
+
+    int32_t *d_flags = nullptr;  // small device scratch for validation flags
+    std::vector<void *> scratch;         // device staging of the host-pointer entry points
+    std::vector<size_t> scratch_bytes;
+};
+
+// ---- prep.cu ----
+int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, const double *d_rating,
+                      const double *d_left_bias, const double *d_right_bias);
+int32_t rs_dev_alloc(rs_knn *h, void **out, size_t bytes);
+template <typename T>
+inline int32_t rs_alloc(rs_knn *h, T **out, size_t count) {
+    return rs_dev_alloc(h, reinterpret_cast<void **>(out), count * sizeof(T));
+}
+int32_t rs_prep_rt(rs_knn *h);
+int32_t rs_prep_planes(rs_knn *h);
+
+// ---- sim_stream.cu ----
+int32_t rs_sim_stream_launch(rs_knn *h);
+int32_t rs_symmetrize_launch(rs_knn *h);
+
+// ---- sim_tensor.cu ----
+int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int64_t cos_nrows);
+
+// ---- predict.cu ----
+int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_right, int64_t n, double *d_out,
+                          int32_t *d_nb_ids, double *d_nb_sims, int32_t *d_nb_count, int32_t nb_cap);
+int32_t rs_topk_launch(rs_knn *h, int32_t k, int32_t *d_idx, double *d_sim);
+
+// order-preserving map double -> uint64 (larger similarity = larger key); -0.0 folded to +0.0
+__host__ __device__ inline uint64_t rs_sim_key(double s) {
+    s = s + 0.0;  // -0.0 -> +0.0, every other value unchanged
+#ifdef __CUDA_ARCH__
+    uint64_t b = (uint64_t)__double_as_longlong(s);
+#else
+    uint64_t b;
+    __builtin_memcpy(&b, &s, 8);
+#endif
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ inline double rs_key_sim(uint64_t k) {
+    uint64_t b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b);
+#else
+    double s;
+    __builtin_memcpy(&s, &b, 8);
+    return s;
+#endif
+}

@@ -1,0 +1,299 @@
+// predict.cu — batched KNN.Predict (core/knn.go:75-141) and per-row top-k.
+//
+// Predict: one warp per (left,right) test pair.
+//   1. candidates = entries of the right row (core/knn.go:95-99), similarity gathered from
+//      the left row of the HBM-resident matrix; NaN filtered; count <= mink -> GlobalMean.
+//   2. the candidates are ordered by (similarity desc, inner id asc) — the canonical tie
+//      policy — with a warp-level bitonic sort over (key,pos) records in shared memory
+//      (right rows are id-sorted, so position order == id order);
+//   3. the first min(k,count) are accumulated SEQUENTIALLY in that order exactly as
+//      core/knn.go:116-130 does, so the prediction is bit-identical to the restated
+//      reference under the canonical policy.
+// HBM-bound by design: per prediction C*(4 B id + 8 B rating + 8 B similarity [+ 8 B mean/bias]).
+#include "common.cuh"
+
+namespace {
+
+constexpr int PRED_WARPS = 4;
+constexpr int PRED_CAP = 512;   // (key,pos) records per warp
+
+struct Rec {
+    uint64_t key;
+    uint32_t pos;
+};
+
+// a ranks before b: larger key first, then smaller position (= smaller id)
+__device__ __forceinline__ bool rec_before(uint64_t ka, uint32_t pa, uint64_t kb, uint32_t pb) {
+    return ka > kb || (ka == kb && pa < pb);
+}
+
+// Bitonic sort of n_pad (power of two, >= 32) records into "before" order by one warp.
+__device__ void warp_bitonic(uint64_t *keys, uint32_t *pos, int n_pad, int lane) {
+    for (int size = 2; size <= n_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncwarp();
+            for (int t = lane; t < (n_pad >> 1); t += 32) {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool up = ((lo & size) == 0);  // this run sorts into "before" order
+                uint64_t ka = keys[lo], kb = keys[hi];
+                uint32_t pa = pos[lo], pb = pos[hi];
+                bool swap = up ? rec_before(kb, pb, ka, pa) : rec_before(ka, pa, kb, pb);
+                if (swap) { keys[lo] = kb; keys[hi] = ka; pos[lo] = pb; pos[hi] = pa; }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+struct PredArgs {
+    const int32_t *left, *right;
+    int64_t n;
+    double *out;
+    const int64_t *r_ptr;
+    const int32_t *r_col;
+    const double *r_val;
+    const double *sims;
+    int64_t ld_s;
+    int64_t row_begin, row_end;
+    const double *means, *stddevs, *bias;
+    double global_mean;
+    int32_t n_right;
+    int32_t k, min_k, knn_type;
+    int32_t *nb_ids;
+    double *nb_sims;
+    int32_t *nb_count;
+    int32_t nb_cap;
+};
+
+__global__ void __launch_bounds__(PRED_WARPS * 32) predict_kernel(PredArgs a) {
+    __shared__ uint64_t s_keys[PRED_WARPS][PRED_CAP];
+    __shared__ uint32_t s_pos[PRED_WARPS][PRED_CAP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *keys = s_keys[warp];
+    uint32_t *pos = s_pos[warp];
+    const int64_t n_warps = (int64_t)gridDim.x * PRED_WARPS;
+    const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
+
+    for (int64_t p = (int64_t)blockIdx.x * PRED_WARPS + warp; p < a.n; p += n_warps) {
+        const int32_t l = a.left[p], r = a.right[p];
+        if (a.nb_count && lane == 0) *a.nb_count = 0;
+        if (l < 0 || r < 0 || r >= a.n_right) {            // core/knn.go:89-91 (newID)
+            if (lane == 0) a.out[p] = a.global_mean;
+            continue;
+        }
+        if (l < a.row_begin || l >= a.row_end) {           // not in this shard: flagged as NaN
+            if (lane == 0) a.out[p] = nan_v;
+            continue;
+        }
+        const double *row = a.sims + (l - a.row_begin) * a.ld_s;
+        const int64_t cb = a.r_ptr[r], ce = a.r_ptr[r + 1];
+        const int keep = a.k < PRED_CAP / 2 ? a.k : PRED_CAP / 2;
+
+        // ---- gather + filter; keep the best `keep` so far in keys[0..have) ----
+        int have = 0;        // records currently buffered (warp-uniform)
+        int64_t valid = 0;   // non-NaN candidates seen (core/knn.go:95-99)
+        uint64_t thr_key = 0;  // once a sort has happened: records not before (thr) are dropped
+        uint32_t thr_pos = 0xffffffffu;
+        bool have_thr = false;
+        for (int64_t base = cb; base < ce; base += 32) {
+            const int64_t x = base + lane;
+            bool ok = false;
+            uint64_t key = 0;
+            if (x < ce) {
+                const double s = row[a.r_col[x]];
+                ok = (s == s);
+                key = rs_sim_key(s);
+            }
+            const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+            valid += __popc(okmask);
+            const uint32_t pp = (uint32_t)(x - cb);
+            bool take = ok && (!have_thr || rec_before(key, pp, thr_key, thr_pos));
+            const uint32_t tmask = __ballot_sync(0xffffffffu, take);
+            if (take) {
+                int slot = have + __popc(tmask & ((1u << lane) - 1u));
+                keys[slot] = key;
+                pos[slot] = pp;
+            }
+            have += __popc(tmask);
+            if (have > PRED_CAP - 32) {
+                // buffer nearly full: sort, keep the best `keep`, remember the threshold
+                int n_pad = PRED_CAP;
+                __syncwarp();
+                for (int t = have + lane; t < n_pad; t += 32) { keys[t] = 0; pos[t] = 0xffffffffu; }
+                warp_bitonic(keys, pos, n_pad, lane);
+                have = keep;
+                thr_key = keys[keep - 1];
+                thr_pos = pos[keep - 1];
+                have_thr = true;
+                __syncwarp();
+            }
+        }
+        if (valid <= (int64_t)a.min_k) {                   // core/knn.go:102-104 (note <=)
+            if (lane == 0) a.out[p] = a.global_mean;
+            continue;
+        }
+        int n_pad = 32;
+        while (n_pad < have) n_pad <<= 1;
+        __syncwarp();
+        for (int t = have + lane; t < n_pad; t += 32) { keys[t] = 0; pos[t] = 0xffffffffu; }
+        warp_bitonic(keys, pos, n_pad, lane);
+
+        int num = a.k;                                     // core/knn.go:111-114
+        if ((int64_t)num > valid) num = (int)valid;
+        if (num > have) num = have;                        // only when k > PRED_CAP/2 (rejected by the host)
+
+        // ---- weighted mean over the first `num`, sequential in sorted order ----
+        double wsum = 0.0, wrat = 0.0;
+        for (int b0 = 0; b0 < num; b0 += 32) {
+            const int t = b0 + lane;
+            double s = 0.0, adj = 0.0;
+            int32_t id = -1;
+            if (t < num) {
+                const int64_t x = cb + pos[t];
+                id = a.r_col[x];
+                s = row[id];
+                double rating = a.r_val[x];
+                if (a.knn_type == RS_KNN_CENTERED) rating -= a.means[id];                       // core/knn.go:121
+                else if (a.knn_type == RS_KNN_ZSCORE) rating = (rating - a.means[id]) / a.stddevs[id];
+                else if (a.knn_type == RS_KNN_BASELINE) rating -= a.bias[id];
+                adj = rating;
+                if (a.nb_ids && t < a.nb_cap) { a.nb_ids[t] = id; a.nb_sims[t] = s; }
+            }
+            const int lim = (num - b0) < 32 ? (num - b0) : 32;
+            for (int q = 0; q < lim; q++) {
+                const double sq = __shfl_sync(0xffffffffu, s, q);
+                const double aq = __shfl_sync(0xffffffffu, adj, q);
+                wsum += sq;                                // core/knn.go:117
+                wrat += sq * aq;                           // core/knn.go:127
+            }
+        }
+        if (lane == 0) {
+            double pred = wrat / wsum;                     // core/knn.go:131
+            if (a.knn_type == RS_KNN_CENTERED) pred += a.means[l];
+            else if (a.knn_type == RS_KNN_BASELINE) pred += a.bias[l];
+            else if (a.knn_type == RS_KNN_ZSCORE) { pred *= a.stddevs[l]; pred += a.means[l]; }
+            a.out[p] = pred;
+            if (a.nb_count) *a.nb_count = num < a.nb_cap ? num : a.nb_cap;
+        }
+    }
+}
+
+// ---------------- per-row top-k from the resident matrix ----------------
+constexpr int TOPK_THREADS = 256;
+constexpr int TOPK_CAP = 2048;
+
+__device__ void block_bitonic(uint64_t *keys, uint32_t *pos, int n_pad) {
+    for (int size = 2; size <= n_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                uint64_t ka = keys[lo], kb = keys[hi];
+                uint32_t pa = pos[lo], pb = pos[hi];
+                bool swap = up ? rec_before(kb, pb, ka, pa) : rec_before(ka, pa, kb, pb);
+                if (swap) { keys[lo] = kb; keys[hi] = ka; pos[lo] = pb; pos[hi] = pa; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS) topk_rows_kernel(const double *__restrict__ sims, int64_t ld_s,
+                                                                 int32_t n, int32_t k, int32_t *__restrict__ idx,
+                                                                 double *__restrict__ sim) {
+    __shared__ uint64_t keys[TOPK_CAP];
+    __shared__ uint32_t pos[TOPK_CAP];
+    __shared__ int s_have;
+    __shared__ uint64_t s_thr_key;
+    __shared__ uint32_t s_thr_pos;
+    const int64_t r = blockIdx.x;
+    const double *row = sims + r * ld_s;
+    if (threadIdx.x == 0) { s_have = 0; s_thr_key = 0; s_thr_pos = 0xffffffffu; }
+    __syncthreads();
+    bool have_thr = false;
+    for (int32_t base = 0; base < n; base += TOPK_THREADS) {
+        const int32_t j = base + threadIdx.x;
+        bool take = false;
+        uint64_t key = 0;
+        if (j < n) {
+            const double s = row[j];
+            if (s == s) {
+                key = rs_sim_key(s);
+                take = !have_thr || rec_before(key, (uint32_t)j, s_thr_key, s_thr_pos);
+            }
+        }
+        if (take) {
+            int slot = atomicAdd(&s_have, 1);
+            keys[slot] = key;
+            pos[slot] = (uint32_t)j;
+        }
+        __syncthreads();
+        if (s_have > TOPK_CAP - TOPK_THREADS) {
+            const int have = s_have;
+            for (int t = have + threadIdx.x; t < TOPK_CAP; t += blockDim.x) { keys[t] = 0; pos[t] = 0xffffffffu; }
+            block_bitonic(keys, pos, TOPK_CAP);
+            if (threadIdx.x == 0) {
+                s_have = k;
+                s_thr_key = keys[k - 1];
+                s_thr_pos = pos[k - 1];
+            }
+            have_thr = true;
+            __syncthreads();
+        }
+    }
+    const int have = s_have;
+    int n_pad = 32;
+    while (n_pad < have) n_pad <<= 1;
+    for (int t = have + threadIdx.x; t < n_pad; t += blockDim.x) { keys[t] = 0; pos[t] = 0xffffffffu; }
+    block_bitonic(keys, pos, n_pad);
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const int64_t o = r * k + t;
+        if (t < have) { idx[o] = (int32_t)pos[t]; sim[o] = rs_key_sim(keys[t]); }
+        else { idx[o] = -1; sim[o] = __longlong_as_double(0x7ff8000000000001ll); }
+    }
+}
+
+}  // namespace
+
+int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_right, int64_t n, double *d_out,
+                          int32_t *d_nb_ids, double *d_nb_sims, int32_t *d_nb_count, int32_t nb_cap) {
+    if (n <= 0) return RS_OK;
+    if (h->p.k > PRED_CAP / 2) {
+        rs_set_error("k=%d exceeds the %d neighbours the predict kernel supports", h->p.k, PRED_CAP / 2);
+        return RS_ERR_UNSUPPORTED;
+    }
+    PredArgs a{};
+    a.left = d_left; a.right = d_right; a.n = n; a.out = d_out;
+    a.r_ptr = h->r_ptr; a.r_col = h->r_col; a.r_val = h->r_val;
+    a.sims = h->sims; a.ld_s = h->ld_s; a.row_begin = h->row_begin; a.row_end = h->row_end;
+    a.means = h->means; a.stddevs = h->stddevs; a.bias = h->left_bias;
+    a.global_mean = h->global_mean; a.n_right = h->n_right;
+    a.k = h->p.k; a.min_k = h->p.min_k; a.knn_type = h->p.knn_type;
+    a.nb_ids = d_nb_ids; a.nb_sims = d_nb_sims; a.nb_count = d_nb_count; a.nb_cap = nb_cap;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    int64_t blocks = (n + PRED_WARPS - 1) / PRED_WARPS;
+    const int64_t cap = (int64_t)sms * 4 * 8;  // persistent-ish: a few waves of resident CTAs
+    if (blocks > cap) blocks = cap;
+    predict_kernel<<<(unsigned)blocks, PRED_WARPS * 32, 0, h->stream>>>(a);
+    h->prof.predict_launches++;
+    h->prof.total_launches++;
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
+int32_t rs_topk_launch(rs_knn *h, int32_t k, int32_t *d_idx, double *d_sim) {
+    const int64_t rows = h->row_end - h->row_begin;
+    if (rows <= 0) return RS_OK;
+    if (k < 1 || k > TOPK_CAP / 4) {
+        rs_set_error("top-k supports 1 <= k <= %d (got %d)", TOPK_CAP / 4, k);
+        return RS_ERR_UNSUPPORTED;
+    }
+    topk_rows_kernel<<<(unsigned)rows, TOPK_THREADS, 0, h->stream>>>(h->sims, h->ld_s, h->n_left, k, d_idx, d_sim);
+    h->prof.total_launches++;
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}

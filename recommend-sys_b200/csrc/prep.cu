@@ -1,0 +1,369 @@
+// prep.cu — device-side preparation for Fit: CSR construction from the inner-id COO,
+// rating classification, row statistics, and the dense byte/int8 layouts the similarity
+// kernels consume.  Follows the data-model contract of the reference:
+//   core/data.go:185-216  adjacency lists are appended in dataset order
+//   core/data.go:236-243  left rows are then sorted by id (unique keys)
+//   core/data.go:222-235  means = sequential sum / count over the dataset-order row
+//   core/knn.go:167-177   StdDevs[i] = sqrt(sum((x-mean)^2)/n) + 1e-5, dataset order
+//   core/sim.go:49-62     Pearson recomputes sum/count over the id-sorted row
+// CUB (ships with the CUDA toolkit) is used for the radix sorts and scans only.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+int32_t rs_dev_alloc(rs_knn *h, void **out, size_t bytes) {
+    void *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        rs_set_error("cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? RS_ERR_OOM : RS_ERR_CUDA;
+    }
+    h->allocs.push_back(p);
+    *out = p;
+    return RS_OK;
+}
+
+namespace {
+
+constexpr int T = 256;
+inline unsigned blocks_for(int64_t n, int t = T) { return (unsigned)((n + t - 1) / t); }
+
+enum { FLAG_BAD_ID = 1, FLAG_NOT_INT8 = 2, FLAG_DUP = 4, FLAG_NAN = 8 };
+
+__global__ void iota_validate_kernel(const int32_t *__restrict__ left, const int32_t *__restrict__ right,
+                                     const double *__restrict__ rating, int64_t nnz, int32_t n_left,
+                                     int32_t n_right, int32_t *__restrict__ idx, int32_t *__restrict__ lcount,
+                                     int32_t *__restrict__ rcount, int32_t *__restrict__ flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    idx[i] = (int32_t)i;
+    int32_t l = left[i], r = right[i];
+    int f = 0;
+    if (l < 0 || l >= n_left || r < 0 || r >= n_right) {
+        f |= FLAG_BAD_ID;
+    } else {
+        atomicAdd(&lcount[l], 1);
+        atomicAdd(&rcount[r], 1);
+    }
+    double v = rating[i];
+    if (v != v) f |= FLAG_NAN;
+    if (!(v == rint(v) && fabs(v) <= 11.0)) f |= FLAG_NOT_INT8;
+    if (f) atomicOr(flags, f);
+}
+
+__global__ void gather_keys_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ perm, int64_t n,
+                                   int32_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[perm[i]];
+}
+
+__global__ void widen_kernel(const int32_t *__restrict__ in, int64_t n, int64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
+// entries of the (major, minor)-sorted permutation -> CSR column / value arrays
+__global__ void gather_csr_kernel(const int32_t *__restrict__ perm, const int32_t *__restrict__ major,
+                                  const int32_t *__restrict__ minor, const double *__restrict__ rating,
+                                  int64_t nnz, int32_t *__restrict__ col, double *__restrict__ val,
+                                  int32_t *__restrict__ flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    int32_t p = perm[i];
+    col[i] = minor[p];
+    val[i] = rating[p];
+    if (i > 0 && flags) {
+        int32_t q = perm[i - 1];
+        if (major[p] == major[q] && minor[p] == minor[q]) atomicOr(flags, FLAG_DUP);
+    }
+}
+
+__global__ void gather_val_kernel(const int32_t *__restrict__ perm, const double *__restrict__ rating, int64_t nnz,
+                                  double *__restrict__ val) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) val[i] = rating[perm[i]];
+}
+
+__global__ void code_int8_kernel(const double *__restrict__ val, int64_t nnz, uint8_t *__restrict__ code) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) code[i] = (uint8_t)((int)val[i] + RS_INT8_BIAS);
+}
+
+__global__ void lut_int8_kernel(double *__restrict__ lut) {
+    int c = threadIdx.x;
+    lut[c] = (c >= 1 && c <= 2 * RS_INT8_BIAS - 1) ? (double)(c - RS_INT8_BIAS) : 0.0;
+}
+
+__global__ void lut_table_kernel(const double *__restrict__ uniq, int n, double *__restrict__ lut) {
+    int c = threadIdx.x;
+    lut[c] = (c >= 1 && c <= n) ? uniq[c - 1] : 0.0;
+}
+
+__global__ void code_table_kernel(const double *__restrict__ val, int64_t nnz, const double *__restrict__ uniq,
+                                  int n, uint8_t *__restrict__ code) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    double v = val[i] + 0.0;
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (uniq[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    code[i] = (uint8_t)(lo + 1);
+}
+
+// One thread per left row, strictly sequential sums in the reference's order.
+__global__ void row_stats_kernel(const int64_t *__restrict__ l_ptr, const double *__restrict__ ld_val,
+                                 const double *__restrict__ l_val, int32_t n_left, int want_std,
+                                 double *__restrict__ means, double *__restrict__ stddevs,
+                                 double *__restrict__ pmeans) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_left) return;
+    int64_t b = l_ptr[i], e = l_ptr[i + 1];
+    double sum = 0.0, count = 0.0;
+    for (int64_t x = b; x < e; x++) { sum += ld_val[x]; count += 1.0; }   // core/data.go:226-232
+    double mean = sum / count;
+    means[i] = mean;
+    if (want_std) {
+        double s2 = 0.0, c2 = 0.0;
+        for (int64_t x = b; x < e; x++) {                                 // core/knn.go:170-175
+            double r = ld_val[x];
+            s2 += (r - mean) * (r - mean);
+            c2 += 1.0;
+        }
+        stddevs[i] = sqrt(s2 / c2) + 1e-5;
+    }
+    double psum = 0.0, pcount = 0.0;
+    for (int64_t x = b; x < e; x++) { psum += l_val[x]; pcount += 1.0; }  // core/sim.go:49-54
+    pmeans[i] = psum / pcount;
+}
+
+__global__ void scatter_rt_kernel(const int64_t *__restrict__ l_ptr, const int32_t *__restrict__ l_col,
+                                  const uint8_t *__restrict__ l_code, int32_t n_left, int64_t ld_rt,
+                                  uint8_t *__restrict__ rt) {
+    // one warp per left row
+    int32_t row = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= n_left) return;
+    for (int64_t x = l_ptr[row] + lane; x < l_ptr[row + 1]; x += 32)
+        rt[(int64_t)l_col[x] * ld_rt + row] = l_code[x];
+}
+
+// planes[p][row][col]: p=0 rating, p=1 rating^2, p=2 mask; K-major int8
+__global__ void scatter_planes_kernel(const int64_t *__restrict__ l_ptr, const int32_t *__restrict__ l_col,
+                                      const uint8_t *__restrict__ l_code, int32_t n_left, int64_t npad,
+                                      int64_t kpad, int8_t *__restrict__ planes) {
+    int32_t row = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= n_left) return;
+    int64_t plane = npad * kpad;
+    for (int64_t x = l_ptr[row] + lane; x < l_ptr[row + 1]; x += 32) {
+        int v = (int)l_code[x] - RS_INT8_BIAS;
+        int64_t o = (int64_t)row * kpad + l_col[x];
+        planes[o] = (int8_t)v;
+        planes[plane + o] = (int8_t)(v * v);
+        planes[2 * plane + o] = 1;
+    }
+}
+
+struct SortTmp {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+int bits_for(int32_t n) {
+    int b = 1;
+    while ((1ll << b) < (long long)n) b++;
+    return b;
+}
+
+}  // namespace
+
+#define RS_SORT_PAIRS(keys_in, keys_out, vals_in, vals_out, n, end_bit)                                      \
+    do {                                                                                                     \
+        size_t need_ = 0;                                                                                    \
+        RS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need_, keys_in, keys_out, vals_in, vals_out, (int)(n), \
+                                                0, end_bit, st));                                            \
+        if (need_ > tmp.bytes) {                                                                             \
+            RS_TRY(rs_dev_alloc(h, &tmp.p, need_));                                                          \
+            tmp.bytes = need_;                                                                               \
+        }                                                                                                    \
+        RS_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp.bytes, keys_in, keys_out, vals_in, vals_out,      \
+                                                (int)(n), 0, end_bit, st));                                  \
+    } while (0)
+
+int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, const double *d_rating,
+                      const double *d_left_bias, const double *d_right_bias) {
+    cudaStream_t st = h->stream;
+    const int64_t nnz = h->nnz;
+    const int32_t nl = h->n_left, nr = h->n_right;
+    if (nnz >= (1ll << 31)) {
+        rs_set_error("nnz %lld exceeds the 2^31-1 entries supported", (long long)nnz);
+        return RS_ERR_UNSUPPORTED;
+    }
+    SortTmp tmp;
+    int32_t *idx, *keys_a, *keys_b, *perm_l, *perm_r, *perm_lr, *perm_rl, *lcount, *rcount;
+    RS_TRY(rs_alloc(h, &idx, nnz));
+    RS_TRY(rs_alloc(h, &keys_a, nnz));
+    RS_TRY(rs_alloc(h, &keys_b, nnz));
+    RS_TRY(rs_alloc(h, &perm_l, nnz));
+    RS_TRY(rs_alloc(h, &perm_r, nnz));
+    RS_TRY(rs_alloc(h, &perm_lr, nnz));
+    RS_TRY(rs_alloc(h, &perm_rl, nnz));
+    RS_TRY(rs_alloc(h, &lcount, (size_t)nl + 1));
+    RS_TRY(rs_alloc(h, &rcount, (size_t)nr + 1));
+    RS_TRY(rs_alloc(h, &h->d_flags, 4));
+    RS_CUDA(cudaMemsetAsync(lcount, 0, ((size_t)nl + 1) * 4, st));
+    RS_CUDA(cudaMemsetAsync(rcount, 0, ((size_t)nr + 1) * 4, st));
+    RS_CUDA(cudaMemsetAsync(h->d_flags, 0, 16, st));
+
+    iota_validate_kernel<<<blocks_for(nnz), T, 0, st>>>(d_left, d_right, d_rating, nnz, nl, nr, idx, lcount,
+                                                       rcount, h->d_flags);
+    h->prof.total_launches++;
+    int32_t flags = 0;
+    RS_CUDA(cudaMemcpyAsync(&flags, h->d_flags, 4, cudaMemcpyDeviceToHost, st));
+    RS_CUDA(cudaStreamSynchronize(st));
+    if (flags & FLAG_BAD_ID) {
+        rs_set_error("rating rows contain inner ids outside [0,n_left) x [0,n_right)");
+        return RS_ERR_INVALID;
+    }
+    if (flags & FLAG_NAN) {
+        rs_set_error("NaN ratings are not supported");
+        return RS_ERR_UNSUPPORTED;
+    }
+    h->rating_class = (flags & FLAG_NOT_INT8) ? RS_CLASS_TABLE : RS_CLASS_INT8;
+
+    const int lb = bits_for(nl), rb = bits_for(nr);
+    // stable LSD sorts: perm_l = by left (dataset order inside a row), perm_r = by right
+    RS_SORT_PAIRS(d_left, keys_a, idx, perm_l, nnz, lb);
+    RS_SORT_PAIRS(d_right, keys_a, idx, perm_r, nnz, rb);
+    // (left, right asc): stable sort by left of the right-sorted sequence
+    gather_keys_kernel<<<blocks_for(nnz), T, 0, st>>>(d_left, perm_r, nnz, keys_a);
+    RS_SORT_PAIRS(keys_a, keys_b, perm_r, perm_lr, nnz, lb);
+    // (right, left asc)
+    gather_keys_kernel<<<blocks_for(nnz), T, 0, st>>>(d_right, perm_l, nnz, keys_a);
+    RS_SORT_PAIRS(keys_a, keys_b, perm_l, perm_rl, nnz, rb);
+    h->prof.total_launches += 2;  // own kernels only; CUB's sort/scan kernels are not counted
+
+    // row pointers
+    RS_TRY(rs_alloc(h, &h->l_ptr, (size_t)nl + 1));
+    RS_TRY(rs_alloc(h, &h->r_ptr, (size_t)nr + 1));
+    {
+        int64_t *wide;
+        size_t mx = (size_t)(nl > nr ? nl : nr) + 1;
+        RS_TRY(rs_alloc(h, &wide, mx));
+        size_t need = 0;
+        RS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, wide, h->l_ptr, (int)mx, st));
+        if (need > tmp.bytes) { RS_TRY(rs_dev_alloc(h, &tmp.p, need)); tmp.bytes = need; }
+        widen_kernel<<<blocks_for(nl + 1), T, 0, st>>>(lcount, nl + 1, wide);
+        RS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp.bytes, wide, h->l_ptr, nl + 1, st));
+        widen_kernel<<<blocks_for(nr + 1), T, 0, st>>>(rcount, nr + 1, wide);
+        RS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp.bytes, wide, h->r_ptr, nr + 1, st));
+        h->prof.total_launches += 2;
+    }
+
+    RS_TRY(rs_alloc(h, &h->l_col, nnz));
+    RS_TRY(rs_alloc(h, &h->l_val, nnz));
+    RS_TRY(rs_alloc(h, &h->ld_val, nnz));
+    RS_TRY(rs_alloc(h, &h->r_col, nnz));
+    RS_TRY(rs_alloc(h, &h->r_val, nnz));
+    RS_TRY(rs_alloc(h, &h->l_code, nnz));
+    gather_csr_kernel<<<blocks_for(nnz), T, 0, st>>>(perm_lr, d_left, d_right, d_rating, nnz, h->l_col, h->l_val,
+                                                    h->d_flags);
+    gather_csr_kernel<<<blocks_for(nnz), T, 0, st>>>(perm_rl, d_right, d_left, d_rating, nnz, h->r_col, h->r_val,
+                                                    nullptr);
+    gather_val_kernel<<<blocks_for(nnz), T, 0, st>>>(perm_l, d_rating, nnz, h->ld_val);
+    h->prof.total_launches += 3;
+
+    // rating codes + value table
+    RS_TRY(rs_alloc(h, &h->lut, 256));
+    if (h->rating_class == RS_CLASS_INT8) {
+        code_int8_kernel<<<blocks_for(nnz), T, 0, st>>>(h->l_val, nnz, h->l_code);
+        lut_int8_kernel<<<1, 256, 0, st>>>(h->lut);
+        h->n_codes = 2 * RS_INT8_BIAS - 1;
+        h->prof.total_launches += 2;
+    } else {
+        double *sorted, *uniq;
+        int *d_num;
+        RS_TRY(rs_alloc(h, &sorted, nnz));
+        RS_TRY(rs_alloc(h, &uniq, nnz));
+        RS_TRY(rs_alloc(h, &d_num, 4));
+        size_t need = 0;
+        RS_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, need, h->l_val, sorted, (int)nnz, 0, 64, st));
+        if (need > tmp.bytes) { RS_TRY(rs_dev_alloc(h, &tmp.p, need)); tmp.bytes = need; }
+        RS_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp.bytes, h->l_val, sorted, (int)nnz, 0, 64, st));
+        need = 0;
+        RS_CUDA(cub::DeviceSelect::Unique(nullptr, need, sorted, uniq, d_num, (int)nnz, st));
+        if (need > tmp.bytes) { RS_TRY(rs_dev_alloc(h, &tmp.p, need)); tmp.bytes = need; }
+        RS_CUDA(cub::DeviceSelect::Unique(tmp.p, tmp.bytes, sorted, uniq, d_num, (int)nnz, st));
+        int num = 0;
+        RS_CUDA(cudaMemcpyAsync(&num, d_num, 4, cudaMemcpyDeviceToHost, st));
+        RS_CUDA(cudaStreamSynchronize(st));
+        if (num > 255) {
+            rs_set_error("%d distinct rating values; the device path supports at most 255", num);
+            return RS_ERR_UNSUPPORTED;
+        }
+        h->n_codes = num;
+        lut_table_kernel<<<1, 256, 0, st>>>(uniq, num, h->lut);
+        code_table_kernel<<<blocks_for(nnz), T, 0, st>>>(h->l_val, nnz, uniq, num, h->l_code);
+        h->prof.total_launches += 2;
+    }
+
+    // row statistics
+    RS_TRY(rs_alloc(h, &h->means, (size_t)nl + 1));
+    RS_TRY(rs_alloc(h, &h->stddevs, (size_t)nl + 1));
+    RS_TRY(rs_alloc(h, &h->pmeans, (size_t)nl + 1));
+    row_stats_kernel<<<blocks_for(nl, 128), 128, 0, st>>>(h->l_ptr, h->ld_val, h->l_val, nl,
+                                                         h->p.knn_type == RS_KNN_ZSCORE, h->means, h->stddevs,
+                                                         h->pmeans);
+    h->prof.total_launches++;
+
+    if (d_left_bias) {
+        RS_TRY(rs_alloc(h, &h->left_bias, (size_t)nl + 1));
+        RS_CUDA(cudaMemcpyAsync(h->left_bias, d_left_bias, (size_t)nl * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    if (d_right_bias) {
+        RS_TRY(rs_alloc(h, &h->right_bias, (size_t)nr + 1));
+        RS_CUDA(cudaMemcpyAsync(h->right_bias, d_right_bias, (size_t)nr * 8, cudaMemcpyDeviceToDevice, st));
+    }
+
+    RS_CUDA(cudaMemcpyAsync(&flags, h->d_flags, 4, cudaMemcpyDeviceToHost, st));
+    RS_CUDA(cudaStreamSynchronize(st));
+    if (flags & FLAG_DUP) {
+        rs_set_error("duplicate (left,right) rating pairs are not supported (the reference's merge-join "
+                     "double-counts them)");
+        return RS_ERR_DUPLICATE;
+    }
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
+int32_t rs_prep_rt(rs_knn *h) {
+    cudaStream_t st = h->stream;
+    h->ld_rt = ((int64_t)h->n_left + RS_STREAM_JC - 1) / RS_STREAM_JC * RS_STREAM_JC;
+    size_t bytes = (size_t)h->n_right * (size_t)h->ld_rt;
+    RS_TRY(rs_alloc(h, &h->rt, bytes));
+    RS_CUDA(cudaMemsetAsync(h->rt, 0, bytes, st));
+    scatter_rt_kernel<<<blocks_for((int64_t)h->n_left * 32), T, 0, st>>>(h->l_ptr, h->l_col, h->l_code, h->n_left,
+                                                                        h->ld_rt, h->rt);
+    h->prof.total_launches++;
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
+int32_t rs_prep_planes(rs_knn *h) {
+    cudaStream_t st = h->stream;
+    h->tc_npad = ((int64_t)h->n_left + RS_TC_BM - 1) / RS_TC_BM * RS_TC_BM;
+    h->tc_kpad = ((int64_t)h->n_right + RS_TC_BK - 1) / RS_TC_BK * RS_TC_BK;
+    size_t bytes = 3 * (size_t)h->tc_npad * (size_t)h->tc_kpad;
+    RS_TRY(rs_alloc(h, &h->planes, bytes));
+    RS_CUDA(cudaMemsetAsync(h->planes, 0, bytes, st));
+    scatter_planes_kernel<<<blocks_for((int64_t)h->n_left * 32), T, 0, st>>>(h->l_ptr, h->l_col, h->l_code,
+                                                                            h->n_left, h->tc_npad, h->tc_kpad,
+                                                                            h->planes);
+    h->prof.total_launches++;
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}

@@ -1,0 +1,36 @@
+/*
+ * rs_host.h — host-side (CPU) pieces of the drop-in that stay on the host in the reference
+ * too and feed the device path through include/rs_knn.h.  Not part of the accelerated path.
+ *
+ *   rs_host_inner_ids     NewTrainSet's id maps (core/data.go:137-151): inner id = order of
+ *                         first appearance; returns the number of distinct ids.
+ *   rs_host_baseline_sgd  BaseLine.Fit (core/base.go:135-163): strictly sequential SGD over
+ *                         the ratings in dataset order (every step depends on the previous
+ *                         one through globalBias, so it cannot be parallelised bit-exactly).
+ *                         KNN-baseline only needs its bias vectors (core/knn.go:179-187).
+ * Built with -ffp-contract=off (Go on amd64 never fuses x*y+z).
+ */
+#ifndef RS_HOST_H
+#define RS_HOST_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int64_t rs_host_inner_ids(const int64_t *raw, int64_t n, int32_t *inner_out);
+
+void rs_host_baseline_sgd(const int32_t *inner_user, const int32_t *inner_item, const double *rating,
+                          int64_t n, int32_t n_users, int32_t n_items, double reg, double lr,
+                          int32_t n_epochs, double *user_bias, double *item_bias, double *global_bias);
+
+/* Deterministic synthetic rating matrices of the BASELINE.json shapes:
+ * unique (user,item) pairs, heavy-tailed degrees, integer ratings 1..5 with a MovieLens-like
+ * marginal, rows emitted in a seeded shuffled order.  Returns the number of ratings written
+ * (<= nnz_target; exactly nnz_target unless the matrix is too small). */
+int64_t rs_host_synth_ratings(int32_t n_users, int32_t n_items, int64_t nnz_target, uint64_t seed,
+                              int64_t *users, int64_t *items, double *ratings);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,52 @@
+"""Row sharding of the similarity rows across the GPUs of one box.
+
+Every rank holds the full (replicated) rating matrix and owns a contiguous block of left rows;
+it computes that block against all N rows and selects top-k locally.  The only exchange is one
+all-gather of the fixed-size neighbour lists (int32 idx, float64 sim)[rows][k] over NCCL/NVLink
+(gloo in the CPU tests).  torch.distributed is the plumbing, not the product."""
+from __future__ import annotations
+
+
+def shard_rows(n: int, world: int, rank: int, align: int = 128):
+    """[begin,end) of the left rows owned by `rank`: contiguous, `align`-row aligned boundaries
+    (the tensor-core tile height) except for the last shard, sizes differing by <= align."""
+    blocks = (n + align - 1) // align
+    b0 = blocks * rank // world
+    b1 = blocks * (rank + 1) // world
+    return min(b0 * align, n), min(b1 * align, n)
+
+
+def allgather_topk(idx_local, sim_local, n: int, k: int, group=None):
+    """All-gather the per-shard neighbour lists into the full (n, k) lists on every rank.
+    idx_local/sim_local: torch tensors (rows_of_this_rank, k) on the collective's device."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    bounds = [shard_rows(n, world, r) for r in range(world)]
+    max_rows = max(b - a for a, b in bounds)
+    pad_i = torch.full((max_rows, k), -1, dtype=torch.int32, device=idx_local.device)
+    pad_s = torch.full((max_rows, k), float("nan"), dtype=torch.float64, device=sim_local.device)
+    pad_i[: idx_local.shape[0]] = idx_local
+    pad_s[: sim_local.shape[0]] = sim_local
+    all_i = torch.empty((world * max_rows, k), dtype=torch.int32, device=idx_local.device)
+    all_s = torch.empty((world * max_rows, k), dtype=torch.float64, device=sim_local.device)
+    dist.all_gather_into_tensor(all_i, pad_i, group=group)
+    dist.all_gather_into_tensor(all_s, pad_s, group=group)
+    out_i = torch.cat([all_i[r * max_rows: r * max_rows + (b - a)] for r, (a, b) in enumerate(bounds)])
+    out_s = torch.cat([all_s[r * max_rows: r * max_rows + (b - a)] for r, (a, b) in enumerate(bounds)])
+    return out_i, out_s
+
+
+def allgather_predictions(pred_local, counts, group=None):
+    """All-gather per-rank prediction vectors of (known) lengths `counts` into one vector."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    m = max(counts)
+    pad = torch.zeros(m, dtype=torch.float64, device=pred_local.device)
+    pad[: pred_local.shape[0]] = pred_local
+    out = torch.empty(world * m, dtype=torch.float64, device=pred_local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return torch.cat([out[r * m: r * m + c] for r, c in enumerate(counts)])

@@ -1,0 +1,88 @@
+"""Host logic of the drop-in (no device): Parameters, TrainSet ids, KFold, BaseLine SGD, synth."""
+import numpy as np
+import pytest
+
+import recommend_sys_b200 as rs
+from oracle import binding as ob
+from conftest import split
+
+
+def test_parameters_typed_getters_panic_like_go():
+    p = rs.Parameters({"k": 10, "userBased": False, "reg": 0.1, "sim": rs.Pearson, "type": "x"})
+    assert p.GetInt("k", 40) == 10 and p.GetInt("mink", 1) == 1
+    assert p.GetBool("userBased", True) is False
+    assert p.GetFloat64("reg", 0.02) == 0.1 and p.GetFloat64("lr", 0.005) == 0.005
+    assert p.GetSim("sim", rs.MSD) is rs.Pearson and p.GetSim("other", rs.MSD) is rs.MSD
+    with pytest.raises(TypeError):        # val.(int) on a float64 panics, core/base.go:26
+        rs.Parameters({"k": 10.0}).GetInt("k", 40)
+    with pytest.raises(TypeError):        # val.(Sim) on anything else panics, core/base.go:47
+        rs.Parameters({"sim": "pearson"}).GetSim("sim", rs.MSD)
+    with pytest.raises(TypeError):
+        rs.Parameters({"reg": 1}).GetFloat64("reg", 0.02)
+    q = p.Copy()
+    q["k"] = 3
+    assert p["k"] == 10
+
+
+def test_trainset_inner_ids_first_appearance(ml100k):
+    u, i, r = split(ml100k["u1_base"])
+    ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
+    ots = ob.TrainSet(u, i, r)
+    assert ts.UserCount == ots.user_count == 943
+    assert ts.ItemCount == ots.item_count
+    assert np.array_equal(ts.innerUsers, ots.inner_users())
+    assert np.array_equal(ts.innerItems, ots.inner_items())
+    assert ts.GlobalMean == ots.global_mean
+    assert ts.ConvertUserID(int(u[0])) == 0 and ts.ConvertItemID(int(i[0])) == 0
+    assert ts.ConvertUserID(10 ** 9) == rs.core.newID
+    got = ts.convert_users(np.array([u[0], 10 ** 9, u[-1]]))
+    assert got[0] == 0 and got[1] == -1 and got[2] == ts.ConvertUserID(int(u[-1]))
+
+
+def test_kfold_partitions(ml100k):
+    d = rs.NewRawSet(*split(ml100k["u_data"][:1003]))
+    trains, tests = d.KFold(5, 0)
+    assert [t.Length() for t in tests] == [201, 201, 201, 200, 200]   # core/data.go:54-60
+    assert all(tr.Length() + te.Length() == 1003 for tr, te in zip(trains, tests))
+    seen = np.concatenate([np.stack([t.Users, t.Items], 1) for t in tests])
+    assert len({tuple(x) for x in seen.tolist()}) == 1003
+
+
+def test_baseline_sgd_matches_oracle_bits(ml100k):
+    u, i, r = split(ml100k["u2_base"])
+    ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
+    bl = rs.NewBaseLine(rs.Parameters({"nEpochs": 7}))
+    bl.Fit(ts)
+    ub, ib, gb = ob.TrainSet(u, i, r).baseline(n_epochs=7)
+    assert np.array_equal(bl.userBias, ub) and np.array_equal(bl.itemBias, ib) and bl.globalBias == gb
+    assert bl.Predict(int(u[0]), 10 ** 9) == gb + ub[0]
+
+
+def test_synth_is_deterministic_and_well_formed():
+    a = rs.core.synth_ratings(943, 1682, 100000, 0x5EED0001)
+    b = rs.core.synth_ratings(943, 1682, 100000, 0x5EED0001)
+    assert a.Length() == 100000
+    assert np.array_equal(a.Users, b.Users) and np.array_equal(a.Items, b.Items) and np.array_equal(a.Ratings, b.Ratings)
+    assert len(set(zip(a.Users.tolist(), a.Items.tolist()))) == 100000      # unique pairs
+    assert set(np.unique(a.Ratings)) == {1.0, 2.0, 3.0, 4.0, 5.0}
+    assert np.bincount(rs.NewTrainSet(a).innerUsers).min() >= 20            # MovieLens-like floor
+    c = rs.core.synth_ratings(943, 1682, 100000, 0x5EED0002)
+    assert not np.array_equal(a.Items, c.Items)
+
+
+def test_metrics_match_oracle():
+    rng = np.random.RandomState(0)
+    p, t = rng.rand(1000) * 5, rng.randint(1, 6, 1000).astype(float)
+    assert abs(rs.RMSE(p, t) - ob.rmse(p, t)) < 1e-12
+    assert abs(rs.MAE(p, t) - ob.mae(p, t)) < 1e-12
+
+
+def test_shard_rows_cover_everything():
+    from recommend_sys_b200.shard import shard_rows
+
+    for n in (1, 7, 128, 943, 26744, 138493):
+        for w in (1, 2, 3, 4, 8):
+            parts = [shard_rows(n, w, r) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[x][1] == parts[x + 1][0] for x in range(w - 1))
+            assert max(b - a for a, b in parts) - min(b - a for a, b in parts) <= 128

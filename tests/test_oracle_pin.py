@@ -1,0 +1,113 @@
+"""Pins the CPU oracle (oracle/knn_oracle.c) against everything the reference's own tests hold
+for the path: the three known-answer vectors of core/sim_test.go at their exact
+float64 value, and the statistical bounds of core/base_test.go:50-64 on MovieLens-100K."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from conftest import split
+
+A = [(1, 4), (2, 5), (3, 6)]   # core/sim_test.go:11-15
+B = [(0, 0), (1, 1), (2, 2)]   # core/sim_test.go:16-20
+
+
+def test_cosine_kat():  # core/sim_test.go:10-25 (0.978 +- 0.01)
+    assert ob.sim_lists("cosine", A, B) == 0.9778024140774094
+
+
+def test_msd_kat():  # core/sim_test.go:27-42 (0.1 +- 0.01)
+    assert ob.sim_lists("msd", A, B) == 0.1
+
+
+def test_pearson_kat():  # core/sim_test.go:44-59 (0 +- 0.01); means are over the FULL rows
+    assert ob.sim_lists("pearson", A, B) == 0.0
+
+
+def test_no_corating_is_nan():  # 0/0 in every formula of core/sim.go
+    for sim in ("cosine", "msd", "pearson"):
+        assert np.isnan(ob.sim_lists(sim, [(1, 4.0)], [(2, 3.0)]))
+
+
+def test_sims_are_bit_symmetric():
+    rng = np.random.RandomState(3)
+    for _ in range(50):
+        ia = rng.choice(60, 25, replace=False)
+        ib = rng.choice(60, 25, replace=False)
+        a = [(int(i), float(rng.randint(1, 6))) for i in ia]
+        b = [(int(i), float(rng.randint(1, 6))) for i in ib]
+        for sim in ("cosine", "msd", "pearson"):
+            x, y = ob.sim_lists(sim, a, b), ob.sim_lists(sim, b, a)
+            assert (np.isnan(x) and np.isnan(y)) or x == y
+
+
+def _kfold(d, cv, seed):
+    """core/data.go:49-70 with a seeded permutation (the reference's is unseeded, SURVEY hazard 3)."""
+    n = len(d)
+    perm = np.random.RandomState(seed).permutation(n)
+    begin = end = 0
+    for i in range(cv):
+        end += n // cv + (1 if i < n % cv else 0)
+        yield d[np.concatenate([perm[:begin], perm[end:]])], d[perm[begin:end]]
+        begin = end
+
+
+# core/base_test.go:50-64: Evaluate() passes params=nil -> user-based MSD, k=40, mink=1, and
+# asserts mean RMSE <= expect+0.008, mean MAE <= expect+0.008 over 5 folds.
+@pytest.mark.parametrize("knn_type,rmse,mae", [("basic", 0.980, 0.774), ("centered", 0.951, 0.749),
+                                               ("zscore", 0.951, 0.746), ("baseline", 0.931, 0.733)])
+def test_ml100k_bounds(ml100k, knn_type, rmse, mae):
+    rm, ma = [], []
+    for tr, te in _kfold(ml100k["u_data"], 5, 0):
+        ts = ob.TrainSet(*split(tr))
+        knn = ob.KNN(sim="msd", knn_type=knn_type, user_based=True, k=40, min_k=1, n_jobs=8,
+                     tie_policy="go").fit(ts)
+        u, i, r = split(te)
+        p = knn.predict_batch(u, i, n_threads=8)
+        rm.append(ob.rmse(p, r))
+        ma.append(ob.mae(p, r))
+    assert np.mean(rm) <= rmse + 0.008, np.mean(rm)
+    assert np.mean(ma) <= mae + 0.008, np.mean(ma)
+    # and not absurdly better than the reference's expectation either
+    assert np.mean(rm) >= rmse - 0.03
+
+
+def test_fit_threads_do_not_change_bits(ml100k):
+    ts = ob.TrainSet(*split(ml100k["u1_base"][:20000]))
+    a = ob.KNN(sim="pearson", user_based=False, n_jobs=1).fit(ts).sims().copy()
+    b = ob.KNN(sim="pearson", user_based=False, n_jobs=7).fit(ts).sims().copy()
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+    assert np.isnan(np.diag(a)).all()          # core/knn.go:202 i != j: diagonal stays NaN
+    assert np.array_equal(np.nan_to_num(a), np.nan_to_num(a.T))
+
+
+def test_go_sort_port_sorts_and_is_deterministic():
+    """The pdqsort restatement (sort.Sort, Go >= 1.19) must at least be a correct, deterministic
+    sort on the shapes Predict feeds it (many duplicate keys)."""
+    import ctypes as C
+
+    L = ob.lib()
+    rng = np.random.RandomState(1)
+    for n in (0, 1, 2, 12, 13, 49, 50, 51, 200, 1000, 5000):
+        for dup in (3, 50, 10 ** 9):
+            arr = np.array([(i, float(rng.randint(0, dup))) for i in range(n)],
+                           dtype=[("id", "<i8"), ("rating", "<f8")])
+            ids = rng.permutation(n)
+            arr["id"] = ids
+            buf = (ob.IdRating * max(1, n))(*[ob.IdRating(int(a), float(b)) for a, b in arr])
+            L.or_sort_by_id(buf, n)
+            got = [buf[i].id for i in range(n)]
+            assert got == sorted(ids.tolist())
+
+
+def test_tie_policies_agree_without_ties(ml100k):
+    """Cosine on ml-100k has few ties; where the k-boundary has none the two policies must give
+    the same neighbour SET, hence predictions equal to rounding of the summation order."""
+    tr, te = ml100k["u1_base"], ml100k["u1_test"][:3000]
+    ts = ob.TrainSet(*split(tr))
+    go = ob.KNN(sim="cosine", k=40, tie_policy="go", n_jobs=8).fit(ts)
+    ca = ob.KNN(sim="cosine", k=40, tie_policy="canonical", n_jobs=8).fit(ts)
+    u, i, _ = split(te)
+    pg, pc = go.predict_batch(u, i), ca.predict_batch(u, i)
+    close = np.isclose(pg, pc, rtol=1e-12, atol=0)
+    assert close.mean() > 0.9   # SURVEY hazard 1: ~3.5 % of cosine predictions straddle a tie
