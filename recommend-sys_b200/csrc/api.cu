@@ -1,5 +1,6 @@
 // api.cu — the C ABI of include/rs_knn.h: handle lifetime, Fit / Predict orchestration.
 // No CPU fallback anywhere: every compute entry point needs a CUDA device.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -37,6 +38,7 @@ void free_fit_state(rs_knn *h) {
     h->lut = h->means = h->stddevs = h->pmeans = h->left_bias = h->right_bias = nullptr;
     h->rt = nullptr;
     h->planes = nullptr;
+    h->row_cnt = h->row_sum = nullptr;
     h->sims = nullptr;
     h->topk_idx = nullptr;
     h->topk_sim = nullptr;
@@ -216,6 +218,10 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
     if (rc != RS_OK) { free_fit_state(h); return rc; }
 
     int path = h->p.sim_path;
+    if (const char *force = getenv("RS_KNN_FORCE_PATH")) {  // debugging aid: "stream" | "tensor"
+        if (!strcmp(force, "stream")) path = RS_PATH_STREAM;
+        else if (!strcmp(force, "tensor")) path = RS_PATH_TENSOR;
+    }
     if (path == RS_PATH_AUTO) path = tensor_eligible(h) ? RS_PATH_TENSOR : RS_PATH_STREAM;
     if (path == RS_PATH_TENSOR && !tensor_eligible(h)) {
         rs_set_error("tensor path needs integer ratings in [-11,11] and Cosine/MSD (or Pearson in SUMS mode)");

@@ -80,6 +80,9 @@ struct rs_knn {
     double *stddevs = nullptr;    // KNN.StdDevs
     double *pmeans = nullptr;     // Pearson's own row means (sorted-order sum, core/sim.go:49-62)
     double *left_bias = nullptr;  // KNN.Bias
+    int32_t *row_cnt = nullptr;   // ratings per left row and their integer sum (tensor path, Pearson)
+    int32_t *row_sum = nullptr;
+    int64_t max_row_cnt = 0;
     double *right_bias = nullptr;
 
     // transposed rating bytes RT[right][left] (n_right x ld_rt), stream path

@@ -151,7 +151,22 @@ __global__ void scatter_rt_kernel(const int64_t *__restrict__ l_ptr, const int32
         rt[(int64_t)l_col[x] * ld_rt + row] = l_code[x];
 }
 
-// planes[p][row][col]: p=0 rating, p=1 rating^2, p=2 mask; K-major int8
+__global__ void row_isum_kernel(const int64_t *__restrict__ l_ptr, const uint8_t *__restrict__ l_code,
+                                int32_t n_left, int32_t *__restrict__ row_cnt, int32_t *__restrict__ row_sum) {
+    int32_t row = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= n_left) return;
+    int s = 0;
+    for (int64_t x = l_ptr[row] + lane; x < l_ptr[row + 1]; x += 32) s += (int)l_code[x] - RS_INT8_BIAS;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        row_cnt[row] = (int32_t)(l_ptr[row + 1] - l_ptr[row]);
+        row_sum[row] = s;
+    }
+}
+
+// planes[p][row][col]: p=0 rating^2, p=1 mask, p=2 rating (the order the MMAs of sim_tensor.cu
+// rely on: B planes adjacent in shared memory as X2 | M | X); K-major int8
 __global__ void scatter_planes_kernel(const int64_t *__restrict__ l_ptr, const int32_t *__restrict__ l_col,
                                       const uint8_t *__restrict__ l_code, int32_t n_left, int64_t npad,
                                       int64_t kpad, int8_t *__restrict__ planes) {
@@ -162,9 +177,9 @@ __global__ void scatter_planes_kernel(const int64_t *__restrict__ l_ptr, const i
     for (int64_t x = l_ptr[row] + lane; x < l_ptr[row + 1]; x += 32) {
         int v = (int)l_code[x] - RS_INT8_BIAS;
         int64_t o = (int64_t)row * kpad + l_col[x];
-        planes[o] = (int8_t)v;
-        planes[plane + o] = (int8_t)(v * v);
-        planes[2 * plane + o] = 1;
+        planes[o] = (int8_t)(v * v);
+        planes[plane + o] = 1;
+        planes[2 * plane + o] = (int8_t)v;
     }
 }
 
@@ -363,7 +378,11 @@ int32_t rs_prep_planes(rs_knn *h) {
     scatter_planes_kernel<<<blocks_for((int64_t)h->n_left * 32), T, 0, st>>>(h->l_ptr, h->l_col, h->l_code,
                                                                             h->n_left, h->tc_npad, h->tc_kpad,
                                                                             h->planes);
-    h->prof.total_launches++;
+    RS_TRY(rs_alloc(h, &h->row_cnt, (size_t)h->n_left + 1));
+    RS_TRY(rs_alloc(h, &h->row_sum, (size_t)h->n_left + 1));
+    row_isum_kernel<<<blocks_for((int64_t)h->n_left * 32), T, 0, st>>>(h->l_ptr, h->l_code, h->n_left, h->row_cnt,
+                                                                      h->row_sum);
+    h->prof.total_launches += 2;
     RS_CUDA(cudaGetLastError());
     return RS_OK;
 }

@@ -1,6 +1,503 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// sim_tensor.cu — the co-rated similarity as masked integer contractions on the 5th-gen
+// tensor cores (tcgen05.mma.kind::i8, int32 accumulators in TMEM), sm_100a only.
+//
+// For integer ratings every sum core/sim.go accumulates over the co-rated entries of two left
+// rows a, b is a dot product of int8 planes of the left matrix (X = rating, X2 = rating^2,
+// M = 1 where rated):
+//     count = M_a.M_b   Sx = X_a.M_b   Sy = M_a.X_b   Sxx = X2_a.M_b   Syy = M_a.X2_b   Sxy = X_a.X_b
+// The int32 accumulation is exact, so the FP64 epilogue reproduces the reference bit for bit
+// for Cosine (core/sim.go:10-25) and MSD (core/sim.go:28-44), whose Go sums are sums of small
+// integers.  Pearson from the sums is exact arithmetic on integers (see pearson_from_sums),
+// i.e. the correctly rounded value, but NOT the reference's rounding sequence; the bit-exact
+// Pearson is the stream path (sim_stream.cu).
+//
+// Kernel shape (one CTA per SM, persistent over a static tile list):
+//   tile      = 128 left rows (MMA M, TMEM lanes) x 64 left rows (MMA N) x all K
+//   operands  = planes laid out [plane][row][K] int8, K-major; TMA 3-D boxes (128 B of K x rows
+//               x 3 planes) with SWIZZLE_128B land one pipeline stage (48 KB A + 24 KB B)
+//   pipeline  = 3 smem stages, mbarrier full/empty ring; warp 0 lane 0 issues TMA, warp 1 lane 0
+//               issues tcgen05.mma, warps 2-5 run the epilogue (tcgen05.ld -> FP64 -> HBM)
+//   MMAs      = the B planes of a stage are adjacent in shared memory in the order (X2, M, X), so
+//               products that share an A plane are ONE instruction with a wider N:
+//                 Pearson: M_I x [X2|M|X]_J (N=192), X_I x [M|X]_J (N=128), X2_I x M_J (N=64)
+//                 MSD    : M_I x [X2|M]_J (N=128), X_I x X_J, X2_I x M_J
+//                 Cosine : M_I x X2_J, X_I x X_J, X2_I x M_J
+//   TMEM      = 192 / 256 / 384 accumulator columns; Cosine and MSD double-buffer them so the
+//               epilogue of tile t overlaps the MMAs of tile t+1
+//   schedule  = block-triangular: tile (bi,bj) runs iff bj >= 2*bi and writes both S[i][j] and
+//               S[j][i] (the similarities are bit-symmetric, core/knn.go:205-208); a row-sharded
+//               handle runs every bj for its own row blocks and writes S[i][j] only.
+#include <cuda.h>
+
 #include "common.cuh"
-int32_t rs_sim_tensor_launch(rs_knn *, int32_t *, int64_t, int64_t) {
-    rs_set_error("tensor path not built yet");
-    return RS_ERR_UNSUPPORTED;
+
+namespace {
+
+constexpr int BM = RS_TC_BM;   // 128
+constexpr int BN = RS_TC_BN;   // 64
+constexpr int BK = RS_TC_BK;   // 128 bytes of K per stage
+constexpr int STAGES = 3;
+constexpr int A_PLANE_BYTES = BM * BK;            // 16 KB
+constexpr int B_PLANE_BYTES = BN * BK;            // 8 KB
+constexpr int A_STAGE_BYTES = 3 * A_PLANE_BYTES;  // 48 KB
+constexpr int B_STAGE_BYTES = 3 * B_PLANE_BYTES;  // 24 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int TMEM_COLS = 512;
+
+// plane order in global and shared memory
+constexpr int PL_X2 = 0, PL_M = 1, PL_X = 2;
+
+enum { TC_COSINE = 0, TC_MSD = 1, TC_PEARSON = 2, TC_COSUMS = 3 };
+
+template <int MODE> struct Cfg;
+template <> struct Cfg<TC_COSINE> {
+    static constexpr int ACC_COLS = 192, ACC_STAGES = 2;
+    static constexpr int C_SYY = 0, C_SXY = 64, C_SXX = 128, C_CNT = -1, C_SX = -1, C_SY = -1;
+};
+template <> struct Cfg<TC_MSD> {
+    static constexpr int ACC_COLS = 256, ACC_STAGES = 2;
+    static constexpr int C_SYY = 0, C_CNT = 64, C_SXY = 128, C_SXX = 192, C_SX = -1, C_SY = -1;
+};
+template <> struct Cfg<TC_PEARSON> {
+    static constexpr int ACC_COLS = 384, ACC_STAGES = 1;
+    static constexpr int C_SYY = 0, C_CNT = 64, C_SY = 128, C_SX = 192, C_SXY = 256, C_SXX = 320;
+};
+template <> struct Cfg<TC_COSUMS> : Cfg<TC_PEARSON> {};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must trap loudly instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {  // ~2 s at 1.9 GHz
+            printf("sim_tensor_kernel: mbarrier timeout (role %d, block %d, thread %d)\n", who, blockIdx.x,
+                   threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], "
+        "[%5];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, int8 x int8 -> int32
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrive once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, int32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(addr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (one 128-byte swizzle atom along K,
+// 8-row groups 1024 B apart), sm_100 descriptor version 1.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address      bits [0,14)
+    d |= (uint64_t)0 << 16;                         // leading byte offset (unused: one atom along K)
+    d |= (uint64_t)(1024u >> 4) << 32;              // stride byte offset  bits [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version  bits [46,48)
+    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B        bits [61,64)
+    return d;
+}
+// kind::i8 instruction descriptor: D=S32, A=B=signed int8, both K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct TcArgs {
+    const int2 *tiles;      // (bi, bj) per tile
+    int32_t num_tiles;
+    int32_t k_blocks;       // K / 128
+    int32_t n_left;
+    int64_t row_begin, row_end;
+    int mirror;
+    double *sims;
+    int64_t ld_s;
+    const int32_t *row_cnt; // Pearson: ratings per left row, and their integer sum
+    const int32_t *row_sum;
+    int32_t *cosums;        // TC_COSUMS: raw sums of rows [cos_row0, cos_row0+cos_nrows)
+    int64_t cos_row0, cos_nrows;
+};
+
+// Pearson from exact integer sums.  With a-row count ca and sum sa (b: cb, sb) and n co-ratings:
+//   m  = sum (x-sa/ca)^2 = Mi/ca^2,  Mi = ca^2*Sxx - 2*ca*sa*Sx + n*sa^2          (integers)
+//   nn = Ni/cb^2,                    Ni = cb^2*Syy - 2*cb*sb*Sy + n*sb^2
+//   l  = L/(ca*cb),                  L  = ca*cb*Sxy - ca*sb*Sx - cb*sa*Sy + n*sa*sb
+//   l/(sqrt(m)*sqrt(nn)) = L/(sqrt(Mi)*sqrt(Ni))   — the counts cancel; Mi==0 <=> m==0 exactly,
+// so NaN-ness matches the reference's 0/0 (core/sim.go:80) with no cancellation noise.
+__device__ __forceinline__ double pearson_from_sums(long long n, long long sx, long long sy, long long sxx,
+                                                    long long syy, long long sxy, long long ca, long long sa,
+                                                    long long cb, long long sb) {
+    const long long Mi = ca * ca * sxx - 2 * ca * sa * sx + n * sa * sa;
+    const long long Ni = cb * cb * syy - 2 * cb * sb * sy + n * sb * sb;
+    const long long L = ca * cb * sxy - ca * sb * sx - cb * sa * sy + n * sa * sb;
+    return (double)L / (sqrt((double)Mi) * sqrt((double)Ni));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
+    using C = Cfg<MODE>;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B needs 1024-byte aligned tiles
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t full_bar = bars;                    // STAGES x 8 B
+    const uint32_t empty_bar = bars + 8 * STAGES;      // STAGES x 8 B
+    const uint32_t tfull_bar = bars + 16 * STAGES;     // 2 x 8 B   accumulator ready
+    const uint32_t tempty_bar = tfull_bar + 16;        // 2 x 8 B   accumulator drained
+    const uint32_t tmem_slot = tempty_bar + 16;        // 4 B       TMEM base address
+    uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + STAGES * STAGE_BYTES +
+                                                                              16 * STAGES + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(full_bar + 8 * s, 1);
+            mbar_init(empty_bar + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(tfull_bar + 8 * s, 1);
+            mbar_init(tempty_bar + 8 * s, 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ======================= TMA producer =======================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+                const int2 tile = a.tiles[t];
+                const int row_a = tile.x * BM, row_b = tile.y * BN;
+                for (int kb = 0; kb < a.k_blocks; kb++) {
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1u, 0);
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+                    mbar_arrive_expect_tx(full_bar + 8 * stage, STAGE_BYTES);
+                    tma_load_3d(sa, &map_a, kb * BK, row_a, 0, full_bar + 8 * stage);
+                    tma_load_3d(sb, &map_b, kb * BK, row_b, 0, full_bar + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+                mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1u, 1);   // epilogue drained this buffer
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * C::ACC_COLS);
+                for (int kb = 0; kb < a.k_blocks; kb++) {
+                    mbar_wait(full_bar + 8 * stage, phase, 2);        // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 32; k++) {
+                        const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+                        const uint32_t ko = (uint32_t)k * 32u;
+                        const uint64_t a_x2 = make_desc(sa + PL_X2 * A_PLANE_BYTES + ko);
+                        const uint64_t a_m = make_desc(sa + PL_M * A_PLANE_BYTES + ko);
+                        const uint64_t a_x = make_desc(sa + PL_X * A_PLANE_BYTES + ko);
+                        const uint64_t b_x2 = make_desc(sb + PL_X2 * B_PLANE_BYTES + ko);
+                        const uint64_t b_m = make_desc(sb + PL_M * B_PLANE_BYTES + ko);
+                        const uint64_t b_x = make_desc(sb + PL_X * B_PLANE_BYTES + ko);
+                        if constexpr (MODE == TC_COSINE) {
+                            umma_i8(d0 + C::C_SYY, a_m, b_x2, make_idesc(64), accum);
+                            umma_i8(d0 + C::C_SXY, a_x, b_x, make_idesc(64), accum);
+                            umma_i8(d0 + C::C_SXX, a_x2, b_m, make_idesc(64), accum);
+                        } else if constexpr (MODE == TC_MSD) {
+                            umma_i8(d0 + C::C_SYY, a_m, b_x2, make_idesc(128), accum);   // [Syy | count]
+                            umma_i8(d0 + C::C_SXY, a_x, b_x, make_idesc(64), accum);
+                            umma_i8(d0 + C::C_SXX, a_x2, b_m, make_idesc(64), accum);
+                        } else {
+                            umma_i8(d0 + C::C_SYY, a_m, b_x2, make_idesc(192), accum);   // [Syy | count | Sy]
+                            umma_i8(d0 + C::C_SX, a_x, b_m, make_idesc(128), accum);     // [Sx | Sxy]
+                            umma_i8(d0 + C::C_SXX, a_x2, b_m, make_idesc(64), accum);
+                        }
+                    }
+                    umma_commit(empty_bar + 8 * stage);               // frees the smem stage when done
+                    if (kb == a.k_blocks - 1) umma_commit(tfull_bar + 8 * acc);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ======================= epilogue (4 warps, TMEM lane quarter = warp % 4) =======================
+        const int q = warp & 3;
+        const int r_in_tile = q * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
+        for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+            const int2 tile = a.tiles[t];
+            const int64_t i = (int64_t)tile.x * BM + r_in_tile;
+            const int64_t j0 = (int64_t)tile.y * BN;
+            mbar_wait(tfull_bar + 8 * acc, acc_phase, 3);
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::ACC_COLS);
+            long long ca = 0, sa = 0;
+            if (MODE == TC_PEARSON && i < a.n_left) { ca = a.row_cnt[i]; sa = a.row_sum[i]; }
+            const bool row_ok = (i < a.n_left) && (i >= a.row_begin) && (i < a.row_end);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 8) {
+                int32_t v_syy[8], v_sxy[8], v_sxx[8], v_cnt[8], v_sx[8], v_sy[8];
+                tmem_ld8(tbase + C::C_SYY + c0, v_syy);
+                tmem_ld8(tbase + C::C_SXY + c0, v_sxy);
+                tmem_ld8(tbase + C::C_SXX + c0, v_sxx);
+                if (C::C_CNT >= 0) tmem_ld8(tbase + (C::C_CNT >= 0 ? C::C_CNT : 0) + c0, v_cnt);
+                if (C::C_SX >= 0) {
+                    tmem_ld8(tbase + (C::C_SX >= 0 ? C::C_SX : 0) + c0, v_sx);
+                    tmem_ld8(tbase + (C::C_SY >= 0 ? C::C_SY : 0) + c0, v_sy);
+                }
+                tmem_ld_wait();
+                if constexpr (MODE == TC_COSUMS) {
+                    const int64_t r = i - a.cos_row0;
+                    if (i < a.n_left && r >= 0 && r < a.cos_nrows) {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            const int64_t j = j0 + c0 + c;
+                            if (j < a.n_left) {
+                                int32_t *o = a.cosums + (r * a.n_left + j) * 6;
+                                o[0] = v_cnt[c]; o[1] = v_sx[c]; o[2] = v_sy[c];
+                                o[3] = v_sxx[c]; o[4] = v_syy[c]; o[5] = v_sxy[c];
+                            }
+                        }
+                    }
+                } else {
+                double s[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const int64_t j = j0 + c0 + c;
+                    if constexpr (MODE == TC_COSINE) {
+                        // core/sim.go:24  l / (sqrt(m) * sqrt(n)),  m = Sxx, n = Syy, l = Sxy
+                        s[c] = (double)v_sxy[c] / (sqrt((double)v_sxx[c]) * sqrt((double)v_syy[c]));
+                    } else if constexpr (MODE == TC_MSD) {
+                        // core/sim.go:43  1 / (sum/count + 1),  sum = Sxx - 2 Sxy + Syy (exact integer)
+                        const int32_t sum = v_sxx[c] - 2 * v_sxy[c] + v_syy[c];
+                        s[c] = 1.0 / ((double)sum / (double)v_cnt[c] + 1.0);
+                    } else {
+                        long long cb = 0, sb = 0;
+                        if (j < a.n_left) { cb = a.row_cnt[j]; sb = a.row_sum[j]; }
+                        s[c] = pearson_from_sums(v_cnt[c], v_sx[c], v_sy[c], v_sxx[c], v_syy[c], v_sxy[c], ca, sa,
+                                                 cb, sb);
+                    }
+                    if (j == i) s[c] = nan_v;   // diagonal stays unset (core/knn.go:202)
+                }
+                // S[i][j0+c0 .. +8): 64 contiguous bytes per thread
+                if (row_ok) {
+                    double *o = a.sims + (i - a.row_begin) * a.ld_s + j0 + c0;
+                    if (j0 + c0 + 8 <= a.n_left) {
+#pragma unroll
+                        for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2 *>(o + c) = make_double2(s[c], s[c + 1]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) if (j0 + c0 + c < a.n_left) o[c] = s[c];
+                    }
+                }
+                // mirrored S[j][i]: for a fixed j the 32 lanes write 32 consecutive doubles
+                if (a.mirror && i < a.n_left) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const int64_t j = j0 + c0 + c;
+                        if (j < a.n_left) a.sims[j * a.ld_s + i] = s[c];
+                    }
+                }
+                }  // !COSUMS
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar + 8 * acc);     // 128 arrivals release the accumulator buffer
+            if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int32_t get_encode_fn(EncodeTiledFn *out) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        RS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !p) {
+            rs_set_error("cuTensorMapEncodeTiled is not available from the driver");
+            return RS_ERR_CUDA;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    *out = fn;
+    return RS_OK;
+}
+
+int32_t make_map(const rs_knn *h, int box_rows, CUtensorMap *map) {
+    EncodeTiledFn enc;
+    RS_TRY(get_encode_fn(&enc));
+    const cuuint64_t dims[3] = {(cuuint64_t)h->tc_kpad, (cuuint64_t)h->tc_npad, 3};
+    const cuuint64_t strides[2] = {(cuuint64_t)h->tc_kpad, (cuuint64_t)h->tc_kpad * (cuuint64_t)h->tc_npad};
+    const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 3};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->planes, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        rs_set_error("cuTensorMapEncodeTiled failed with CUresult %d (npad=%lld kpad=%lld)", (int)r,
+                     (long long)h->tc_npad, (long long)h->tc_kpad);
+        return RS_ERR_CUDA;
+    }
+    return RS_OK;
+}
+
+template <int MODE>
+int32_t launch_mode(rs_knn *h, const CUtensorMap &ma, const CUtensorMap &mb, const TcArgs &a, int grid) {
+    auto kern = sim_tensor_kernel<MODE>;
+    RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    kern<<<grid, NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, a);
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
+}  // namespace
+
+int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int64_t cos_nrows) {
+    if (!h->planes) {
+        rs_set_error("tensor path: int8 planes were not built");
+        return RS_ERR_INVALID;
+    }
+    const bool cosums = d_cosums != nullptr;
+    const int64_t rb = cosums ? cos_row0 : h->row_begin;
+    const int64_t re = cosums ? cos_row0 + cos_nrows : h->row_end;
+    if (re <= rb) return RS_OK;
+    const bool mirror = !cosums && rb == 0 && re == h->n_left;
+    const int nbj = (int)((h->n_left + BN - 1) / BN);
+    const int bi0 = (int)(rb / BM), bi1 = (int)((re + BM - 1) / BM);
+    std::vector<int2> tiles;
+    for (int bi = bi0; bi < bi1; bi++)
+        for (int bj = mirror ? 2 * bi : 0; bj < nbj; bj++) tiles.push_back(make_int2(bi, bj));
+    if (tiles.empty()) return RS_OK;
+    int2 *d_tiles;
+    RS_TRY(rs_alloc(h, &d_tiles, tiles.size()));
+    RS_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    RS_CUDA(cudaStreamSynchronize(h->stream));  // `tiles` is a pageable temporary
+
+    CUtensorMap ma, mb;
+    RS_TRY(make_map(h, BM, &ma));
+    RS_TRY(make_map(h, BN, &mb));
+
+    TcArgs a{};
+    a.tiles = d_tiles;
+    a.num_tiles = (int32_t)tiles.size();
+    a.k_blocks = (int32_t)(h->tc_kpad / BK);
+    a.n_left = h->n_left;
+    a.row_begin = rb;
+    a.row_end = re;
+    a.mirror = mirror ? 1 : 0;
+    a.sims = h->sims;
+    a.ld_s = h->ld_s;
+    a.row_cnt = h->row_cnt;
+    a.row_sum = h->row_sum;
+    a.cosums = d_cosums;
+    a.cos_row0 = cos_row0;
+    a.cos_nrows = cos_nrows;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+    int32_t rc;
+    if (cosums) rc = launch_mode<TC_COSUMS>(h, ma, mb, a, grid);
+    else if (h->p.sim == RS_SIM_COSINE) rc = launch_mode<TC_COSINE>(h, ma, mb, a, grid);
+    else if (h->p.sim == RS_SIM_MSD) rc = launch_mode<TC_MSD>(h, ma, mb, a, grid);
+    else if (h->p.sim == RS_SIM_PEARSON) rc = launch_mode<TC_PEARSON>(h, ma, mb, a, grid);
+    else {
+        rs_set_error("tensor path supports Cosine, MSD and Pearson (sums mode) only");
+        return RS_ERR_UNSUPPORTED;
+    }
+    RS_TRY(rc);
+    if (!cosums) h->prof.sim_launches++;
+    h->prof.total_launches++;
+    return RS_OK;
 }
