@@ -255,7 +255,8 @@ def run_ours(args, rank, world, local_rank):
         t_left, t_right = t_left[mine], t_right[mine]
     n_pred = len(t_left)
 
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)   # a dedicated (non-default) stream for the whole bench
+    torch.cuda.set_stream(stream)
     h = rs.core._Handle(sim=sim, knn_type=knn_type, k=k, device=local_rank, row_begin=rb, row_end=re,
                         store="topk" if (shard and not n_test) else "matrix", topk=k,
                         pearson_mode=args.pearson_mode, sim_path=args.sim_path)

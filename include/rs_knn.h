@@ -111,9 +111,10 @@ int32_t rs_knn_create(const rs_knn_params *p, rs_knn **out);
  * round-trip in Copy (core/dump.go:37-43) never sees it. */
 int32_t rs_knn_destroy(rs_knn *h);
 
-/* Run all of this handle's work on `cuda_stream` (a cudaStream_t / CUstream), e.g. the
- * caller's current stream.  NULL = the handle's own stream. */
-int32_t rs_knn_set_stream(rs_knn *h, void *cuda_stream);
+/* Run all of this handle's work on `cuda_stream` (a cudaStream_t / CUstream; NULL is the
+ * legacy default stream), e.g. the caller's current stream.  use_own != 0 switches back to
+ * the non-blocking stream the handle created for itself (the default). */
+int32_t rs_knn_set_stream(rs_knn *h, void *cuda_stream, int32_t use_own);
 
 /* Replaces KNN.Fit (core/knn.go:143-217) after the Go side has built the inner-id COO:
  * left[i], right[i], rating[i] for i in dataset order (the order matters: Means/StdDevs are

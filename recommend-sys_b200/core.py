@@ -86,7 +86,7 @@ def knn_lib():
     L.rs_knn_params_default.argtypes = [C.POINTER(RsKnnParams)]
     L.rs_knn_create.argtypes = [C.POINTER(RsKnnParams), C.POINTER(vp)]
     L.rs_knn_destroy.argtypes = [vp]
-    L.rs_knn_set_stream.argtypes = [vp, vp]
+    L.rs_knn_set_stream.argtypes = [vp, vp, i32]
     L.rs_knn_fit.argtypes = [vp, vp, vp, vp, i64, i32, i32, dbl, vp, vp, dbl]
     L.rs_knn_fit_device.argtypes = [vp, vp, vp, vp, i64, i32, i32, dbl, vp, vp, dbl]
     L.rs_knn_predict_batch.argtypes = [vp, vp, vp, i64, vp]
@@ -403,8 +403,9 @@ class _Handle:
 
     __del__ = close
 
-    def set_stream(self, stream_ptr):
-        _check(knn_lib().rs_knn_set_stream(self.h, C.c_void_p(stream_ptr)))
+    def set_stream(self, stream_ptr, use_own=False):
+        """stream_ptr: a cudaStream_t as an int (0 = the legacy default stream)."""
+        _check(knn_lib().rs_knn_set_stream(self.h, C.c_void_p(stream_ptr), int(use_own)))
 
     def fit(self, left, right, rating, n_left, n_right, global_mean, left_bias=None, right_bias=None,
             global_bias=0.0):

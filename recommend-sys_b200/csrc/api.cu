@@ -27,9 +27,10 @@ int32_t enter(rs_knn *h) {
     return RS_OK;
 }
 
+// Forget the fitted state; the arena's chunks are kept for the next Fit.
 void free_fit_state(rs_knn *h) {
-    for (void *p : h->allocs) cudaFree(p);
-    h->allocs.clear();
+    h->cur_chunk = 0;
+    h->cur_off = 0;
     h->fitted = false;
     h->l_ptr = h->r_ptr = nullptr;
     h->l_col = h->r_col = nullptr;
@@ -156,6 +157,9 @@ int32_t rs_knn_destroy(rs_knn *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     free_fit_state(h);
+    for (auto &c : h->chunks) cudaFree(c.p);
+    h->chunks.clear();
+    if (h->tile_buf) cudaFree(h->tile_buf);
     for (void *p : h->scratch) cudaFree(p);
     cudaEventDestroy(h->ev_a);
     cudaEventDestroy(h->ev_b);
@@ -167,10 +171,11 @@ int32_t rs_knn_destroy(rs_knn *h) {
     return RS_OK;
 }
 
-int32_t rs_knn_set_stream(rs_knn *h, void *cuda_stream) {
+int32_t rs_knn_set_stream(rs_knn *h, void *cuda_stream, int32_t use_own) {
     RS_TRY(enter(h));
     RS_CUDA(cudaStreamSynchronize(h->stream));
-    h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    // NULL is a real stream (the legacy default stream), so "own" needs its own flag
+    h->stream = use_own ? h->own_stream : reinterpret_cast<cudaStream_t>(cuda_stream);
     return RS_OK;
 }
 
@@ -277,6 +282,28 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
     return RS_OK;
 }
 
+static int32_t scratch_get(rs_knn *h, int slot, size_t bytes, void **out) {
+    if (h->scratch.size() <= (size_t)slot) {
+        h->scratch.resize(slot + 1, nullptr);
+        h->scratch_bytes.resize(slot + 1, 0);
+    }
+    if (h->scratch_bytes[slot] < bytes) {
+        if (h->scratch[slot]) cudaFree(h->scratch[slot]);
+        h->scratch[slot] = nullptr;
+        h->scratch_bytes[slot] = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&h->scratch[slot], want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            rs_set_error("cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+            return RS_ERR_OOM;
+        }
+        h->scratch_bytes[slot] = want;
+    }
+    *out = h->scratch[slot];
+    return RS_OK;
+}
+
 int32_t rs_knn_fit(rs_knn *h, const int32_t *left, const int32_t *right, const double *rating, int64_t nnz,
                    int32_t n_left, int32_t n_right, double global_mean, const double *left_bias,
                    const double *right_bias, double global_bias) {
@@ -286,46 +313,33 @@ int32_t rs_knn_fit(rs_knn *h, const int32_t *left, const int32_t *right, const d
                      n_right);
         return RS_ERR_INVALID;
     }
-    int32_t *d_left = nullptr, *d_right = nullptr;
-    double *d_rating = nullptr, *d_lb = nullptr, *d_rb = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(d_left); cudaFree(d_right); cudaFree(d_rating); cudaFree(d_lb); cudaFree(d_rb);
-    };
-#define FIT_CUDA(expr)                                                                              \
-    do {                                                                                            \
-        cudaError_t e_ = (expr);                                                                    \
-        if (e_ != cudaSuccess) {                                                                    \
-            rs_set_error("%s: %s", #expr, cudaGetErrorString(e_));                                  \
-            cleanup();                                                                              \
-            return e_ == cudaErrorMemoryAllocation ? RS_ERR_OOM : RS_ERR_CUDA;                      \
-        }                                                                                           \
-    } while (0)
-    FIT_CUDA(cudaMalloc(&d_left, (size_t)nnz * 4));
-    FIT_CUDA(cudaMalloc(&d_right, (size_t)nnz * 4));
-    FIT_CUDA(cudaMalloc(&d_rating, (size_t)nnz * 8));
-    FIT_CUDA(cudaMemcpyAsync(d_left, left, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
-    FIT_CUDA(cudaMemcpyAsync(d_right, right, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
-    FIT_CUDA(cudaMemcpyAsync(d_rating, rating, (size_t)nnz * 8, cudaMemcpyHostToDevice, h->stream));
+    // persistent device staging (grow-only): a refit of the same size allocates nothing
+    void *d_left, *d_right, *d_rating, *d_lb = nullptr, *d_rb = nullptr;
+    RS_TRY(scratch_get(h, 7, (size_t)nnz * 4, &d_left));
+    RS_TRY(scratch_get(h, 8, (size_t)nnz * 4, &d_right));
+    RS_TRY(scratch_get(h, 9, (size_t)nnz * 8, &d_rating));
+    RS_CUDA(cudaMemcpyAsync(d_left, left, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
+    RS_CUDA(cudaMemcpyAsync(d_right, right, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
+    RS_CUDA(cudaMemcpyAsync(d_rating, rating, (size_t)nnz * 8, cudaMemcpyHostToDevice, h->stream));
     if (left_bias) {
-        FIT_CUDA(cudaMalloc(&d_lb, (size_t)n_left * 8));
-        FIT_CUDA(cudaMemcpyAsync(d_lb, left_bias, (size_t)n_left * 8, cudaMemcpyHostToDevice, h->stream));
+        RS_TRY(scratch_get(h, 10, (size_t)n_left * 8, &d_lb));
+        RS_CUDA(cudaMemcpyAsync(d_lb, left_bias, (size_t)n_left * 8, cudaMemcpyHostToDevice, h->stream));
     }
     if (right_bias) {
-        FIT_CUDA(cudaMalloc(&d_rb, (size_t)n_right * 8));
-        FIT_CUDA(cudaMemcpyAsync(d_rb, right_bias, (size_t)n_right * 8, cudaMemcpyHostToDevice, h->stream));
+        RS_TRY(scratch_get(h, 11, (size_t)n_right * 8, &d_rb));
+        RS_CUDA(cudaMemcpyAsync(d_rb, right_bias, (size_t)n_right * 8, cudaMemcpyHostToDevice, h->stream));
     }
-    int32_t rc = rs_knn_fit_device(h, d_left, d_right, d_rating, nnz, n_left, n_right, global_mean, d_lb, d_rb,
-                                   global_bias);
-    cudaError_t e = cudaStreamSynchronize(h->stream);  // inputs are borrowed only for the call
-    cleanup();
-    if (rc != RS_OK) return rc;
+    RS_TRY(rs_knn_fit_device(h, (const int32_t *)d_left, (const int32_t *)d_right, (const double *)d_rating, nnz,
+                             n_left, n_right, global_mean, (const double *)d_lb, (const double *)d_rb,
+                             global_bias));
+    // the inputs are borrowed for the duration of the call only
+    cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) {
         rs_set_error("rs_knn_fit: %s", cudaGetErrorString(e));
         h->fitted = false;
         return RS_ERR_CUDA;
     }
     return RS_OK;
-#undef FIT_CUDA
 }
 
 static int32_t require_matrix(rs_knn *h, const char *who) {
@@ -354,28 +368,6 @@ int32_t rs_knn_predict_batch_device(rs_knn *h, const int32_t *d_left, const int3
     RS_TRY(rs_predict_launch(h, d_left, d_right, n, d_out, nullptr, nullptr, nullptr, 0));
     RS_CUDA(cudaEventRecord(h->ev_e, h->stream));
     h->pred_pending = true;
-    return RS_OK;
-}
-
-static int32_t scratch_get(rs_knn *h, int slot, size_t bytes, void **out) {
-    if (h->scratch.size() <= (size_t)slot) {
-        h->scratch.resize(slot + 1, nullptr);
-        h->scratch_bytes.resize(slot + 1, 0);
-    }
-    if (h->scratch_bytes[slot] < bytes) {
-        if (h->scratch[slot]) cudaFree(h->scratch[slot]);
-        h->scratch[slot] = nullptr;
-        h->scratch_bytes[slot] = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&h->scratch[slot], want);
-        if (e != cudaSuccess) {
-            (void)cudaGetLastError();
-            rs_set_error("cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
-            return RS_ERR_OOM;
-        }
-        h->scratch_bytes[slot] = want;
-    }
-    *out = h->scratch[slot];
     return RS_OK;
 }
 

@@ -62,7 +62,16 @@ struct rs_knn {
     int rating_class = RS_CLASS_INT8;
     int n_codes = 0;
 
-    std::vector<void *> allocs;  // everything Fit allocated (freed on refit / destroy)
+    // Grow-only device arena: Fit bump-allocates from it and the next Fit reuses the same
+    // chunks, so a refit of the same shape performs no cudaMalloc / cudaFree at all.
+    struct Chunk { char *p; size_t bytes; };
+    std::vector<Chunk> chunks;
+    size_t cur_chunk = 0, cur_off = 0;
+    // cached tensor-path tile list
+    void *tile_buf = nullptr;
+    size_t tile_buf_bytes = 0;
+    int64_t tile_key[4] = {-1, -1, -1, -1};
+    int32_t tile_count = 0;
 
     // CSR of the left rows, entries ascending by right id (core/data.go:236-243)
     int64_t *l_ptr = nullptr;

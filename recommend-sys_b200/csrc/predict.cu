@@ -46,6 +46,56 @@ __device__ void warp_bitonic(uint64_t *keys, uint32_t *pos, int n_pad, int lane)
     __syncwarp();
 }
 
+
+// ---- fast path: all candidates of one prediction live in registers (R per lane, blocked
+// layout e = lane*R + x) and are ordered by a warp-wide bitonic network: strides < R are
+// in-register compare-exchanges, strides >= R are __shfl_xor exchanges.  No shared memory.
+template <int R>
+__device__ __forceinline__ void ce_regs(uint64_t (&key)[R], uint32_t (&pos)[R], int i, int j, bool up) {
+    // order (i, j), i < j: "before" element first when up
+    const bool j_before_i = rec_before(key[j], pos[j], key[i], pos[i]);
+    if (j_before_i == up) {
+        const uint64_t tk = key[i]; key[i] = key[j]; key[j] = tk;
+        const uint32_t tp = pos[i]; pos[i] = pos[j]; pos[j] = tp;
+    }
+}
+
+template <int R, int STRIDE>
+__device__ __forceinline__ void stage_regs(uint64_t (&key)[R], uint32_t (&pos)[R], int lane, int size) {
+#pragma unroll
+    for (int x = 0; x < R; x++) {
+        if ((x & STRIDE) == 0) {
+            const bool up = (((lane * R + x) & size) == 0);
+            ce_regs<R>(key, pos, x, x | STRIDE, up);
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void warp_sort_regs(uint64_t (&key)[R], uint32_t (&pos)[R], int lane) {
+#pragma unroll 1
+    for (int size = 2; size <= 32 * R; size <<= 1) {
+#pragma unroll 1
+        for (int stride = size >> 1; stride >= R; stride >>= 1) {
+            const int lm = stride / R;  // lane xor mask
+            const bool lower = (lane & lm) == 0;
+#pragma unroll
+            for (int x = 0; x < R; x++) {
+                const bool up = (((lane * R + x) & size) == 0);
+                const uint64_t ok = __shfl_xor_sync(0xffffffffu, key[x], lm);
+                const uint32_t op = __shfl_xor_sync(0xffffffffu, pos[x], lm);
+                const bool other_before = rec_before(ok, op, key[x], pos[x]);
+                // the lower index of the pair keeps the "before" element when the run is up
+                if (other_before == (up == lower)) { key[x] = ok; pos[x] = op; }
+            }
+        }
+        if (R >= 16 && size >= 16) stage_regs<R, (R >= 16 ? 8 : 0)>(key, pos, lane, size);
+        if (R >= 8 && size >= 8) stage_regs<R, (R >= 8 ? 4 : 0)>(key, pos, lane, size);
+        if (R >= 4 && size >= 4) stage_regs<R, (R >= 4 ? 2 : 0)>(key, pos, lane, size);
+        if (R >= 2) stage_regs<R, (R >= 2 ? 1 : 0)>(key, pos, lane, size);
+    }
+}
+
 struct PredArgs {
     const int32_t *left, *right;
     int64_t n;
@@ -65,6 +115,78 @@ struct PredArgs {
     int32_t *nb_count;
     int32_t nb_cap;
 };
+
+template <int R>
+__device__ __forceinline__ void predict_regs(const PredArgs &a, int64_t p, int32_t l, const double *row, int64_t cb,
+                                             int cnt, int lane);
+
+template <int R>
+__device__ __forceinline__ void predict_regs(const PredArgs &a, int64_t p, int32_t l, const double *row, int64_t cb,
+                                             int cnt, int lane) {
+    uint64_t key[R];
+    uint32_t pos[R];
+    int mine = 0;
+#pragma unroll
+    for (int x = 0; x < R; x++) {
+        const int e = lane * R + x;
+        key[x] = 0;
+        pos[x] = 0xffffffffu;
+        if (e < cnt) {
+            const double s = row[a.r_col[cb + e]];
+            if (s == s) { key[x] = rs_sim_key(s); pos[x] = (uint32_t)e; mine++; }
+        }
+    }
+    int valid = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+    if (valid <= a.min_k) {                                  // core/knn.go:102-104 (note <=)
+        if (lane == 0) a.out[p] = a.global_mean;
+        return;
+    }
+    warp_sort_regs<R>(key, pos, lane);
+    const int num = a.k < valid ? a.k : valid;                // core/knn.go:111-114
+    // neighbour e sits in lane e / R, register e % R
+    double sv[R], av[R];
+#pragma unroll
+    for (int x = 0; x < R; x++) {
+        const int e = lane * R + x;
+        sv[x] = 0.0;
+        av[x] = 0.0;
+        if (e < num) {
+            const int64_t xx = cb + pos[x];
+            const int32_t id = a.r_col[xx];
+            const double s = row[id];
+            double rating = a.r_val[xx];
+            if (a.knn_type == RS_KNN_CENTERED) rating -= a.means[id];                           // core/knn.go:121
+            else if (a.knn_type == RS_KNN_ZSCORE) rating = (rating - a.means[id]) / a.stddevs[id];
+            else if (a.knn_type == RS_KNN_BASELINE) rating -= a.bias[id];
+            sv[x] = s;
+            av[x] = rating;
+            if (a.nb_ids && e < a.nb_cap) { a.nb_ids[e] = id; a.nb_sims[e] = s; }
+        }
+    }
+    double wsum = 0.0, wrat = 0.0;
+    const int lanes_used = (num + R - 1) / R;
+    for (int src = 0; src < lanes_used; src++) {
+#pragma unroll
+        for (int x = 0; x < R; x++) {
+            const double sq = __shfl_sync(0xffffffffu, sv[x], src);
+            const double aq = __shfl_sync(0xffffffffu, av[x], src);
+            if (src * R + x < num) {
+                wsum += sq;                                    // core/knn.go:117
+                wrat += sq * aq;                               // core/knn.go:127
+            }
+        }
+    }
+    if (lane == 0) {
+        double pred = wrat / wsum;                             // core/knn.go:131
+        if (a.knn_type == RS_KNN_CENTERED) pred += a.means[l];
+        else if (a.knn_type == RS_KNN_BASELINE) pred += a.bias[l];
+        else if (a.knn_type == RS_KNN_ZSCORE) { pred *= a.stddevs[l]; pred += a.means[l]; }
+        a.out[p] = pred;
+        if (a.nb_count) *a.nb_count = num < a.nb_cap ? num : a.nb_cap;
+    }
+}
 
 __global__ void __launch_bounds__(PRED_WARPS * 32) predict_kernel(PredArgs a) {
     __shared__ uint64_t s_keys[PRED_WARPS][PRED_CAP];
@@ -88,6 +210,12 @@ __global__ void __launch_bounds__(PRED_WARPS * 32) predict_kernel(PredArgs a) {
         }
         const double *row = a.sims + (l - a.row_begin) * a.ld_s;
         const int64_t cb = a.r_ptr[r], ce = a.r_ptr[r + 1];
+        const int64_t cnt64 = ce - cb;
+        if (cnt64 <= 32) { predict_regs<1>(a, p, l, row, cb, (int)cnt64, lane); continue; }
+        if (cnt64 <= 64) { predict_regs<2>(a, p, l, row, cb, (int)cnt64, lane); continue; }
+        if (cnt64 <= 128) { predict_regs<4>(a, p, l, row, cb, (int)cnt64, lane); continue; }
+        if (cnt64 <= 256) { predict_regs<8>(a, p, l, row, cb, (int)cnt64, lane); continue; }
+        if (cnt64 <= 512) { predict_regs<16>(a, p, l, row, cb, (int)cnt64, lane); continue; }
         const int keep = a.k < PRED_CAP / 2 ? a.k : PRED_CAP / 2;
 
         // ---- gather + filter; keep the best `keep` so far in keys[0..have) ----

@@ -12,15 +12,30 @@
 #include "common.cuh"
 
 int32_t rs_dev_alloc(rs_knn *h, void **out, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    while (h->cur_chunk < h->chunks.size()) {
+        rs_knn::Chunk &c = h->chunks[h->cur_chunk];
+        if (h->cur_off + bytes <= c.bytes) {
+            *out = c.p + h->cur_off;
+            h->cur_off += bytes;
+            return RS_OK;
+        }
+        h->cur_chunk++;
+        h->cur_off = 0;
+    }
+    const size_t min_chunk = (size_t)64 << 20;
+    const size_t want = bytes > min_chunk ? bytes : min_chunk;
     void *p = nullptr;
-    if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMalloc(&p, bytes);
+    cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {
-        rs_set_error("cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+        rs_set_error("cudaMalloc(%zu bytes): %s", want, cudaGetErrorString(e));
         (void)cudaGetLastError();
         return e == cudaErrorMemoryAllocation ? RS_ERR_OOM : RS_ERR_CUDA;
     }
-    h->allocs.push_back(p);
+    h->chunks.push_back({(char *)p, want});
+    h->cur_chunk = h->chunks.size() - 1;
+    h->cur_off = bytes;
     *out = p;
     return RS_OK;
 }
@@ -114,43 +129,6 @@ __global__ void code_table_kernel(const double *__restrict__ val, int64_t nnz, c
     code[i] = (uint8_t)(lo + 1);
 }
 
-// One thread per left row, strictly sequential sums in the reference's order.
-__global__ void row_stats_kernel(const int64_t *__restrict__ l_ptr, const double *__restrict__ ld_val,
-                                 const double *__restrict__ l_val, int32_t n_left, int want_std,
-                                 double *__restrict__ means, double *__restrict__ stddevs,
-                                 double *__restrict__ pmeans) {
-    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_left) return;
-    int64_t b = l_ptr[i], e = l_ptr[i + 1];
-    double sum = 0.0, count = 0.0;
-    for (int64_t x = b; x < e; x++) { sum += ld_val[x]; count += 1.0; }   // core/data.go:226-232
-    double mean = sum / count;
-    means[i] = mean;
-    if (want_std) {
-        double s2 = 0.0, c2 = 0.0;
-        for (int64_t x = b; x < e; x++) {                                 // core/knn.go:170-175
-            double r = ld_val[x];
-            s2 += (r - mean) * (r - mean);
-            c2 += 1.0;
-        }
-        stddevs[i] = sqrt(s2 / c2) + 1e-5;
-    }
-    double psum = 0.0, pcount = 0.0;
-    for (int64_t x = b; x < e; x++) { psum += l_val[x]; pcount += 1.0; }  // core/sim.go:49-54
-    pmeans[i] = psum / pcount;
-}
-
-__global__ void scatter_rt_kernel(const int64_t *__restrict__ l_ptr, const int32_t *__restrict__ l_col,
-                                  const uint8_t *__restrict__ l_code, int32_t n_left, int64_t ld_rt,
-                                  uint8_t *__restrict__ rt) {
-    // one warp per left row
-    int32_t row = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    int lane = threadIdx.x & 31;
-    if (row >= n_left) return;
-    for (int64_t x = l_ptr[row] + lane; x < l_ptr[row + 1]; x += 32)
-        rt[(int64_t)l_col[x] * ld_rt + row] = l_code[x];
-}
-
 __global__ void row_isum_kernel(const int64_t *__restrict__ l_ptr, const uint8_t *__restrict__ l_code,
                                 int32_t n_left, int32_t *__restrict__ row_cnt, int32_t *__restrict__ row_sum) {
     int32_t row = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -163,6 +141,67 @@ __global__ void row_isum_kernel(const int64_t *__restrict__ l_ptr, const uint8_t
         row_cnt[row] = (int32_t)(l_ptr[row + 1] - l_ptr[row]);
         row_sum[row] = s;
     }
+}
+
+// Row statistics in the reference's order.  One warp per left row: the lanes load 32 entries
+// at a time (coalesced) and the additions are then applied one after the other through
+// shuffles, so every sum sees exactly the reference's sequence of IEEE additions:
+//   means   core/data.go:226-232   (dataset order)
+//   stddevs core/knn.go:170-175    (dataset order)
+//   pmeans  core/sim.go:49-54      (ascending id order, the row after `sorts`)
+__device__ __forceinline__ double ordered_sum(const double *__restrict__ v, int64_t b, int64_t e, int lane,
+                                              double mean, bool squared_dev) {
+    double sum = 0.0;
+    for (int64_t base = b; base < e; base += 32) {
+        double x = (base + lane < e) ? v[base + lane] : 0.0;
+        if (squared_dev) x = (x - mean) * (x - mean);
+        const int lim = (e - base) < 32 ? (int)(e - base) : 32;
+        for (int q = 0; q < lim; q++) sum += __shfl_sync(0xffffffffu, x, q);
+    }
+    return sum;
+}
+
+__global__ void row_stats_ordered_kernel(const int64_t *__restrict__ l_ptr, const double *__restrict__ ld_val,
+                                         const double *__restrict__ l_val, int32_t n_left, int want_mean,
+                                         int want_std, double *__restrict__ means, double *__restrict__ stddevs,
+                                         double *__restrict__ pmeans) {
+    const int32_t i = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= n_left) return;
+    const int64_t b = l_ptr[i], e = l_ptr[i + 1];
+    const double count = (double)(e - b);
+    double mean = means[i];
+    if (want_mean) {
+        mean = ordered_sum(ld_val, b, e, lane, 0.0, false) / count;
+        const double pm = ordered_sum(l_val, b, e, lane, 0.0, false) / count;
+        if (lane == 0) { means[i] = mean; pmeans[i] = pm; }
+    }
+    if (want_std) {
+        const double s2 = ordered_sum(ld_val, b, e, lane, mean, true);
+        if (lane == 0) stddevs[i] = sqrt(s2 / count) + 1e-5;
+    }
+}
+
+// Integer ratings: every partial sum is an exact integer < 2^53, so sum/count is the same
+// double in any order — computed from the exact integer row sum.
+__global__ void means_from_isum_kernel(const int32_t *__restrict__ row_cnt, const int32_t *__restrict__ row_sum,
+                                       int32_t n_left, double *__restrict__ means, double *__restrict__ pmeans) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_left) return;
+    const double m = (double)row_sum[i] / (double)row_cnt[i];
+    means[i] = m;
+    pmeans[i] = m;
+}
+
+__global__ void scatter_rt_kernel(const int64_t *__restrict__ l_ptr, const int32_t *__restrict__ l_col,
+                                  const uint8_t *__restrict__ l_code, int32_t n_left, int64_t ld_rt,
+                                  uint8_t *__restrict__ rt) {
+    // one warp per left row
+    int32_t row = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= n_left) return;
+    for (int64_t x = l_ptr[row] + lane; x < l_ptr[row + 1]; x += 32)
+        rt[(int64_t)l_col[x] * ld_rt + row] = l_code[x];
 }
 
 // planes[p][row][col]: p=0 rating^2, p=1 mask, p=2 rating (the order the MMAs of sim_tensor.cu
@@ -330,10 +369,20 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     RS_TRY(rs_alloc(h, &h->means, (size_t)nl + 1));
     RS_TRY(rs_alloc(h, &h->stddevs, (size_t)nl + 1));
     RS_TRY(rs_alloc(h, &h->pmeans, (size_t)nl + 1));
-    row_stats_kernel<<<blocks_for(nl, 128), 128, 0, st>>>(h->l_ptr, h->ld_val, h->l_val, nl,
-                                                         h->p.knn_type == RS_KNN_ZSCORE, h->means, h->stddevs,
-                                                         h->pmeans);
-    h->prof.total_launches++;
+    const int want_std = h->p.knn_type == RS_KNN_ZSCORE;
+    if (h->rating_class == RS_CLASS_INT8) {
+        RS_TRY(rs_alloc(h, &h->row_cnt, (size_t)nl + 1));
+        RS_TRY(rs_alloc(h, &h->row_sum, (size_t)nl + 1));
+        row_isum_kernel<<<blocks_for((int64_t)nl * 32), T, 0, st>>>(h->l_ptr, h->l_code, nl, h->row_cnt, h->row_sum);
+        means_from_isum_kernel<<<blocks_for(nl), T, 0, st>>>(h->row_cnt, h->row_sum, nl, h->means, h->pmeans);
+        h->prof.total_launches += 2;
+    }
+    if (h->rating_class != RS_CLASS_INT8 || want_std) {
+        row_stats_ordered_kernel<<<blocks_for((int64_t)nl * 32), T, 0, st>>>(
+            h->l_ptr, h->ld_val, h->l_val, nl, h->rating_class != RS_CLASS_INT8, want_std, h->means, h->stddevs,
+            h->pmeans);
+        h->prof.total_launches++;
+    }
 
     if (d_left_bias) {
         RS_TRY(rs_alloc(h, &h->left_bias, (size_t)nl + 1));
@@ -378,11 +427,7 @@ int32_t rs_prep_planes(rs_knn *h) {
     scatter_planes_kernel<<<blocks_for((int64_t)h->n_left * 32), T, 0, st>>>(h->l_ptr, h->l_col, h->l_code,
                                                                             h->n_left, h->tc_npad, h->tc_kpad,
                                                                             h->planes);
-    RS_TRY(rs_alloc(h, &h->row_cnt, (size_t)h->n_left + 1));
-    RS_TRY(rs_alloc(h, &h->row_sum, (size_t)h->n_left + 1));
-    row_isum_kernel<<<blocks_for((int64_t)h->n_left * 32), T, 0, st>>>(h->l_ptr, h->l_code, h->n_left, h->row_cnt,
-                                                                      h->row_sum);
-    h->prof.total_launches += 2;
+    h->prof.total_launches++;
     RS_CUDA(cudaGetLastError());
     return RS_OK;
 }

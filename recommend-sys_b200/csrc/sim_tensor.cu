@@ -29,6 +29,8 @@
 //               handle runs every bj for its own row blocks and writes S[i][j] only.
 #include <cuda.h>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace {
@@ -456,14 +458,30 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
     const bool mirror = !cosums && rb == 0 && re == h->n_left;
     const int nbj = (int)((h->n_left + BN - 1) / BN);
     const int bi0 = (int)(rb / BM), bi1 = (int)((re + BM - 1) / BM);
-    std::vector<int2> tiles;
-    for (int bi = bi0; bi < bi1; bi++)
-        for (int bj = mirror ? 2 * bi : 0; bj < nbj; bj++) tiles.push_back(make_int2(bi, bj));
-    if (tiles.empty()) return RS_OK;
-    int2 *d_tiles;
-    RS_TRY(rs_alloc(h, &d_tiles, tiles.size()));
-    RS_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
-    RS_CUDA(cudaStreamSynchronize(h->stream));  // `tiles` is a pageable temporary
+    // the static tile list depends only on (n_left, shard, mirror): build it once per shape
+    const int64_t key[4] = {h->n_left, rb, re, mirror ? 1 : 0};
+    if (memcmp(key, h->tile_key, sizeof(key)) != 0) {
+        std::vector<int2> tiles;
+        for (int bi = bi0; bi < bi1; bi++)
+            for (int bj = mirror ? 2 * bi : 0; bj < nbj; bj++) tiles.push_back(make_int2(bi, bj));
+        const size_t bytes = tiles.size() * sizeof(int2);
+        if (bytes > h->tile_buf_bytes) {
+            RS_CUDA(cudaStreamSynchronize(h->stream));
+            if (h->tile_buf) cudaFree(h->tile_buf);
+            h->tile_buf = nullptr;
+            h->tile_buf_bytes = 0;
+            RS_CUDA(cudaMalloc(&h->tile_buf, bytes + 256));
+            h->tile_buf_bytes = bytes + 256;
+        }
+        if (bytes) {
+            RS_CUDA(cudaMemcpyAsync(h->tile_buf, tiles.data(), bytes, cudaMemcpyHostToDevice, h->stream));
+            RS_CUDA(cudaStreamSynchronize(h->stream));  // `tiles` is a pageable temporary
+        }
+        memcpy(h->tile_key, key, sizeof(key));
+        h->tile_count = (int32_t)tiles.size();
+    }
+    if (h->tile_count == 0) return RS_OK;
+    const int2 *d_tiles = reinterpret_cast<const int2 *>(h->tile_buf);
 
     CUtensorMap ma, mb;
     RS_TRY(make_map(h, BM, &ma));
@@ -471,7 +489,7 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
 
     TcArgs a{};
     a.tiles = d_tiles;
-    a.num_tiles = (int32_t)tiles.size();
+    a.num_tiles = h->tile_count;
     a.k_blocks = (int32_t)(h->tc_kpad / BK);
     a.n_left = h->n_left;
     a.row_begin = rb;
