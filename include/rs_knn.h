@@ -169,6 +169,9 @@ int32_t rs_knn_stddevs(rs_knn *h, double *out);
 
 int32_t rs_knn_profile_get(rs_knn *h, rs_knn_profile *out);
 int32_t rs_knn_profile_reset(rs_knn *h);
+/* Destroyed handles park their device memory in a process-wide cache (estimator copies are
+ * created and destroyed per fold, core/eval.go:29-35); this returns it to the driver. */
+int32_t rs_knn_trim_cache(void);
 /* Block until everything queued on the handle's stream has finished. */
 int32_t rs_knn_synchronize(rs_knn *h);
 

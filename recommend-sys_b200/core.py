@@ -63,7 +63,7 @@ ABI_SYMBOLS = [
     "rs_knn_destroy", "rs_knn_set_stream", "rs_knn_fit", "rs_knn_fit_device", "rs_knn_predict_batch",
     "rs_knn_predict_batch_device", "rs_knn_predict_neighbors", "rs_knn_sims_rows", "rs_knn_topk",
     "rs_knn_topk_device", "rs_knn_cosums", "rs_knn_means", "rs_knn_stddevs", "rs_knn_profile_get",
-    "rs_knn_profile_reset", "rs_knn_synchronize",
+    "rs_knn_profile_reset", "rs_knn_synchronize", "rs_knn_trim_cache",
 ]
 
 _knn_lib = None

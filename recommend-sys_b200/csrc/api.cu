@@ -157,10 +157,11 @@ int32_t rs_knn_destroy(rs_knn *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     free_fit_state(h);
-    for (auto &c : h->chunks) cudaFree(c.p);
+    for (auto &c : h->chunks) rs_cached_free(h->device, c.p, c.bytes);
     h->chunks.clear();
     if (h->tile_buf) cudaFree(h->tile_buf);
-    for (void *p : h->scratch) cudaFree(p);
+    if (h->ovf) rs_cached_free(h->device, h->ovf, h->ovf_bytes);
+    for (size_t i = 0; i < h->scratch.size(); i++) rs_cached_free(h->device, h->scratch[i], h->scratch_bytes[i]);
     cudaEventDestroy(h->ev_a);
     cudaEventDestroy(h->ev_b);
     cudaEventDestroy(h->ev_c);
@@ -288,17 +289,15 @@ static int32_t scratch_get(rs_knn *h, int slot, size_t bytes, void **out) {
         h->scratch_bytes.resize(slot + 1, 0);
     }
     if (h->scratch_bytes[slot] < bytes) {
-        if (h->scratch[slot]) cudaFree(h->scratch[slot]);
+        if (h->scratch[slot]) {
+            RS_CUDA(cudaStreamSynchronize(h->stream));
+            rs_cached_free(h->device, h->scratch[slot], h->scratch_bytes[slot]);
+        }
         h->scratch[slot] = nullptr;
         h->scratch_bytes[slot] = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&h->scratch[slot], want);
-        if (e != cudaSuccess) {
-            (void)cudaGetLastError();
-            rs_set_error("cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
-            return RS_ERR_OOM;
-        }
-        h->scratch_bytes[slot] = want;
+        size_t want = bytes + bytes / 4 + 256, got = 0;
+        RS_TRY(rs_cached_malloc(h->device, &h->scratch[slot], want, &got));
+        h->scratch_bytes[slot] = got;
     }
     *out = h->scratch[slot];
     return RS_OK;
@@ -521,6 +520,11 @@ int32_t rs_knn_profile_get(rs_knn *h, rs_knn_profile *out) {
     if (!out) return RS_ERR_INVALID;
     RS_TRY(fold_profile(h));
     *out = h->prof;
+    return RS_OK;
+}
+
+int32_t rs_knn_trim_cache(void) {
+    rs_cache_trim();
     return RS_OK;
 }
 

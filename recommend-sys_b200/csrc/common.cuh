@@ -108,9 +108,19 @@ struct rs_knn {
     double *topk_sim = nullptr;
 
     int32_t *d_flags = nullptr;  // small device scratch for validation flags
+    void *ovf = nullptr;         // predict: overflow list (count + indices)
+    size_t ovf_bytes = 0;
     std::vector<void *> scratch;         // device staging of the host-pointer entry points
     std::vector<size_t> scratch_bytes;
 };
+
+// ---- devmem.cu: process-wide cache of device allocations ----
+// Estimator copies are created and destroyed per cross-validation fold (core/eval.go:29-35);
+// freed device blocks are parked here and handed to the next handle on the same device, so a
+// create/Fit/Predict/destroy cycle performs no cudaMalloc/cudaFree after the first one.
+int32_t rs_cached_malloc(int device, void **out, size_t bytes, size_t *got);
+void rs_cached_free(int device, void *p, size_t bytes);
+void rs_cache_trim(void);
 
 // ---- prep.cu ----
 int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, const double *d_rating,

@@ -1,0 +1,63 @@
+// devmem.cu — see common.cuh.  A small best-fit cache of device blocks per device.
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+struct Block { int device; void *p; size_t bytes; };
+std::mutex g_mu;
+std::vector<Block> g_free;
+}  // namespace
+
+int32_t rs_cached_malloc(int device, void **out, size_t bytes, size_t *got) {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        int best = -1;
+        for (int i = 0; i < (int)g_free.size(); i++) {
+            const Block &b = g_free[i];
+            if (b.device != device || b.bytes < bytes) continue;
+            if (b.bytes > 2 * bytes + (64u << 20)) continue;   // do not waste a huge block on a small request
+            if (best < 0 || b.bytes < g_free[best].bytes) best = i;
+        }
+        if (best >= 0) {
+            *out = g_free[best].p;
+            if (got) *got = g_free[best].bytes;
+            g_free.erase(g_free.begin() + best);
+            return RS_OK;
+        }
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {   // give cached blocks back to the driver and retry once
+        (void)cudaGetLastError();
+        rs_cache_trim();
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        rs_set_error("cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? RS_ERR_OOM : RS_ERR_CUDA;
+    }
+    *out = p;
+    if (got) *got = bytes;
+    return RS_OK;
+}
+
+void rs_cached_free(int device, void *p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_free.push_back({device, p, bytes});
+}
+
+void rs_cache_trim(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (const Block &b : g_free) {
+        cudaSetDevice(b.device);
+        cudaFree(b.p);
+    }
+    g_free.clear();
+    cudaSetDevice(cur);
+}

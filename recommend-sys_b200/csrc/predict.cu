@@ -47,55 +47,6 @@ __device__ void warp_bitonic(uint64_t *keys, uint32_t *pos, int n_pad, int lane)
 }
 
 
-// ---- fast path: all candidates of one prediction live in registers (R per lane, blocked
-// layout e = lane*R + x) and are ordered by a warp-wide bitonic network: strides < R are
-// in-register compare-exchanges, strides >= R are __shfl_xor exchanges.  No shared memory.
-template <int R>
-__device__ __forceinline__ void ce_regs(uint64_t (&key)[R], uint32_t (&pos)[R], int i, int j, bool up) {
-    // order (i, j), i < j: "before" element first when up
-    const bool j_before_i = rec_before(key[j], pos[j], key[i], pos[i]);
-    if (j_before_i == up) {
-        const uint64_t tk = key[i]; key[i] = key[j]; key[j] = tk;
-        const uint32_t tp = pos[i]; pos[i] = pos[j]; pos[j] = tp;
-    }
-}
-
-template <int R, int STRIDE>
-__device__ __forceinline__ void stage_regs(uint64_t (&key)[R], uint32_t (&pos)[R], int lane, int size) {
-#pragma unroll
-    for (int x = 0; x < R; x++) {
-        if ((x & STRIDE) == 0) {
-            const bool up = (((lane * R + x) & size) == 0);
-            ce_regs<R>(key, pos, x, x | STRIDE, up);
-        }
-    }
-}
-
-template <int R>
-__device__ __forceinline__ void warp_sort_regs(uint64_t (&key)[R], uint32_t (&pos)[R], int lane) {
-#pragma unroll 1
-    for (int size = 2; size <= 32 * R; size <<= 1) {
-#pragma unroll 1
-        for (int stride = size >> 1; stride >= R; stride >>= 1) {
-            const int lm = stride / R;  // lane xor mask
-            const bool lower = (lane & lm) == 0;
-#pragma unroll
-            for (int x = 0; x < R; x++) {
-                const bool up = (((lane * R + x) & size) == 0);
-                const uint64_t ok = __shfl_xor_sync(0xffffffffu, key[x], lm);
-                const uint32_t op = __shfl_xor_sync(0xffffffffu, pos[x], lm);
-                const bool other_before = rec_before(ok, op, key[x], pos[x]);
-                // the lower index of the pair keeps the "before" element when the run is up
-                if (other_before == (up == lower)) { key[x] = ok; pos[x] = op; }
-            }
-        }
-        if (R >= 16 && size >= 16) stage_regs<R, (R >= 16 ? 8 : 0)>(key, pos, lane, size);
-        if (R >= 8 && size >= 8) stage_regs<R, (R >= 8 ? 4 : 0)>(key, pos, lane, size);
-        if (R >= 4 && size >= 4) stage_regs<R, (R >= 4 ? 2 : 0)>(key, pos, lane, size);
-        if (R >= 2) stage_regs<R, (R >= 2 ? 1 : 0)>(key, pos, lane, size);
-    }
-}
-
 struct PredArgs {
     const int32_t *left, *right;
     int64_t n;
@@ -116,79 +67,283 @@ struct PredArgs {
     int32_t nb_cap;
 };
 
-template <int R>
-__device__ __forceinline__ void predict_regs(const PredArgs &a, int64_t p, int32_t l, const double *row, int64_t cb,
-                                             int cnt, int lane);
+// =====================================================================================
+// Main predict kernel: selection, not sorting.  One warp per prediction:
+//   pass A  gather the similarity of every candidate, count the non-NaN ones (core/knn.go:95-99)
+//           and find their min / max;
+//   pass B  (only when more candidates than the register capacity CAP = 32*R) 256-bucket
+//           histogram of a monotone linear bucket of the similarity in shared memory, suffix
+//           scan -> boundary bucket: everything above it is certainly in the top k, everything
+//           below certainly not; refined (up to 3 levels) inside the boundary bucket when it is
+//           too full; genuine ties are taken in scan order = ascending inner id (canonical);
+//   pass C  compaction of the surviving <= CAP candidates into registers (R per lane);
+//   sort    one warp-wide bitonic network over CAP (key,pos) records in registers
+//           (strides < R in-register, >= R via __shfl_xor);
+//   reduce  the first min(k,valid) neighbours are accumulated sequentially in sorted order,
+//           exactly as core/knn.go:116-130 does.
+// A prediction whose boundary bucket still overflows after 3 levels is appended to an
+// overflow list and finished by the generic shared-memory kernel below.
+// =====================================================================================
+constexpr int SEL_WARPS = 8;
 
 template <int R>
-__device__ __forceinline__ void predict_regs(const PredArgs &a, int64_t p, int32_t l, const double *row, int64_t cb,
-                                             int cnt, int lane) {
-    uint64_t key[R];
-    uint32_t pos[R];
-    int mine = 0;
-#pragma unroll
-    for (int x = 0; x < R; x++) {
-        const int e = lane * R + x;
-        key[x] = 0;
-        pos[x] = 0xffffffffu;
-        if (e < cnt) {
-            const double s = row[a.r_col[cb + e]];
-            if (s == s) { key[x] = rs_sim_key(s); pos[x] = (uint32_t)e; mine++; }
-        }
-    }
-    int valid = mine;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
-    if (valid <= a.min_k) {                                  // core/knn.go:102-104 (note <=)
-        if (lane == 0) a.out[p] = a.global_mean;
-        return;
-    }
-    warp_sort_regs<R>(key, pos, lane);
-    const int num = a.k < valid ? a.k : valid;                // core/knn.go:111-114
-    // neighbour e sits in lane e / R, register e % R
-    double sv[R], av[R];
-#pragma unroll
-    for (int x = 0; x < R; x++) {
-        const int e = lane * R + x;
-        sv[x] = 0.0;
-        av[x] = 0.0;
-        if (e < num) {
-            const int64_t xx = cb + pos[x];
-            const int32_t id = a.r_col[xx];
-            const double s = row[id];
-            double rating = a.r_val[xx];
-            if (a.knn_type == RS_KNN_CENTERED) rating -= a.means[id];                           // core/knn.go:121
-            else if (a.knn_type == RS_KNN_ZSCORE) rating = (rating - a.means[id]) / a.stddevs[id];
-            else if (a.knn_type == RS_KNN_BASELINE) rating -= a.bias[id];
-            sv[x] = s;
-            av[x] = rating;
-            if (a.nb_ids && e < a.nb_cap) { a.nb_ids[e] = id; a.nb_sims[e] = s; }
-        }
-    }
-    double wsum = 0.0, wrat = 0.0;
-    const int lanes_used = (num + R - 1) / R;
-    for (int src = 0; src < lanes_used; src++) {
-#pragma unroll
-        for (int x = 0; x < R; x++) {
-            const double sq = __shfl_sync(0xffffffffu, sv[x], src);
-            const double aq = __shfl_sync(0xffffffffu, av[x], src);
-            if (src * R + x < num) {
-                wsum += sq;                                    // core/knn.go:117
-                wrat += sq * aq;                               // core/knn.go:127
-            }
-        }
-    }
-    if (lane == 0) {
-        double pred = wrat / wsum;                             // core/knn.go:131
-        if (a.knn_type == RS_KNN_CENTERED) pred += a.means[l];
-        else if (a.knn_type == RS_KNN_BASELINE) pred += a.bias[l];
-        else if (a.knn_type == RS_KNN_ZSCORE) { pred *= a.stddevs[l]; pred += a.means[l]; }
-        a.out[p] = pred;
-        if (a.nb_count) *a.nb_count = num < a.nb_cap ? num : a.nb_cap;
+__device__ __forceinline__ void ce_regs(uint64_t (&key)[R], uint32_t (&pos)[R], int i, int j, bool up) {
+    const bool j_before_i = rec_before(key[j], pos[j], key[i], pos[i]);
+    if (j_before_i == up) {
+        const uint64_t tk = key[i]; key[i] = key[j]; key[j] = tk;
+        const uint32_t tp = pos[i]; pos[i] = pos[j]; pos[j] = tp;
     }
 }
 
-__global__ void __launch_bounds__(PRED_WARPS * 32) predict_kernel(PredArgs a) {
+template <int R, int STRIDE>
+__device__ __forceinline__ void stage_regs(uint64_t (&key)[R], uint32_t (&pos)[R], int lane, int size) {
+#pragma unroll
+    for (int x = 0; x < R; x++) {
+        if ((x & STRIDE) == 0) {
+            const bool up = (((lane * R + x) & size) == 0);
+            ce_regs<R>(key, pos, x, x | STRIDE, up);
+        }
+    }
+}
+
+// blocked layout: element e = lane*R + x
+template <int R>
+__device__ __forceinline__ void warp_sort_regs(uint64_t (&key)[R], uint32_t (&pos)[R], int lane) {
+#pragma unroll 1
+    for (int size = 2; size <= 32 * R; size <<= 1) {
+#pragma unroll 1
+        for (int stride = size >> 1; stride >= R; stride >>= 1) {
+            const int lm = stride / R;
+            const bool lower = (lane & lm) == 0;
+#pragma unroll
+            for (int x = 0; x < R; x++) {
+                const bool up = (((lane * R + x) & size) == 0);
+                const uint64_t ok = __shfl_xor_sync(0xffffffffu, key[x], lm);
+                const uint32_t op = __shfl_xor_sync(0xffffffffu, pos[x], lm);
+                const bool other_before = rec_before(ok, op, key[x], pos[x]);
+                if (other_before == (up == lower)) { key[x] = ok; pos[x] = op; }
+            }
+        }
+        if (R >= 16 && size >= 16) stage_regs<R, (R >= 16 ? 8 : 0)>(key, pos, lane, size);
+        if (R >= 8 && size >= 8) stage_regs<R, (R >= 8 ? 4 : 0)>(key, pos, lane, size);
+        if (R >= 4 && size >= 4) stage_regs<R, (R >= 4 ? 2 : 0)>(key, pos, lane, size);
+        if (R >= 2) stage_regs<R, (R >= 2 ? 1 : 0)>(key, pos, lane, size);
+    }
+}
+
+__device__ __forceinline__ int sel_bucket(double s, double lo, double scale) {
+    int b = (int)((s - lo) * scale);   // monotone non-decreasing in s
+    return b > 255 ? 255 : (b < 0 ? 0 : b);
+}
+
+template <int R>
+__global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs a, int32_t *overflow_list,
+                                                                        int32_t *overflow_count) {
+    constexpr int CAP = 32 * R;
+    __shared__ uint32_t s_hist[SEL_WARPS][256];
+    __shared__ uint64_t s_key[SEL_WARPS][CAP];
+    __shared__ uint32_t s_pos[SEL_WARPS][CAP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *hist = s_hist[warp];
+    uint64_t *ckey = s_key[warp];
+    uint32_t *cpos = s_pos[warp];
+    const int64_t n_warps = (int64_t)gridDim.x * SEL_WARPS;
+    const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    for (int64_t p = (int64_t)blockIdx.x * SEL_WARPS + warp; p < a.n; p += n_warps) {
+        const int32_t l = a.left[p], r = a.right[p];
+        if (a.nb_count && lane == 0) *a.nb_count = 0;
+        if (l < 0 || r < 0 || r >= a.n_right) {            // core/knn.go:89-91 (newID)
+            if (lane == 0) a.out[p] = a.global_mean;
+            continue;
+        }
+        if (l < a.row_begin || l >= a.row_end) {           // not in this shard
+            if (lane == 0) a.out[p] = nan_v;
+            continue;
+        }
+        const double *row = a.sims + (l - a.row_begin) * a.ld_s;
+        const int64_t cb = a.r_ptr[r];
+        const int64_t cnt = a.r_ptr[r + 1] - cb;
+        const int32_t *ids = a.r_col + cb;
+
+        // ---- pass A: count + range ----
+        double lo = __longlong_as_double(0x7ff0000000000000ll), hi = -lo;
+        int valid = 0;
+        for (int64_t e = lane; e < cnt; e += 32) {
+            const double s = row[ids[e]];
+            if (s == s) { valid++; lo = fmin(lo, s); hi = fmax(hi, s); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            valid += __shfl_xor_sync(0xffffffffu, valid, o);
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (valid <= a.min_k) {                            // core/knn.go:102-104 (note <=)
+            if (lane == 0) a.out[p] = a.global_mean;
+            continue;
+        }
+        const int num = a.k < valid ? a.k : valid;         // core/knn.go:111-114
+
+        // ---- pass B: narrow to <= CAP candidates that contain the top `num` ----
+        // selected  <=>  s > hi_sure  ||  (lo <= s <= hi && bucket(s) >= T)   [+ scan-order ties]
+        double hi_sure = __longlong_as_double(0x7ff0000000000000ll);  // +inf: nothing above yet
+        double scale = 0.0;
+        int T = 0;
+        int sure = 0;          // candidates already known to be in the top `num`
+        int tie_take = -1;     // >= 0: the interval is one value; take this many in scan order
+        bool overflow = false;
+        if (valid > CAP) {
+            for (int level = 0;; level++) {
+                for (int x = lane; x < 256; x += 32) hist[x] = 0;
+                __syncwarp();
+                scale = (hi > lo) ? 256.0 / (hi - lo) : 0.0;
+                for (int64_t e = lane; e < cnt; e += 32) {
+                    const double s = row[ids[e]];
+                    if (s >= lo && s <= hi) atomicAdd(&hist[sel_bucket(s, lo, scale)], 1u);
+                }
+                __syncwarp();
+                // suffix counts: lane owns buckets [8*lane, 8*lane+8)
+                uint32_t h[8], mine = 0;
+#pragma unroll
+                for (int x = 0; x < 8; x++) { h[x] = hist[8 * lane + x]; mine += h[x]; }
+                uint32_t above = mine;   // inclusive suffix over lanes
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_down_sync(0xffffffffu, above, o);
+                    if (lane + o < 32) above += v;
+                }
+                above -= mine;           // candidates in buckets of higher lanes
+                const int need = num - sure;
+                // the boundary bucket is the highest T with count(bucket >= T) >= need
+                int myT = -1;
+                uint32_t run = above, sure_here = 0, bd_here = 0;
+#pragma unroll
+                for (int x = 7; x >= 0; x--) {
+                    if (myT < 0 && run + h[x] >= (uint32_t)need) { myT = 8 * lane + x; sure_here = run; bd_here = h[x]; }
+                    run += h[x];
+                }
+                const uint32_t has = __ballot_sync(0xffffffffu, myT >= 0);
+                const int src = 31 - __clz(has);           // highest lane that found it
+                T = __shfl_sync(0xffffffffu, myT, src);
+                const int sure_lvl = (int)__shfl_sync(0xffffffffu, sure_here, src);
+                const int bd = (int)__shfl_sync(0xffffffffu, bd_here, src);
+                if (sure + sure_lvl + bd <= CAP) break;    // compaction fits
+                // too many in the boundary bucket: refine inside it
+                double lo2 = __longlong_as_double(0x7ff0000000000000ll), hi2 = -lo2;
+                for (int64_t e = lane; e < cnt; e += 32) {
+                    const double s = row[ids[e]];
+                    if (s >= lo && s <= hi && sel_bucket(s, lo, scale) == T) { lo2 = fmin(lo2, s); hi2 = fmax(hi2, s); }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    lo2 = fmin(lo2, __shfl_xor_sync(0xffffffffu, lo2, o));
+                    hi2 = fmax(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
+                }
+                sure += sure_lvl;
+                hi_sure = hi2;            // everything above the boundary bucket is certain
+                lo = lo2; hi = hi2; T = 0; scale = 0.0;
+                if (lo2 == hi2) { tie_take = num - sure; break; }   // genuine ties: scan order
+                if (level == 2) { overflow = true; break; }
+            }
+        }
+        const bool take_all = valid <= CAP;   // every valid candidate fits in the registers
+        if (overflow) {
+            if (lane == 0) overflow_list[atomicAdd(overflow_count, 1)] = (int32_t)p;
+            continue;
+        }
+
+        // ---- pass C: compaction (scan order = ascending inner id) ----
+        int have = 0, ties_taken = 0;
+        for (int64_t base = 0; base < cnt; base += 32) {
+            const int64_t e = base + lane;
+            bool take = false, tie = false;
+            uint64_t key = 0;
+            if (e < cnt) {
+                const double s = row[ids[e]];
+                if (s == s) {
+                    key = rs_sim_key(s);
+                    if (take_all || s > hi_sure) take = true;
+                    else if (s >= lo && s <= hi) {
+                        if (tie_take >= 0) tie = true;
+                        else take = sel_bucket(s, lo, scale) >= T;
+                    }
+                }
+            }
+            if (tie_take >= 0) {
+                const uint32_t tm = __ballot_sync(0xffffffffu, tie);
+                if (tie && ties_taken + __popc(tm & lt_mask) < tie_take) take = true;
+                ties_taken += __popc(tm);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, take);
+            if (take) {
+                const int slot = have + __popc(m & lt_mask);
+                ckey[slot] = key;
+                cpos[slot] = (uint32_t)e;
+            }
+            have += __popc(m);
+        }
+        __syncwarp();
+
+        // ---- sort the survivors in registers ----
+        uint64_t key[R];
+        uint32_t pos[R];
+#pragma unroll
+        for (int x = 0; x < R; x++) {
+            const int e = lane * R + x;
+            key[x] = e < have ? ckey[e] : 0ull;
+            pos[x] = e < have ? cpos[e] : 0xffffffffu;
+        }
+        __syncwarp();
+        warp_sort_regs<R>(key, pos, lane);
+
+        // ---- weighted mean over the first `num`, sequential in sorted order ----
+        double sv[R], av[R];
+#pragma unroll
+        for (int x = 0; x < R; x++) {
+            const int e = lane * R + x;
+            sv[x] = 0.0;
+            av[x] = 0.0;
+            if (e < num) {
+                const int32_t id = ids[pos[x]];
+                const double s = row[id];
+                double rating = a.r_val[cb + pos[x]];
+                if (a.knn_type == RS_KNN_CENTERED) rating -= a.means[id];                       // core/knn.go:121
+                else if (a.knn_type == RS_KNN_ZSCORE) rating = (rating - a.means[id]) / a.stddevs[id];
+                else if (a.knn_type == RS_KNN_BASELINE) rating -= a.bias[id];
+                sv[x] = s;
+                av[x] = rating;
+                if (a.nb_ids && e < a.nb_cap) { a.nb_ids[e] = id; a.nb_sims[e] = s; }
+            }
+        }
+        double wsum = 0.0, wrat = 0.0;
+        const int lanes_used = (num + R - 1) / R;
+        for (int src = 0; src < lanes_used; src++) {
+#pragma unroll
+            for (int x = 0; x < R; x++) {
+                const double sq = __shfl_sync(0xffffffffu, sv[x], src);
+                const double aq = __shfl_sync(0xffffffffu, av[x], src);
+                if (src * R + x < num) {
+                    wsum += sq;                                // core/knn.go:117
+                    wrat += sq * aq;                           // core/knn.go:127
+                }
+            }
+        }
+        if (lane == 0) {
+            double pred = wrat / wsum;                         // core/knn.go:131
+            if (a.knn_type == RS_KNN_CENTERED) pred += a.means[l];
+            else if (a.knn_type == RS_KNN_BASELINE) pred += a.bias[l];
+            else if (a.knn_type == RS_KNN_ZSCORE) { pred *= a.stddevs[l]; pred += a.means[l]; }
+            a.out[p] = pred;
+            if (a.nb_count) *a.nb_count = num < a.nb_cap ? num : a.nb_cap;
+        }
+    }
+}
+
+// Generic shared-memory kernel: finishes the (rare) predictions on the overflow list.
+__global__ void __launch_bounds__(PRED_WARPS * 32) predict_kernel(PredArgs a, const int32_t *__restrict__ list,
+                                                                  const int32_t *__restrict__ list_count) {
     __shared__ uint64_t s_keys[PRED_WARPS][PRED_CAP];
     __shared__ uint32_t s_pos[PRED_WARPS][PRED_CAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -197,7 +352,9 @@ __global__ void __launch_bounds__(PRED_WARPS * 32) predict_kernel(PredArgs a) {
     const int64_t n_warps = (int64_t)gridDim.x * PRED_WARPS;
     const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
 
-    for (int64_t p = (int64_t)blockIdx.x * PRED_WARPS + warp; p < a.n; p += n_warps) {
+    const int64_t n_work = list ? (int64_t)*list_count : a.n;
+    for (int64_t w = (int64_t)blockIdx.x * PRED_WARPS + warp; w < n_work; w += n_warps) {
+        const int64_t p = list ? (int64_t)list[w] : w;
         const int32_t l = a.left[p], r = a.right[p];
         if (a.nb_count && lane == 0) *a.nb_count = 0;
         if (l < 0 || r < 0 || r >= a.n_right) {            // core/knn.go:89-91 (newID)
@@ -210,12 +367,6 @@ __global__ void __launch_bounds__(PRED_WARPS * 32) predict_kernel(PredArgs a) {
         }
         const double *row = a.sims + (l - a.row_begin) * a.ld_s;
         const int64_t cb = a.r_ptr[r], ce = a.r_ptr[r + 1];
-        const int64_t cnt64 = ce - cb;
-        if (cnt64 <= 32) { predict_regs<1>(a, p, l, row, cb, (int)cnt64, lane); continue; }
-        if (cnt64 <= 64) { predict_regs<2>(a, p, l, row, cb, (int)cnt64, lane); continue; }
-        if (cnt64 <= 128) { predict_regs<4>(a, p, l, row, cb, (int)cnt64, lane); continue; }
-        if (cnt64 <= 256) { predict_regs<8>(a, p, l, row, cb, (int)cnt64, lane); continue; }
-        if (cnt64 <= 512) { predict_regs<16>(a, p, l, row, cb, (int)cnt64, lane); continue; }
         const int keep = a.k < PRED_CAP / 2 ? a.k : PRED_CAP / 2;
 
         // ---- gather + filter; keep the best `keep` so far in keys[0..have) ----
@@ -393,6 +544,10 @@ int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
         rs_set_error("k=%d exceeds the %d neighbours the predict kernel supports", h->p.k, PRED_CAP / 2);
         return RS_ERR_UNSUPPORTED;
     }
+    if (n >= (1ll << 31)) {
+        rs_set_error("at most 2^31-1 predictions per call");
+        return RS_ERR_UNSUPPORTED;
+    }
     PredArgs a{};
     a.left = d_left; a.right = d_right; a.n = n; a.out = d_out;
     a.r_ptr = h->r_ptr; a.r_col = h->r_col; a.r_val = h->r_val;
@@ -401,14 +556,32 @@ int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
     a.global_mean = h->global_mean; a.n_right = h->n_right;
     a.k = h->p.k; a.min_k = h->p.min_k; a.knn_type = h->p.knn_type;
     a.nb_ids = d_nb_ids; a.nb_sims = d_nb_sims; a.nb_count = d_nb_count; a.nb_cap = nb_cap;
+    // overflow list: [0] = count, [1..n] = prediction indices
+    if ((size_t)(n + 1) * 4 > h->ovf_bytes) {
+        RS_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->ovf) rs_cached_free(h->device, h->ovf, h->ovf_bytes);
+        h->ovf = nullptr;
+        h->ovf_bytes = 0;
+        const size_t want = (size_t)(n + 1) * 4 + (size_t)n;  // 25 % headroom
+        size_t got = 0;
+        RS_TRY(rs_cached_malloc(h->device, &h->ovf, want, &got));
+        h->ovf_bytes = got;
+    }
+    int32_t *ovf = reinterpret_cast<int32_t *>(h->ovf);
+    RS_CUDA(cudaMemsetAsync(ovf, 0, 4, h->stream));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    int64_t blocks = (n + PRED_WARPS - 1) / PRED_WARPS;
-    const int64_t cap = (int64_t)sms * 4 * 8;  // persistent-ish: a few waves of resident CTAs
+    int64_t blocks = (n + SEL_WARPS - 1) / SEL_WARPS;
+    const int64_t cap = (int64_t)sms * 8;   // resident CTAs; warps stride over the predictions
     if (blocks > cap) blocks = cap;
-    predict_kernel<<<(unsigned)blocks, PRED_WARPS * 32, 0, h->stream>>>(a);
+    // register capacity of the selection kernel: room for k plus a boundary bucket
+    if (h->p.k <= 44) predict_select_kernel<2><<<(unsigned)blocks, SEL_WARPS * 32, 0, h->stream>>>(a, ovf + 1, ovf);
+    else if (h->p.k <= 104) predict_select_kernel<4><<<(unsigned)blocks, SEL_WARPS * 32, 0, h->stream>>>(a, ovf + 1, ovf);
+    else predict_select_kernel<8><<<(unsigned)blocks, SEL_WARPS * 32, 0, h->stream>>>(a, ovf + 1, ovf);
+    // the generic kernel drains the overflow list (normally empty: a handful of warps exit at once)
+    predict_kernel<<<(unsigned)sms, PRED_WARPS * 32, 0, h->stream>>>(a, ovf + 1, ovf);
     h->prof.predict_launches++;
-    h->prof.total_launches++;
+    h->prof.total_launches += 2;
     RS_CUDA(cudaGetLastError());
     return RS_OK;
 }

@@ -27,13 +27,9 @@ int32_t rs_dev_alloc(rs_knn *h, void **out, size_t bytes) {
     const size_t min_chunk = (size_t)64 << 20;
     const size_t want = bytes > min_chunk ? bytes : min_chunk;
     void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) {
-        rs_set_error("cudaMalloc(%zu bytes): %s", want, cudaGetErrorString(e));
-        (void)cudaGetLastError();
-        return e == cudaErrorMemoryAllocation ? RS_ERR_OOM : RS_ERR_CUDA;
-    }
-    h->chunks.push_back({(char *)p, want});
+    size_t got = 0;
+    RS_TRY(rs_cached_malloc(h->device, &p, want, &got));
+    h->chunks.push_back({(char *)p, got});
     h->cur_chunk = h->chunks.size() - 1;
     h->cur_off = bytes;
     *out = p;
