@@ -16,14 +16,14 @@ def shard_rows(n: int, world: int, rank: int, align: int = 128):
     return min(b0 * align, n), min(b1 * align, n)
 
 
-def allgather_topk(idx_local, sim_local, n: int, k: int, group=None):
+def allgather_topk(idx_local, sim_local, n: int, k: int, group=None, align: int = 128):
     """All-gather the per-shard neighbour lists into the full (n, k) lists on every rank.
     idx_local/sim_local: torch tensors (rows_of_this_rank, k) on the collective's device."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    bounds = [shard_rows(n, world, r) for r in range(world)]
+    bounds = [shard_rows(n, world, r, align) for r in range(world)]
     max_rows = max(b - a for a, b in bounds)
     pad_i = torch.full((max_rows, k), -1, dtype=torch.int32, device=idx_local.device)
     pad_s = torch.full((max_rows, k), float("nan"), dtype=torch.float64, device=sim_local.device)
