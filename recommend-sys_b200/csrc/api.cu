@@ -37,7 +37,8 @@ void free_fit_state(rs_knn *h) {
     h->l_val = h->r_val = h->ld_val = nullptr;
     h->l_code = nullptr;
     h->lut = h->means = h->stddevs = h->pmeans = h->left_bias = h->right_bias = nullptr;
-    h->rt = nullptr;
+    h->mp = nullptr;
+    h->r_dev = h->r_dev2 = nullptr;
     h->planes = nullptr;
     h->row_cnt = h->row_sum = nullptr;
     h->sims = nullptr;

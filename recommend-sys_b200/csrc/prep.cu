@@ -189,16 +189,32 @@ __global__ void means_from_isum_kernel(const int32_t *__restrict__ row_cnt, cons
     pmeans[i] = m;
 }
 
-__global__ void scatter_rt_kernel(const int64_t *__restrict__ l_ptr, const int32_t *__restrict__ l_col,
-                                  const uint8_t *__restrict__ l_code, int32_t n_left, int64_t ld_rt,
-                                  uint8_t *__restrict__ rt) {
-    // one warp per left row
-    int32_t row = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    int lane = threadIdx.x & 31;
-    if (row >= n_left) return;
-    for (int64_t x = l_ptr[row] + lane; x < l_ptr[row + 1]; x += 32)
-        rt[(int64_t)l_col[x] * ld_rt + row] = l_code[x];
+// One warp per right row c: set the bits of MP[c][j/32] and record, for the first entry of every
+// word, its rank in c's id-sorted list; precompute the b-side term of every entry.
+__global__ void build_mp_kernel(const int64_t *__restrict__ r_ptr, const int32_t *__restrict__ r_col,
+                                const double *__restrict__ r_val, int32_t n_right, int64_t words, int sim,
+                                const double *__restrict__ pmeans, const double *__restrict__ left_bias,
+                                const double *__restrict__ right_bias, double global_bias,
+                                uint2 *__restrict__ mp, double *__restrict__ r_dev, double *__restrict__ r_dev2) {
+    const int32_t c = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= n_right) return;
+    const int64_t b = r_ptr[c], e = r_ptr[c + 1];
+    unsigned int *mpw = reinterpret_cast<unsigned int *>(mp + (int64_t)c * words);
+    for (int64_t x = b + lane; x < e; x += 32) {
+        const int32_t j = r_col[x];
+        atomicOr(&mpw[2 * (j >> 5)], 1u << (j & 31));
+        if (x == b || (r_col[x - 1] >> 5) != (j >> 5)) mpw[2 * (j >> 5) + 1] = (unsigned int)(x - b);
+        const double y = r_val[x];
+        double t;
+        if (sim == RS_SIM_PEARSON) t = y - pmeans[j];                             // core/sim.go:74
+        else if (sim == RS_SIM_PEARSON_BASELINE) { const double base = global_bias + left_bias[j]; const double bb = base + right_bias[c]; t = y - bb; }
+        else t = y;
+        r_dev[x] = t;
+        r_dev2[x] = t * t;                                                        // core/sim.go:20 / :76
+    }
 }
+
 
 // planes[p][row][col]: p=0 rating^2, p=1 mask, p=2 rating (the order the MMAs of sim_tensor.cu
 // rely on: B planes adjacent in shared memory as X2 | M | X); K-major int8
@@ -402,12 +418,16 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
 
 int32_t rs_prep_rt(rs_knn *h) {
     cudaStream_t st = h->stream;
-    h->ld_rt = ((int64_t)h->n_left + RS_STREAM_JC - 1) / RS_STREAM_JC * RS_STREAM_JC;
-    size_t bytes = (size_t)h->n_right * (size_t)h->ld_rt;
-    RS_TRY(rs_alloc(h, &h->rt, bytes));
-    RS_CUDA(cudaMemsetAsync(h->rt, 0, bytes, st));
-    scatter_rt_kernel<<<blocks_for((int64_t)h->n_left * 32), T, 0, st>>>(h->l_ptr, h->l_col, h->l_code, h->n_left,
-                                                                        h->ld_rt, h->rt);
+    const int64_t per_cta = RS_STREAM_JC / 32;  // words covered by one CTA
+    h->mp_words = (((int64_t)h->n_left + 31) / 32 + per_cta - 1) / per_cta * per_cta;
+    const size_t bytes = (size_t)h->n_right * (size_t)h->mp_words * sizeof(uint2);
+    RS_TRY(rs_alloc(h, &h->mp, (size_t)h->n_right * (size_t)h->mp_words));
+    RS_TRY(rs_alloc(h, &h->r_dev, (size_t)h->nnz));
+    RS_TRY(rs_alloc(h, &h->r_dev2, (size_t)h->nnz));
+    RS_CUDA(cudaMemsetAsync(h->mp, 0, bytes, st));
+    build_mp_kernel<<<blocks_for((int64_t)h->n_right * 32), T, 0, st>>>(
+        h->r_ptr, h->r_col, h->r_val, h->n_right, h->mp_words, h->p.sim, h->pmeans, h->left_bias, h->right_bias,
+        h->global_bias, h->mp, h->r_dev, h->r_dev2);
     h->prof.total_launches++;
     RS_CUDA(cudaGetLastError());
     return RS_OK;
