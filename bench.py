@@ -287,13 +287,14 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()          # started before the warm-up: NVML start-up must not overlap the timed region
     for _ in range(args.warmup):
         step_device()
         flush.fill_(1)
     barrier()
     h.profile_reset()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.rows.clear()     # keep only the samples taken during the timed region
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for s in range(args.steps):

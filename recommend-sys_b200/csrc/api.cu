@@ -37,8 +37,9 @@ void free_fit_state(rs_knn *h) {
     h->l_val = h->r_val = h->ld_val = nullptr;
     h->l_code = nullptr;
     h->lut = h->means = h->stddevs = h->pmeans = h->left_bias = h->right_bias = nullptr;
-    h->mp = nullptr;
-    h->r_dev = h->r_dev2 = nullptr;
+    h->r_dev = nullptr;
+    h->cp = nullptr;
+    h->l2r = nullptr;
     h->planes = nullptr;
     h->row_cnt = h->row_sum = nullptr;
     h->sims = nullptr;

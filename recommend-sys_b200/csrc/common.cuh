@@ -34,9 +34,8 @@ enum { RS_CLASS_INT8 = 0, RS_CLASS_TABLE = 1 };
 constexpr int RS_INT8_BIAS = 12;
 
 // Column-chunk width of the streaming similarity kernel (threads * bytes per thread).
-constexpr int RS_STREAM_THREADS = 256;
-constexpr int RS_STREAM_JPT = 8;
-constexpr int RS_STREAM_JC = RS_STREAM_THREADS * RS_STREAM_JPT;  // 2048 columns per CTA
+constexpr int RS_STREAM_WARPS = 4;   // warps per CTA, each an independent (row, column-chunk) work item
+constexpr int RS_STREAM_JC = 512;    // columns per work item (3 x 512 doubles of accumulators per warp)
 
 // Tensor-core similarity kernel tile: 128 left rows (MMA M) x 64 left rows (MMA N),
 // K blocked by 128 bytes (one SWIZZLE_128B atom) per pipeline stage.
@@ -94,11 +93,12 @@ struct rs_knn {
     int64_t max_row_cnt = 0;
     double *right_bias = nullptr;
 
-    // stream path: bit matrix MP[right][left/32] = {mask, rank of the word's first entry}, and the
-    // b-side term of every rating in right-CSR order (value - row mean etc.) with its square
-    uint2 *mp = nullptr;
-    int64_t mp_words = 0;
-    double *r_dev = nullptr, *r_dev2 = nullptr;
+    // stream path: b-side term of every rating in right-CSR order (value, value - row mean, ...),
+    // chunk pointers cp[right][Q+1] into each right row, and l2r: left-CSR entry -> right-CSR index
+    double *r_dev = nullptr;
+    int32_t *cp = nullptr;
+    int32_t n_chunks = 0;
+    int64_t *l2r = nullptr;
     // int8 planes X, X^2, M of the left matrix, [3][n_pad][k_pad], K-major (tensor path)
     int8_t *planes = nullptr;
     int64_t tc_npad = 0, tc_kpad = 0;

@@ -189,29 +189,59 @@ __global__ void means_from_isum_kernel(const int32_t *__restrict__ row_cnt, cons
     pmeans[i] = m;
 }
 
-// One warp per right row c: set the bits of MP[c][j/32] and record, for the first entry of every
-// word, its rank in c's id-sorted list; precompute the b-side term of every entry.
-__global__ void build_mp_kernel(const int64_t *__restrict__ r_ptr, const int32_t *__restrict__ r_col,
-                                const double *__restrict__ r_val, int32_t n_right, int64_t words, int sim,
-                                const double *__restrict__ pmeans, const double *__restrict__ left_bias,
-                                const double *__restrict__ right_bias, double global_bias,
-                                uint2 *__restrict__ mp, double *__restrict__ r_dev, double *__restrict__ r_dev2) {
+// b-side term of every right-CSR entry (c, j): the value the reference combines with the a-side
+// term, computed once with the same IEEE operations (core/sim.go:74 `ratingB := jr.Rating - meanB`).
+__global__ void build_rdev_kernel(const int64_t *__restrict__ r_ptr, const int32_t *__restrict__ r_col,
+                                  const double *__restrict__ r_val, int32_t n_right, int sim,
+                                  const double *__restrict__ pmeans, const double *__restrict__ left_bias,
+                                  const double *__restrict__ right_bias, double global_bias,
+                                  double *__restrict__ r_dev) {
     const int32_t c = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (c >= n_right) return;
-    const int64_t b = r_ptr[c], e = r_ptr[c + 1];
-    unsigned int *mpw = reinterpret_cast<unsigned int *>(mp + (int64_t)c * words);
-    for (int64_t x = b + lane; x < e; x += 32) {
+    for (int64_t x = r_ptr[c] + lane; x < r_ptr[c + 1]; x += 32) {
         const int32_t j = r_col[x];
-        atomicOr(&mpw[2 * (j >> 5)], 1u << (j & 31));
-        if (x == b || (r_col[x - 1] >> 5) != (j >> 5)) mpw[2 * (j >> 5) + 1] = (unsigned int)(x - b);
         const double y = r_val[x];
         double t;
-        if (sim == RS_SIM_PEARSON) t = y - pmeans[j];                             // core/sim.go:74
+        if (sim == RS_SIM_PEARSON) t = y - pmeans[j];
         else if (sim == RS_SIM_PEARSON_BASELINE) { const double base = global_bias + left_bias[j]; const double bb = base + right_bias[c]; t = y - bb; }
         else t = y;
         r_dev[x] = t;
-        r_dev2[x] = t * t;                                                        // core/sim.go:20 / :76
+    }
+}
+
+// cp[c][q] = number of entries of right row c with left id < q*JC (lower bound by binary search)
+__global__ void build_cp_kernel(const int64_t *__restrict__ r_ptr, const int32_t *__restrict__ r_col,
+                                int32_t n_right, int32_t n_chunks, int32_t jc, int32_t *__restrict__ cp) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = n_chunks + 1;
+    if (t >= (int64_t)n_right * per) return;
+    const int32_t c = (int32_t)(t / per), q = (int32_t)(t % per);
+    const int64_t b = r_ptr[c], e = r_ptr[c + 1];
+    const int64_t target = (int64_t)q * jc;
+    int64_t lo = b, hi = e;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (r_col[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    cp[t] = (int32_t)(lo - b);
+}
+
+// l2r[e] for the left-CSR entry e = (i, c): position of (c, i) in the right CSR
+__global__ void build_l2r_kernel(const int64_t *__restrict__ l_ptr, const int32_t *__restrict__ l_col,
+                                 const int64_t *__restrict__ r_ptr, const int32_t *__restrict__ r_col,
+                                 int32_t n_right, int64_t *__restrict__ l2r) {
+    const int32_t c = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= n_right) return;
+    for (int64_t x = r_ptr[c] + lane; x < r_ptr[c + 1]; x += 32) {
+        const int32_t j = r_col[x];
+        int64_t lo = l_ptr[j], hi = l_ptr[j + 1];
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (l_col[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        l2r[lo] = x;
     }
 }
 
@@ -280,7 +310,7 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     RS_TRY(rs_alloc(h, &perm_rl, nnz));
     RS_TRY(rs_alloc(h, &lcount, (size_t)nl + 1));
     RS_TRY(rs_alloc(h, &rcount, (size_t)nr + 1));
-    RS_TRY(rs_alloc(h, &h->d_flags, 4));
+    RS_TRY(rs_alloc(h, &h->d_flags, 8));
     RS_CUDA(cudaMemsetAsync(lcount, 0, ((size_t)nl + 1) * 4, st));
     RS_CUDA(cudaMemsetAsync(rcount, 0, ((size_t)nr + 1) * 4, st));
     RS_CUDA(cudaMemsetAsync(h->d_flags, 0, 16, st));
@@ -418,17 +448,18 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
 
 int32_t rs_prep_rt(rs_knn *h) {
     cudaStream_t st = h->stream;
-    const int64_t per_cta = RS_STREAM_JC / 32;  // words covered by one CTA
-    h->mp_words = (((int64_t)h->n_left + 31) / 32 + per_cta - 1) / per_cta * per_cta;
-    const size_t bytes = (size_t)h->n_right * (size_t)h->mp_words * sizeof(uint2);
-    RS_TRY(rs_alloc(h, &h->mp, (size_t)h->n_right * (size_t)h->mp_words));
+    h->n_chunks = (int32_t)(((int64_t)h->n_left + RS_STREAM_JC - 1) / RS_STREAM_JC);
     RS_TRY(rs_alloc(h, &h->r_dev, (size_t)h->nnz));
-    RS_TRY(rs_alloc(h, &h->r_dev2, (size_t)h->nnz));
-    RS_CUDA(cudaMemsetAsync(h->mp, 0, bytes, st));
-    build_mp_kernel<<<blocks_for((int64_t)h->n_right * 32), T, 0, st>>>(
-        h->r_ptr, h->r_col, h->r_val, h->n_right, h->mp_words, h->p.sim, h->pmeans, h->left_bias, h->right_bias,
-        h->global_bias, h->mp, h->r_dev, h->r_dev2);
-    h->prof.total_launches++;
+    RS_TRY(rs_alloc(h, &h->l2r, (size_t)h->nnz));
+    RS_TRY(rs_alloc(h, &h->cp, (size_t)h->n_right * ((size_t)h->n_chunks + 1)));
+    build_rdev_kernel<<<blocks_for((int64_t)h->n_right * 32), T, 0, st>>>(
+        h->r_ptr, h->r_col, h->r_val, h->n_right, h->p.sim, h->pmeans, h->left_bias, h->right_bias, h->global_bias,
+        h->r_dev);
+    build_cp_kernel<<<blocks_for((int64_t)h->n_right * (h->n_chunks + 1)), T, 0, st>>>(
+        h->r_ptr, h->r_col, h->n_right, h->n_chunks, RS_STREAM_JC, h->cp);
+    build_l2r_kernel<<<blocks_for((int64_t)h->n_right * 32), T, 0, st>>>(h->l_ptr, h->l_col, h->r_ptr, h->r_col,
+                                                                        h->n_right, h->l2r);
+    h->prof.total_launches += 3;
     RS_CUDA(cudaGetLastError());
     return RS_OK;
 }

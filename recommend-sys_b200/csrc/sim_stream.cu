@@ -2,151 +2,142 @@
 //
 // Reproduces core/sim.go (Cosine :10-25, MSD :28-44, Pearson :47-81) bit for bit.  For a left
 // row i the reference walks i's entries in ascending right id c and, for every other left row
-// j that also rated c, adds one term to each of three running sums — in that order.  Here
-//   * a thread OWNS 8 consecutive j and their accumulators (shared memory, layout
-//     [sum][bit][thread] so a warp's 64-bit accesses never bank-conflict);
-//   * the CTA walks row i's entries in ascending c; per entry every thread reads one 8-byte
-//     {mask, prefix} word of the bit matrix  MP[c][j/32]  (bit = "row j rated c", prefix =
-//     rank of the word's first entry in c's id-sorted rating list) and visits ONLY its set
-//     bits; the b-side term of each visited entry (rating - row mean, core/sim.go:74, and its
-//     square) was precomputed once per rating in the same IEEE operations;
-//   * each accumulator therefore receives exactly the reference's terms in the reference's
-//     order (the library is built with --fmad=false).
-// Work is proportional to the co-rated triples plus one 8-byte word per (entry, 32 columns),
-// not to N x nnz bytes.  Bound: issue slots / FP64 pipe / L2; see DESIGN.md and profiles/.
+// j that also rated c, adds one term to each of three running sums — in that order.
+//
+// Mapping ("column walk"): one WARP owns a work item (row i, chunk of JC consecutive columns j)
+// and keeps that chunk's accumulators in shared memory.  It walks row i's entries in ascending
+// c; for each c the raters of c that fall in the chunk are a CONTIGUOUS slice of c's id-sorted
+// list in the right CSR (chunk pointers `cp`, precomputed), so the lanes read (j, b-side term)
+// coalesced and update acc[j] — every j at most once per c, and c strictly in order, so each
+// accumulator receives exactly the reference's terms in the reference's order with the same
+// IEEE operations (the library is built with --fmad=false).  With the full matrix only j > i
+// is visited (the slice starts right after i's own position in c's list, `l2r`); the mirror
+// pass fills j < i.  Work = the co-rated triples; no N x nnz term anywhere.
+//
+// Bound: shared-memory RMW bandwidth (6 accesses per triple, random banks) and L2 reads of
+// 12 B per triple; see DESIGN.md and profiles/.
 #include "common.cuh"
 
 namespace {
 
-constexpr int ST = RS_STREAM_THREADS;      // 256 threads
-constexpr int JPT = RS_STREAM_JPT;         // 8 columns per thread
-constexpr int TS = 256;                    // entries of row i staged per pass
+constexpr int SW = RS_STREAM_WARPS;        // warps per CTA, each an independent work item
+constexpr int JC = RS_STREAM_JC;           // columns per work item
 
 struct StreamArgs {
     const int64_t *l_ptr;
     const int32_t *l_col;
     const double *l_val;
+    const int64_t *l2r;       // left-CSR entry (i,c) -> index of (c,i) in the right CSR
     const int64_t *r_ptr;
-    const uint2 *mp;          // [n_right][words] {mask, prefix}
-    int64_t words;            // words per right row (multiple of ST*JPT/32)
-    const double *r_dev;      // b-side term per right-CSR entry
-    const double *r_dev2;     // its square
+    const int32_t *r_col;
+    const double *r_dev;      // b-side term per right-CSR entry (rating, or rating - row mean, ...)
+    const int32_t *cp;        // [n_right][Q+1] offsets (relative to r_ptr[c]) of the chunk boundaries
+    int32_t n_chunks;         // Q
     const double *pmeans;
     const double *left_bias, *right_bias;
     double global_bias, shrinkage;
     double *sims;
     int64_t ld_s;
     int32_t n_left;
-    int64_t row_begin;
+    int64_t row_begin, row_end;
     int symmetric;            // 1: only columns j > i are computed (the mirror pass fills j < i)
+    unsigned long long *counter;
 };
 
 template <int SIM, bool SHRINK>
-__global__ void __launch_bounds__(ST) sim_stream_kernel(StreamArgs a) {
+__global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
     constexpr int NACC = SHRINK ? 4 : 3;
-    extern __shared__ double s_acc[];      // [NACC][JPT][ST]
-    __shared__ int32_t s_c[TS];
-    __shared__ int64_t s_off[TS];
-    __shared__ double s_a[TS];
-    __shared__ double s_aa[TS];
+    extern __shared__ double s_acc_all[];                    // [SW][NACC][JC]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *acc = s_acc_all + (size_t)warp * NACC * JC;
+    const int64_t Q = a.n_chunks;
+    const int64_t n_items = (a.row_end - a.row_begin) * Q;
+    const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
 
-    const int tid = threadIdx.x;
-    const int32_t i = (int32_t)(a.row_begin + blockIdx.y);
-    const int64_t jb = ((int64_t)blockIdx.x * ST + tid) * JPT;          // first column of this thread
-    if (a.symmetric && ((int64_t)(blockIdx.x + 1) * ST * JPT <= (int64_t)i)) return;  // every column of this CTA is < i
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(a.counter, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if ((int64_t)item >= n_items) break;
+        // heavy rows first would need a sort; rows are interleaved instead: item -> (q, i)
+        const int64_t q = (int64_t)item % Q;
+        const int32_t i = (int32_t)(a.row_begin + (int64_t)item / Q);
+        const int64_t j0 = q * JC;
+        if (a.symmetric && j0 + JC <= (int64_t)i) continue;  // every column of the chunk is < i
 
-    // bits of this thread's byte that take part
-    uint32_t keep = 0;
-#pragma unroll
-    for (int b = 0; b < JPT; b++) {
-        const int64_t j = jb + b;
-        if (j < a.n_left && j != i && (!a.symmetric || j > i)) keep |= 1u << b;
-    }
-    const int64_t word = jb >> 5;
-    const int shift = (int)(jb & 31);
-    const uint32_t below = (1u << shift) - 1u;                           // bits of the word before my byte
+        for (int x = lane; x < NACC * JC; x += 32) acc[x] = 0.0;
+        __syncwarp();
 
-#pragma unroll
-    for (int k = 0; k < NACC; k++)
-#pragma unroll
-        for (int b = 0; b < JPT; b++) s_acc[(k * JPT + b) * ST + tid] = 0.0;
+        double ai = 0.0;
+        if (SIM == RS_SIM_PEARSON) ai = a.pmeans[i];
+        if (SIM == RS_SIM_PEARSON_BASELINE) ai = a.global_bias + a.left_bias[i];
 
-    double ai = 0.0;
-    if (SIM == RS_SIM_PEARSON) ai = a.pmeans[i];
-    if (SIM == RS_SIM_PEARSON_BASELINE) ai = a.global_bias + a.left_bias[i];
-
-    const int64_t eb = a.l_ptr[i], ee = a.l_ptr[i + 1];
-    for (int64_t base = eb; base < ee; base += TS) {
-        const int cnt = (int)((ee - base) < TS ? (ee - base) : TS);
-        __syncthreads();
-        for (int x = tid; x < cnt; x += ST) {
-            const int32_t c = a.l_col[base + x];
-            const double v = a.l_val[base + x];
-            double ra;
-            if (SIM == RS_SIM_PEARSON) ra = v - ai;                               // core/sim.go:73
-            else if (SIM == RS_SIM_PEARSON_BASELINE) { const double bb = ai + a.right_bias[c]; ra = v - bb; }
-            else ra = v;
-            s_c[x] = c;
-            s_off[x] = a.r_ptr[c];
-            s_a[x] = ra;
-            s_aa[x] = ra * ra;                                                    // core/sim.go:19 / :75
-        }
-        __syncthreads();
-        if (keep == 0) continue;
-
-        for (int x0 = 0; x0 < cnt; x0 += 4) {
-            uint2 w[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int x = x0 + u;
-                w[u] = (x < cnt) ? __ldg(a.mp + (int64_t)s_c[x] * a.words + word) : make_uint2(0u, 0u);
+        const int64_t eb = a.l_ptr[i], ee = a.l_ptr[i + 1];
+        for (int64_t x0 = eb; x0 < ee; x0 += 32) {
+            // each lane prepares one entry (c, x) of row i: its a-side term and the slice of c's list
+            const int64_t e = x0 + lane;
+            double ra = 0.0;
+            int64_t lo = 0, self = -1;
+            int n = 0;
+            if (e < ee) {
+                const int32_t c = a.l_col[e];
+                const double v = a.l_val[e];
+                if (SIM == RS_SIM_PEARSON) ra = v - ai;                           // core/sim.go:73
+                else if (SIM == RS_SIM_PEARSON_BASELINE) { const double bb = ai + a.right_bias[c]; ra = v - bb; }
+                else ra = v;
+                const int64_t rp = a.r_ptr[c];
+                const int32_t *cpc = a.cp + (int64_t)c * (Q + 1) + q;
+                lo = rp + cpc[0];
+                const int64_t hi = rp + cpc[1];
+                self = a.l2r[e];
+                if (a.symmetric && self + 1 > lo) lo = self + 1;                  // only j > i
+                n = hi > lo ? (int)(hi - lo) : 0;
             }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                uint32_t m = (w[u].x >> shift) & 0xffu & keep;
-                if (m == 0) continue;
-                const int x = x0 + u;
-                const uint32_t mine_all = (w[u].x >> shift) & 0xffu;
-                const int64_t first = s_off[x] + w[u].y + __popc(w[u].x & below);  // entry of my byte's bit 0.. in c's list
-                const double ra = s_a[x], raa = s_aa[x];
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int64_t e = first + __popc(mine_all & ((1u << b) - 1u));
-                    double *acc = s_acc + b * ST + tid;
+            const int lim = (ee - x0) < 32 ? (int)(ee - x0) : 32;
+            for (int u = 0; u < lim; u++) {
+                const int n_u = __shfl_sync(0xffffffffu, n, u);
+                if (n_u == 0) continue;
+                const int64_t lo_u = __shfl_sync(0xffffffffu, lo, u);
+                const int64_t self_u = __shfl_sync(0xffffffffu, self, u);
+                const double ra_u = __shfl_sync(0xffffffffu, ra, u);
+                const double raa_u = ra_u * ra_u;                                 // core/sim.go:19 / :75
+                for (int t = lane; t < n_u; t += 32) {
+                    const int64_t idx = lo_u + t;
+                    if (idx == self_u) continue;                                  // the diagonal pair (i,i)
+                    const int j = a.r_col[idx] - (int)j0;
+                    const double rb = a.r_dev[idx];                               // jr | jr - meanB (core/sim.go:74)
                     if (SIM == RS_SIM_MSD) {
-                        const double d = ra - a.r_dev[e];
-                        acc[0] += d * d;                     // sum += (ir-jr)^2   core/sim.go:37
-                        acc[JPT * ST] += 1.0;                // count++            core/sim.go:38
+                        const double d = ra_u - rb;
+                        acc[j] += d * d;                                          // core/sim.go:37
+                        acc[JC + j] += 1.0;                                       // core/sim.go:38
                     } else {
-                        const double rb = a.r_dev[e];        // jr (cosine) / jr - meanB (core/sim.go:74)
-                        acc[0] += raa;                       // m += ..            core/sim.go:19 / :75
-                        acc[JPT * ST] += a.r_dev2[e];        // n += rb*rb         core/sim.go:20 / :76
-                        acc[2 * JPT * ST] += ra * rb;        // l += ra*rb         core/sim.go:21 / :77
-                        if (SHRINK) acc[3 * JPT * ST] += 1.0;
+                        acc[j] += raa_u;                                          // core/sim.go:19 / :75
+                        acc[JC + j] += rb * rb;                                   // core/sim.go:20 / :76
+                        acc[2 * JC + j] += ra_u * rb;                             // core/sim.go:21 / :77
+                        if (SHRINK) acc[3 * JC + j] += 1.0;
                     }
                 }
+                __syncwarp();   // column c is complete before column c+1 touches the same j
             }
         }
-    }
 
-    // epilogue: row i of the shard, 64 contiguous bytes per thread
-    double *out = a.sims + (int64_t)blockIdx.y * a.ld_s + jb;
-#pragma unroll
-    for (int b = 0; b < JPT; b++) {
-        const int64_t j = jb + b;
-        if (j >= a.n_left) continue;
-        if (a.symmetric && j < i) continue;                                       // mirror pass writes it
-        const double *acc = s_acc + b * ST + tid;
-        double s;
-        if (SIM == RS_SIM_MSD) s = 1.0 / (acc[0] / acc[JPT * ST] + 1.0);          // core/sim.go:43
-        else s = acc[2 * JPT * ST] / (sqrt(acc[0]) * sqrt(acc[JPT * ST]));        // core/sim.go:24 / :80
-        if (SHRINK) {
-            const double cn = acc[3 * JPT * ST];
-            s = (cn - 1.0) / (cn - 1.0 + a.shrinkage) * s;
+        // epilogue: JC similarities of row i, coalesced
+        double *out = a.sims + (int64_t)(i - a.row_begin) * a.ld_s + j0;
+        for (int j = lane; j < JC; j += 32) {
+            const int64_t col = j0 + j;
+            if (col >= a.n_left) break;
+            if (a.symmetric && col < i) continue;                                 // mirror pass writes it
+            double s;
+            if (SIM == RS_SIM_MSD) s = 1.0 / (acc[j] / acc[JC + j] + 1.0);        // core/sim.go:43
+            else s = acc[2 * JC + j] / (sqrt(acc[j]) * sqrt(acc[JC + j]));        // core/sim.go:24 / :80
+            if (SHRINK) {
+                const double cn = acc[3 * JC + j];
+                s = (cn - 1.0) / (cn - 1.0 + a.shrinkage) * s;
+            }
+            if (col == (int64_t)i) s = nan_v;                                     // diagonal stays NaN
+            out[j] = s;
         }
-        if (j == (int64_t)i) s = __longlong_as_double(0x7ff8000000000001ll);      // diagonal stays NaN
-        out[b] = s;
+        __syncwarp();
     }
 }
 
@@ -174,44 +165,43 @@ __global__ void symmetrize_kernel(double *__restrict__ s, int64_t ld, int32_t n,
 }  // namespace
 
 template <int SIM, bool SHRINK>
-static int32_t launch_stream(rs_knn *h, const StreamArgs &s, dim3 g) {
-    const int smem = (SHRINK ? 4 : 3) * JPT * ST * (int)sizeof(double);
+static int32_t launch_stream(rs_knn *h, const StreamArgs &s, int grid) {
+    const int smem = SW * (SHRINK ? 4 : 3) * JC * (int)sizeof(double);
     auto kern = sim_stream_kernel<SIM, SHRINK>;
     RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<g, ST, smem, h->stream>>>(s);
+    kern<<<grid, SW * 32, smem, h->stream>>>(s);
     return RS_OK;
 }
 
 int32_t rs_sim_stream_launch(rs_knn *h) {
     StreamArgs a{};
-    a.l_ptr = h->l_ptr; a.l_col = h->l_col; a.l_val = h->l_val; a.r_ptr = h->r_ptr;
-    a.mp = h->mp; a.words = h->mp_words; a.r_dev = h->r_dev; a.r_dev2 = h->r_dev2;
+    a.l_ptr = h->l_ptr; a.l_col = h->l_col; a.l_val = h->l_val; a.l2r = h->l2r;
+    a.r_ptr = h->r_ptr; a.r_col = h->r_col; a.r_dev = h->r_dev; a.cp = h->cp; a.n_chunks = h->n_chunks;
     a.pmeans = h->pmeans; a.left_bias = h->left_bias; a.right_bias = h->right_bias;
     a.global_bias = h->global_bias; a.shrinkage = h->p.shrinkage;
-    a.sims = h->sims; a.ld_s = h->ld_s; a.n_left = h->n_left; a.row_begin = h->row_begin;
-    const int64_t rows = h->row_end - h->row_begin;
+    a.sims = h->sims; a.ld_s = h->ld_s; a.n_left = h->n_left;
+    a.row_begin = h->row_begin; a.row_end = h->row_end;
     a.symmetric = (h->row_begin == 0 && h->row_end == h->n_left) ? 1 : 0;
-    if (rows <= 0) return RS_OK;
-    const unsigned gx = (unsigned)(h->mp_words * 32 / (ST * JPT));
-    for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
-        StreamArgs s = a;
-        const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
-        s.row_begin = h->row_begin + r0;
-        s.sims = h->sims + r0 * h->ld_s;
-        dim3 g(gx, (unsigned)nr);
-        switch (h->p.sim) {
-        case RS_SIM_COSINE: RS_TRY((launch_stream<RS_SIM_COSINE, false>(h, s, g))); break;
-        case RS_SIM_MSD: RS_TRY((launch_stream<RS_SIM_MSD, false>(h, s, g))); break;
-        case RS_SIM_PEARSON: RS_TRY((launch_stream<RS_SIM_PEARSON, false>(h, s, g))); break;
-        case RS_SIM_PEARSON_BASELINE:
-            if (h->p.shrinkage > 0.0) RS_TRY((launch_stream<RS_SIM_PEARSON_BASELINE, true>(h, s, g)));
-            else RS_TRY((launch_stream<RS_SIM_PEARSON_BASELINE, false>(h, s, g)));
-            break;
-        default: rs_set_error("unknown similarity %d", h->p.sim); return RS_ERR_INVALID;
-        }
-        h->prof.sim_launches++;
-        h->prof.total_launches++;
+    if (h->row_end <= h->row_begin) return RS_OK;
+    a.counter = reinterpret_cast<unsigned long long *>(h->d_flags + 2);
+    RS_CUDA(cudaMemsetAsync(a.counter, 0, 8, h->stream));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int64_t items = (h->row_end - h->row_begin) * (int64_t)h->n_chunks;
+    int64_t grid = (int64_t)sms * 4;          // resident CTAs; warps pull work items from the counter
+    if (grid > (items + SW - 1) / SW) grid = (items + SW - 1) / SW;
+    switch (h->p.sim) {
+    case RS_SIM_COSINE: RS_TRY((launch_stream<RS_SIM_COSINE, false>(h, a, (int)grid))); break;
+    case RS_SIM_MSD: RS_TRY((launch_stream<RS_SIM_MSD, false>(h, a, (int)grid))); break;
+    case RS_SIM_PEARSON: RS_TRY((launch_stream<RS_SIM_PEARSON, false>(h, a, (int)grid))); break;
+    case RS_SIM_PEARSON_BASELINE:
+        if (h->p.shrinkage > 0.0) RS_TRY((launch_stream<RS_SIM_PEARSON_BASELINE, true>(h, a, (int)grid)));
+        else RS_TRY((launch_stream<RS_SIM_PEARSON_BASELINE, false>(h, a, (int)grid)));
+        break;
+    default: rs_set_error("unknown similarity %d", h->p.sim); return RS_ERR_INVALID;
     }
+    h->prof.sim_launches++;
+    h->prof.total_launches++;
     RS_CUDA(cudaGetLastError());
     return RS_OK;
 }
