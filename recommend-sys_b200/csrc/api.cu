@@ -40,6 +40,7 @@ void free_fit_state(rs_knn *h) {
     h->r_dev = nullptr;
     h->cp = nullptr;
     h->l2r = nullptr;
+    h->row_order = nullptr;
     h->planes = nullptr;
     h->row_cnt = h->row_sum = nullptr;
     h->sims = nullptr;

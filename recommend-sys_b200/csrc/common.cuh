@@ -34,8 +34,8 @@ enum { RS_CLASS_INT8 = 0, RS_CLASS_TABLE = 1 };
 constexpr int RS_INT8_BIAS = 12;
 
 // Column-chunk width of the streaming similarity kernel (threads * bytes per thread).
-constexpr int RS_STREAM_WARPS = 4;   // warps per CTA, each an independent (row, column-chunk) work item
-constexpr int RS_STREAM_JC = 512;    // columns per work item (3 x 512 doubles of accumulators per warp)
+constexpr int RS_STREAM_WARPS = 8;   // warps per CTA, each an independent (row, column-chunk) work item
+constexpr int RS_STREAM_JC = 256;    // columns per work item (3 x 256 doubles of accumulators per warp)
 
 // Tensor-core similarity kernel tile: 128 left rows (MMA M) x 64 left rows (MMA N),
 // K blocked by 128 bytes (one SWIZZLE_128B atom) per pipeline stage.
@@ -99,6 +99,7 @@ struct rs_knn {
     int32_t *cp = nullptr;
     int32_t n_chunks = 0;
     int64_t *l2r = nullptr;
+    int32_t *row_order = nullptr;  // left rows sorted by descending length
     // int8 planes X, X^2, M of the left matrix, [3][n_pad][k_pad], K-major (tensor path)
     int8_t *planes = nullptr;
     int64_t tc_npad = 0, tc_kpad = 0;

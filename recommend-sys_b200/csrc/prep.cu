@@ -210,6 +210,14 @@ __global__ void build_rdev_kernel(const int64_t *__restrict__ r_ptr, const int32
     }
 }
 
+__global__ void row_len_kernel(const int64_t *__restrict__ l_ptr, int32_t n_left, int32_t *__restrict__ len,
+                               int32_t *__restrict__ ids) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_left) return;
+    len[i] = (int32_t)(l_ptr[i + 1] - l_ptr[i]);
+    ids[i] = i;
+}
+
 // cp[c][q] = number of entries of right row c with left id < q*JC (lower bound by binary search)
 __global__ void build_cp_kernel(const int64_t *__restrict__ r_ptr, const int32_t *__restrict__ r_col,
                                 int32_t n_right, int32_t n_chunks, int32_t jc, int32_t *__restrict__ cp) {
@@ -460,6 +468,31 @@ int32_t rs_prep_rt(rs_knn *h) {
     build_l2r_kernel<<<blocks_for((int64_t)h->n_right * 32), T, 0, st>>>(h->l_ptr, h->l_col, h->r_ptr, h->r_col,
                                                                         h->n_right, h->l2r);
     h->prof.total_launches += 3;
+    // rows of every possible shard ordered longest first: a stable descending sort of the row
+    // lengths inside the shard keeps the order deterministic
+    {
+        const int64_t rb = h->row_begin, rows = h->row_end - h->row_begin;
+        int32_t *len, *len_sorted, *ids;
+        RS_TRY(rs_alloc(h, &len, (size_t)h->n_left));
+        RS_TRY(rs_alloc(h, &len_sorted, (size_t)h->n_left));
+        RS_TRY(rs_alloc(h, &ids, (size_t)h->n_left));
+        RS_TRY(rs_alloc(h, &h->row_order, (size_t)h->n_left));
+        row_len_kernel<<<blocks_for(h->n_left), T, 0, st>>>(h->l_ptr, h->n_left, len, ids);
+        h->prof.total_launches++;
+        if (h->p.store == RS_STORE_TOPK) {
+            // rows are produced slab by slab into a slab-sized buffer: keep the natural order
+            RS_CUDA(cudaMemcpyAsync(h->row_order, ids, (size_t)h->n_left * 4, cudaMemcpyDeviceToDevice, st));
+            RS_CUDA(cudaGetLastError());
+            return RS_OK;
+        }
+        size_t need = 0;
+        RS_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, len + rb, len_sorted + rb, ids + rb,
+                                                          h->row_order + rb, (int)rows, 0, 32, st));
+        void *tmp;
+        RS_TRY(rs_dev_alloc(h, &tmp, need));
+        RS_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, need, len + rb, len_sorted + rb, ids + rb,
+                                                          h->row_order + rb, (int)rows, 0, 32, st));
+    }
     RS_CUDA(cudaGetLastError());
     return RS_OK;
 }

@@ -31,6 +31,7 @@ struct StreamArgs {
     const int64_t *r_ptr;
     const int32_t *r_col;
     const double *r_dev;      // b-side term per right-CSR entry (rating, or rating - row mean, ...)
+    const int32_t *row_order; // left rows of the shard, longest first (load balance)
     const int32_t *cp;        // [n_right][Q+1] offsets (relative to r_ptr[c]) of the chunk boundaries
     int32_t n_chunks;         // Q
     const double *pmeans;
@@ -43,6 +44,22 @@ struct StreamArgs {
     int symmetric;            // 1: only columns j > i are computed (the mirror pass fills j < i)
     unsigned long long *counter;
 };
+
+constexpr int G = 8;   // columns whose first 32 raters are loaded together (must divide 32)
+
+template <int SIM, bool SHRINK>
+__device__ __forceinline__ void stream_update(double *acc, int j, double ra, double raa, double rb) {
+    if (SIM == RS_SIM_MSD) {
+        const double d = ra - rb;
+        acc[j] += d * d;                 // sum += (ir-jr)^2   core/sim.go:37
+        acc[JC + j] += 1.0;              // count++            core/sim.go:38
+    } else {
+        acc[j] += raa;                   // m += ..            core/sim.go:19 / :75
+        acc[JC + j] += rb * rb;          // n += rb*rb         core/sim.go:20 / :76
+        acc[2 * JC + j] += ra * rb;      // l += ra*rb         core/sim.go:21 / :77
+        if (SHRINK) acc[3 * JC + j] += 1.0;
+    }
+}
 
 template <int SIM, bool SHRINK>
 __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
@@ -59,9 +76,9 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
         if (lane == 0) item = atomicAdd(a.counter, 1ull);
         item = __shfl_sync(0xffffffffu, item, 0);
         if ((int64_t)item >= n_items) break;
-        // heavy rows first would need a sort; rows are interleaved instead: item -> (q, i)
+        // items are ordered longest row first, so the critical path starts early
         const int64_t q = (int64_t)item % Q;
-        const int32_t i = (int32_t)(a.row_begin + (int64_t)item / Q);
+        const int32_t i = a.row_order[(int64_t)item / Q];
         const int64_t j0 = q * JC;
         if (a.symmetric && j0 + JC <= (int64_t)i) continue;  // every column of the chunk is < i
 
@@ -94,30 +111,47 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
                 n = hi > lo ? (int)(hi - lo) : 0;
             }
             const int lim = (ee - x0) < 32 ? (int)(ee - x0) : 32;
-            for (int u = 0; u < lim; u++) {
-                const int n_u = __shfl_sync(0xffffffffu, n, u);
-                if (n_u == 0) continue;
-                const int64_t lo_u = __shfl_sync(0xffffffffu, lo, u);
-                const int64_t self_u = __shfl_sync(0xffffffffu, self, u);
-                const double ra_u = __shfl_sync(0xffffffffu, ra, u);
-                const double raa_u = ra_u * ra_u;                                 // core/sim.go:19 / :75
-                for (int t = lane; t < n_u; t += 32) {
-                    const int64_t idx = lo_u + t;
-                    if (idx == self_u) continue;                                  // the diagonal pair (i,i)
-                    const int j = a.r_col[idx] - (int)j0;
-                    const double rb = a.r_dev[idx];                               // jr | jr - meanB (core/sim.go:74)
-                    if (SIM == RS_SIM_MSD) {
-                        const double d = ra_u - rb;
-                        acc[j] += d * d;                                          // core/sim.go:37
-                        acc[JC + j] += 1.0;                                       // core/sim.go:38
-                    } else {
-                        acc[j] += raa_u;                                          // core/sim.go:19 / :75
-                        acc[JC + j] += rb * rb;                                   // core/sim.go:20 / :76
-                        acc[2 * JC + j] += ra_u * rb;                             // core/sim.go:21 / :77
-                        if (SHRINK) acc[3 * JC + j] += 1.0;
+            // Columns are processed in order, G at a time: the (j, b-side) pairs of the first 32
+            // raters of G consecutive columns are loaded up front (independent L2 requests in
+            // flight), then applied column by column.
+            for (int u0 = 0; u0 < lim; u0 += G) {
+                int jj[G];
+                double rbv[G];
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const int u = u0 + g;                                           // < 32 always (G divides 32)
+                    const int n_u = __shfl_sync(0xffffffffu, n, u);
+                    const int64_t lo_u = __shfl_sync(0xffffffffu, lo, u);
+                    const int64_t self_u = __shfl_sync(0xffffffffu, self, u);
+                    jj[g] = -1;
+                    rbv[g] = 0.0;
+                    if (u < lim && lane < n_u) {
+                        const int64_t idx = lo_u + lane;
+                        if (idx != self_u) {                                        // the diagonal pair (i,i)
+                            jj[g] = a.r_col[idx] - (int)j0;
+                            rbv[g] = a.r_dev[idx];                                  // jr | jr - meanB (core/sim.go:74)
+                        }
                     }
                 }
-                __syncwarp();   // column c is complete before column c+1 touches the same j
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const int u = u0 + g;
+                    const int n_u = __shfl_sync(0xffffffffu, n, u);
+                    if (u >= lim || n_u == 0) continue;                             // warp-uniform
+                    const double ra_u = __shfl_sync(0xffffffffu, ra, u);
+                    const double raa_u = ra_u * ra_u;                               // core/sim.go:19 / :75
+                    if (jj[g] >= 0) stream_update<SIM, SHRINK>(acc, jj[g], ra_u, raa_u, rbv[g]);
+                    if (n_u > 32) {                                                 // long slice: remaining raters
+                        const int64_t lo_u = __shfl_sync(0xffffffffu, lo, u);
+                        const int64_t self_u = __shfl_sync(0xffffffffu, self, u);
+                        for (int t = lane + 32; t < n_u; t += 32) {
+                            const int64_t idx = lo_u + t;
+                            if (idx == self_u) continue;
+                            stream_update<SIM, SHRINK>(acc, a.r_col[idx] - (int)j0, ra_u, raa_u, a.r_dev[idx]);
+                        }
+                    }
+                    __syncwarp();   // column c is complete before column c+1 touches the same j
+                }
             }
         }
 
@@ -177,6 +211,7 @@ int32_t rs_sim_stream_launch(rs_knn *h) {
     StreamArgs a{};
     a.l_ptr = h->l_ptr; a.l_col = h->l_col; a.l_val = h->l_val; a.l2r = h->l2r;
     a.r_ptr = h->r_ptr; a.r_col = h->r_col; a.r_dev = h->r_dev; a.cp = h->cp; a.n_chunks = h->n_chunks;
+    a.row_order = h->row_order + h->row_begin;
     a.pmeans = h->pmeans; a.left_bias = h->left_bias; a.right_bias = h->right_bias;
     a.global_bias = h->global_bias; a.shrinkage = h->p.shrinkage;
     a.sims = h->sims; a.ld_s = h->ld_s; a.n_left = h->n_left;
