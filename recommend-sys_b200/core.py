@@ -341,13 +341,28 @@ class TrainSet(DataSet):
 
 
 def _lookup_table(known_raw, known_inner):
+    """raw id -> inner id.  Dense array when the raw ids are small non-negative integers (the
+    usual case: MovieLens / Netflix ids), sorted table + binary search otherwise."""
+    lo, hi = int(known_raw.min()), int(known_raw.max())
+    if lo >= 0 and hi <= 8 * len(known_raw) + 1024:
+        dense = np.full(hi + 2, newID, dtype=np.int32)
+        dense[known_raw] = known_inner
+        return ("dense", dense)
     uniq, first = np.unique(known_raw, return_index=True)
-    return uniq, np.ascontiguousarray(known_inner[first])
+    return ("sorted", uniq, np.ascontiguousarray(known_inner[first]))
 
 
 def _convert(table, raw):
-    uniq, inner = table
     raw = np.ascontiguousarray(raw, dtype=np.int64)
+    if table[0] == "dense":
+        dense = table[1]
+        ok = (raw >= 0) & (raw < len(dense) - 1)
+        if ok.all():
+            return dense[raw]
+        out = np.full(len(raw), newID, dtype=np.int32)
+        out[ok] = dense[raw[ok]]
+        return out
+    _, uniq, inner = table
     pos = np.clip(np.searchsorted(uniq, raw), 0, len(uniq) - 1)
     out = np.where(uniq[pos] == raw, inner[pos], newID).astype(np.int32)
     return np.ascontiguousarray(out)

@@ -132,11 +132,12 @@ int32_t rs_knn_create(const rs_knn_params *p, rs_knn **out) {
         rs_set_error("device %d out of range (%d devices)", dev, ndev);
         return RS_ERR_INVALID;
     }
-    cudaDeviceProp prop;
-    RS_CUDA(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major != 10) {
-        rs_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major,
-                     prop.minor);
+    int cc_major = 0, cc_minor = 0;   // (cudaGetDeviceProperties costs milliseconds per call)
+    RS_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    RS_CUDA(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    if (cc_major != 10) {
+        rs_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, cc_major,
+                     cc_minor);
         return RS_ERR_UNSUPPORTED;
     }
     rs_knn *h = new (std::nothrow) rs_knn();
