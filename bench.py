@@ -46,6 +46,7 @@ WORKLOADS = {
     "ml1m_item_cosine_k40": (6040, 3706, 1_000_000, 200_000, "cosine", "basic", False, 40),
     "ml1m_item_msd_k40": (6040, 3706, 1_000_000, 200_000, "msd", "basic", False, 40),
     "ml20m_item_cosine_k40": (138_493, 26_744, 20_000_000, 4_000_000, "cosine", "basic", False, 40),
+    "ml20m_item_msd_k40": (138_493, 26_744, 20_000_000, 4_000_000, "msd", "basic", False, 40),
     "ml20m_item_pearson_k40": (138_493, 26_744, 20_000_000, 4_000_000, "pearson", "centered", False, 40),
     "ml20m_user_msd_k100": (138_493, 26_744, 20_000_000, 0, "msd", "basic", True, 100),
     "netflix_item_cosine_k50": (480_189, 17_770, 100_000_000, 20_000_000, "cosine", "basic", False, 50),

@@ -29,6 +29,7 @@
 //               handle runs every bj for its own row blocks and writes S[i][j] only.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -114,6 +115,25 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2,
+                                               uint32_t bar, uint16_t cta_mask) {
+    // the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and each of them
+    // gets the complete_tx on its own mbarrier at the same offset
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -140,6 +160,13 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
 // mbarrier arrive once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// same, arriving on the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(cta_mask)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t addr, int32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -195,10 +222,24 @@ __device__ __forceinline__ double pearson_from_sums(long long n, long long sx, l
     return (double)L / (sqrt((double)Mi) * sqrt((double)Ni));
 }
 
-template <int MODE>
+// CI x CJ = thread-block cluster shape.  The CTAs of a cluster work on CI x CJ adjacent tiles in
+// lockstep and share their operand loads: the A tile of a row block is needed by the CJ CTAs of
+// that cluster row, so each of them TMA-loads 1/CJ of it and MULTICASTS the slice to all CJ; the B
+// tile of a column block is shared the same way by the CI CTAs of a cluster column.  Per tile and
+// K block this cuts the L2/HBM operand traffic from 72 KB to 48/CJ + 24/CI KB.
+template <int MODE, int CI, int CJ>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
     using C = Cfg<MODE>;
+    constexpr int CS = CI * CJ;
+    const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
+    const int ci = crank / CJ, cj = crank % CJ;
+    const int cluster_id = blockIdx.x / CS, n_clusters = gridDim.x / CS;
+    uint16_t mask_a = 0, mask_b = 0;        // CTAs sharing my A tile (cluster row) / my B tile (cluster column)
+#pragma unroll
+    for (int x = 0; x < CJ; x++) mask_a |= (uint16_t)(1u << (ci * CJ + x));
+#pragma unroll
+    for (int y = 0; y < CI; y++) mask_b |= (uint16_t)(1u << (y * CJ + cj));
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B needs 1024-byte aligned tiles
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -219,7 +260,7 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         tma_prefetch_desc(&map_b);
         for (int s = 0; s < STAGES; s++) {
             mbar_init(full_bar + 8 * s, 1);
-            mbar_init(empty_bar + 8 * s, 1);
+            mbar_init(empty_bar + 8 * s, CI + CJ - 1);   // released by every CTA I multicast into
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(tfull_bar + 8 * s, 1);
@@ -230,6 +271,7 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();   // every CTA's barriers exist before a peer can signal them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -238,16 +280,24 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+            constexpr int A_SLICE = BM / CJ, B_SLICE = BN / CI;   // rows this CTA loads (and multicasts)
+            for (int t = cluster_id; t < a.num_tiles; t += n_clusters) {
                 const int2 tile = a.tiles[t];
-                const int row_a = tile.x * BM, row_b = tile.y * BN;
+                const int row_a = (tile.x * CI + ci) * BM + cj * A_SLICE;
+                const int row_b = (tile.y * CJ + cj) * BN + ci * B_SLICE;
                 for (int kb = 0; kb < a.k_blocks; kb++) {
-                    mbar_wait(empty_bar + 8 * stage, phase ^ 1u, 0);
-                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                    const uint32_t sb = sa + A_STAGE_BYTES;
-                    mbar_arrive_expect_tx(full_bar + 8 * stage, STAGE_BYTES);
-                    tma_load_3d(sa, &map_a, kb * BK, row_a, 0, full_bar + 8 * stage);
-                    tma_load_3d(sb, &map_b, kb * BK, row_b, 0, full_bar + 8 * stage);
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1u, 0);   // all my destinations freed the stage
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES + cj * A_SLICE * BK;
+                    const uint32_t sb = smem_base + stage * STAGE_BYTES + A_STAGE_BYTES + ci * B_SLICE * BK;
+                    const uint32_t fb = full_bar + 8 * stage;
+                    mbar_arrive_expect_tx(fb, STAGE_BYTES);            // my own stage: slices from all peers
+#pragma unroll
+                    for (int p = 0; p < 3; p++) {
+                        if (CJ > 1) tma_load_3d_mc(sa + p * A_PLANE_BYTES, &map_a, kb * BK, row_a, p, fb, mask_a);
+                        else tma_load_3d(sa + p * A_PLANE_BYTES, &map_a, kb * BK, row_a, p, fb);
+                        if (CI > 1) tma_load_3d_mc(sb + p * B_PLANE_BYTES, &map_b, kb * BK, row_b, p, fb, mask_b);
+                        else tma_load_3d(sb + p * B_PLANE_BYTES, &map_b, kb * BK, row_b, p, fb);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -259,7 +309,7 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+            for (int t = cluster_id; t < a.num_tiles; t += n_clusters) {
                 mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1u, 1);   // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * C::ACC_COLS);
@@ -292,7 +342,9 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             umma_i8(d0 + C::C_SXX, a_x2, b_m, make_idesc(64), accum);
                         }
                     }
-                    umma_commit(empty_bar + 8 * stage);               // frees the smem stage when done
+                    // frees the smem stage (in every CTA that multicasts into it) once the MMAs are done
+                    if (CS > 1) umma_commit_mc(empty_bar + 8 * stage, (uint16_t)(mask_a | mask_b));
+                    else umma_commit(empty_bar + 8 * stage);
                     if (kb == a.k_blocks - 1) umma_commit(tfull_bar + 8 * acc);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -306,10 +358,10 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
-        for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+        for (int t = cluster_id; t < a.num_tiles; t += n_clusters) {
             const int2 tile = a.tiles[t];
-            const int64_t i = (int64_t)tile.x * BM + r_in_tile;
-            const int64_t j0 = (int64_t)tile.y * BN;
+            const int64_t i = ((int64_t)tile.x * CI + ci) * BM + r_in_tile;
+            const int64_t j0 = ((int64_t)tile.y * CJ + cj) * BN;
             mbar_wait(tfull_bar + 8 * acc, acc_phase, 3);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::ACC_COLS);
@@ -390,6 +442,7 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();   // no CTA leaves while a peer may still write into it
     tc_fence_after();
     if (warp == 1) {
         __syncwarp();
@@ -422,7 +475,7 @@ int32_t make_map(const rs_knn *h, int box_rows, CUtensorMap *map) {
     RS_TRY(get_encode_fn(&enc));
     const cuuint64_t dims[3] = {(cuuint64_t)h->tc_kpad, (cuuint64_t)h->tc_npad, 3};
     const cuuint64_t strides[2] = {(cuuint64_t)h->tc_kpad, (cuuint64_t)h->tc_kpad * (cuuint64_t)h->tc_npad};
-    const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 3};
+    const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};   // one plane per TMA instruction
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->planes, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -435,13 +488,53 @@ int32_t make_map(const rs_knn *h, int box_rows, CUtensorMap *map) {
     return RS_OK;
 }
 
-template <int MODE>
-int32_t launch_mode(rs_knn *h, const CUtensorMap &ma, const CUtensorMap &mb, const TcArgs &a, int grid) {
-    auto kern = sim_tensor_kernel<MODE>;
+template <int MODE, int CI, int CJ>
+int32_t launch_mode(rs_knn *h, const TcArgs &a) {
+    constexpr int CS = CI * CJ;
+    CUtensorMap ma, mb;
+    RS_TRY(make_map(h, BM / CJ, &ma));
+    RS_TRY(make_map(h, BN / CI, &mb));
+    auto kern = sim_tensor_kernel<MODE, CI, CJ>;
     RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    kern<<<grid, NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, a);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n_clusters = sms / CS;
+    if (CS > 1) {
+        cfg.gridDim = dim3((unsigned)(n_clusters * CS));
+        int max_clusters = 0;
+        RS_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+        if (max_clusters < 1) {
+            rs_set_error("a %d-CTA cluster of the tensor kernel does not fit on this device", CS);
+            return RS_ERR_CUDA;
+        }
+        if (n_clusters > max_clusters) n_clusters = max_clusters;   // persistent: one resident wave
+    }
+    if (n_clusters > a.num_tiles) n_clusters = a.num_tiles;
+    cfg.gridDim = dim3((unsigned)(n_clusters * CS));
+    RS_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, a));
     RS_CUDA(cudaGetLastError());
     return RS_OK;
+}
+
+template <int CI, int CJ>
+int32_t launch_shape(rs_knn *h, const TcArgs &a, bool cosums) {
+    if (cosums) return launch_mode<TC_COSUMS, CI, CJ>(h, a);
+    if (h->p.sim == RS_SIM_COSINE) return launch_mode<TC_COSINE, CI, CJ>(h, a);
+    if (h->p.sim == RS_SIM_MSD) return launch_mode<TC_MSD, CI, CJ>(h, a);
+    if (h->p.sim == RS_SIM_PEARSON) return launch_mode<TC_PEARSON, CI, CJ>(h, a);
+    rs_set_error("tensor path supports Cosine, MSD and Pearson (sums mode) only");
+    return RS_ERR_UNSUPPORTED;
 }
 
 }  // namespace
@@ -456,14 +549,35 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
     const int64_t re = cosums ? cos_row0 + cos_nrows : h->row_end;
     if (re <= rb) return RS_OK;
     const bool mirror = !cosums && rb == 0 && re == h->n_left;
+    // cluster shape: 2 x 4 tiles share their operand loads; small problems (fewer tiles than
+    // SMs) run unclustered so every SM gets a tile.  RS_KNN_TC_CLUSTER=1x1|1x2|2x2|2x4 overrides.
+    int ci = 2, cj = 4;
+    const int64_t plain_tiles = ((re - rb + BM - 1) / BM) * ((h->n_left + BN - 1) / BN) / (mirror ? 2 : 1);
+    if (plain_tiles < 4 * 148) { ci = 1; cj = 1; }
+    if (const char *e = getenv("RS_KNN_TC_CLUSTER")) {
+        if (!strcmp(e, "1x1")) { ci = 1; cj = 1; }
+        else if (!strcmp(e, "1x2")) { ci = 1; cj = 2; }
+        else if (!strcmp(e, "2x2")) { ci = 2; cj = 2; }
+        else if (!strcmp(e, "2x4")) { ci = 2; cj = 4; }
+    }
+    // tile list in units of cluster tiles (ci x cj plain tiles each)
     const int nbj = (int)((h->n_left + BN - 1) / BN);
     const int bi0 = (int)(rb / BM), bi1 = (int)((re + BM - 1) / BM);
-    // the static tile list depends only on (n_left, shard, mirror): build it once per shape
-    const int64_t key[4] = {h->n_left, rb, re, mirror ? 1 : 0};
+    const int64_t key[4] = {h->n_left, rb, re, (mirror ? 1 : 0) + 2 * (ci * 16 + cj)};
     if (memcmp(key, h->tile_key, sizeof(key)) != 0) {
+        // Rasterised in supertiles so concurrently running clusters touch few distinct row blocks.
+        const int SUP_I = 8 / ci > 0 ? 8 / ci : 1, SUP_J = 16 / cj > 0 ? 16 / cj : 1;
+        const int cbi0 = bi0 / ci, cbi1 = (bi1 + ci - 1) / ci, ncbj = (nbj + cj - 1) / cj;
         std::vector<int2> tiles;
-        for (int bi = bi0; bi < bi1; bi++)
-            for (int bj = mirror ? 2 * bi : 0; bj < nbj; bj++) tiles.push_back(make_int2(bi, bj));
+        auto needed = [&](int cbi, int cbj) {
+            // mirror mode keeps a cluster tile iff any of its plain tiles has bj >= 2*bi
+            return !mirror || (cbj * cj + cj - 1) >= 2 * (cbi * ci);
+        };
+        for (int sbi = cbi0; sbi < cbi1; sbi += SUP_I)
+            for (int sbj = 0; sbj < ncbj; sbj += SUP_J)
+                for (int cbi = sbi; cbi < sbi + SUP_I && cbi < cbi1; cbi++)
+                    for (int cbj = sbj; cbj < sbj + SUP_J && cbj < ncbj; cbj++)
+                        if (needed(cbi, cbj)) tiles.push_back(make_int2(cbi, cbj));
         const size_t bytes = tiles.size() * sizeof(int2);
         if (bytes > h->tile_buf_bytes) {
             RS_CUDA(cudaStreamSynchronize(h->stream));
@@ -481,14 +595,9 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
         h->tile_count = (int32_t)tiles.size();
     }
     if (h->tile_count == 0) return RS_OK;
-    const int2 *d_tiles = reinterpret_cast<const int2 *>(h->tile_buf);
-
-    CUtensorMap ma, mb;
-    RS_TRY(make_map(h, BM, &ma));
-    RS_TRY(make_map(h, BN, &mb));
 
     TcArgs a{};
-    a.tiles = d_tiles;
+    a.tiles = reinterpret_cast<const int2 *>(h->tile_buf);
     a.num_tiles = h->tile_count;
     a.k_blocks = (int32_t)(h->tc_kpad / BK);
     a.n_left = h->n_left;
@@ -502,18 +611,11 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
     a.cosums = d_cosums;
     a.cos_row0 = cos_row0;
     a.cos_nrows = cos_nrows;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    const int grid = a.num_tiles < sms ? a.num_tiles : sms;
     int32_t rc;
-    if (cosums) rc = launch_mode<TC_COSUMS>(h, ma, mb, a, grid);
-    else if (h->p.sim == RS_SIM_COSINE) rc = launch_mode<TC_COSINE>(h, ma, mb, a, grid);
-    else if (h->p.sim == RS_SIM_MSD) rc = launch_mode<TC_MSD>(h, ma, mb, a, grid);
-    else if (h->p.sim == RS_SIM_PEARSON) rc = launch_mode<TC_PEARSON>(h, ma, mb, a, grid);
-    else {
-        rs_set_error("tensor path supports Cosine, MSD and Pearson (sums mode) only");
-        return RS_ERR_UNSUPPORTED;
-    }
+    if (ci == 1 && cj == 1) rc = launch_shape<1, 1>(h, a, cosums);
+    else if (ci == 1 && cj == 2) rc = launch_shape<1, 2>(h, a, cosums);
+    else if (ci == 2 && cj == 2) rc = launch_shape<2, 2>(h, a, cosums);
+    else rc = launch_shape<2, 4>(h, a, cosums);
     RS_TRY(rc);
     if (!cosums) h->prof.sim_launches++;
     h->prof.total_launches++;
