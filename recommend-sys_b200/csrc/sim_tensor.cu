@@ -29,6 +29,7 @@
 //               handle runs every bj for its own row blocks and writes S[i][j] only.
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -559,14 +560,19 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
         else if (!strcmp(e, "1x2")) { ci = 1; cj = 2; }
         else if (!strcmp(e, "2x2")) { ci = 2; cj = 2; }
         else if (!strcmp(e, "2x4")) { ci = 2; cj = 4; }
+        else if (!strcmp(e, "1x4")) { ci = 1; cj = 4; }
+        else if (!strcmp(e, "1x8")) { ci = 1; cj = 8; }
+        else if (!strcmp(e, "2x1")) { ci = 2; cj = 1; }
     }
+    int sup_i = 8, sup_j = 16;   // supertile, in plain tiles
+    if (const char *e = getenv("RS_KNN_TC_SUP")) sscanf(e, "%d,%d", &sup_i, &sup_j);
     // tile list in units of cluster tiles (ci x cj plain tiles each)
     const int nbj = (int)((h->n_left + BN - 1) / BN);
     const int bi0 = (int)(rb / BM), bi1 = (int)((re + BM - 1) / BM);
-    const int64_t key[4] = {h->n_left, rb, re, (mirror ? 1 : 0) + 2 * (ci * 16 + cj)};
+    const int64_t key[4] = {h->n_left, rb, re, (mirror ? 1 : 0) + 2 * (ci * 16 + cj) + 1024 * (sup_i * 4096 + sup_j)};
     if (memcmp(key, h->tile_key, sizeof(key)) != 0) {
         // Rasterised in supertiles so concurrently running clusters touch few distinct row blocks.
-        const int SUP_I = 8 / ci > 0 ? 8 / ci : 1, SUP_J = 16 / cj > 0 ? 16 / cj : 1;
+        const int SUP_I = sup_i / ci > 0 ? sup_i / ci : 1, SUP_J = sup_j / cj > 0 ? sup_j / cj : 1;
         const int cbi0 = bi0 / ci, cbi1 = (bi1 + ci - 1) / ci, ncbj = (nbj + cj - 1) / cj;
         std::vector<int2> tiles;
         auto needed = [&](int cbi, int cbj) {
@@ -614,6 +620,9 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
     int32_t rc;
     if (ci == 1 && cj == 1) rc = launch_shape<1, 1>(h, a, cosums);
     else if (ci == 1 && cj == 2) rc = launch_shape<1, 2>(h, a, cosums);
+    else if (ci == 1 && cj == 4) rc = launch_shape<1, 4>(h, a, cosums);
+    else if (ci == 1 && cj == 8) rc = launch_shape<1, 8>(h, a, cosums);
+    else if (ci == 2 && cj == 1) rc = launch_shape<2, 1>(h, a, cosums);
     else if (ci == 2 && cj == 2) rc = launch_shape<2, 2>(h, a, cosums);
     else rc = launch_shape<2, 4>(h, a, cosums);
     RS_TRY(rc);
