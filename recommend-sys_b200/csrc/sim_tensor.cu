@@ -12,21 +12,25 @@
 // Pearson is the stream path (sim_stream.cu).
 //
 // Kernel shape (one CTA per SM, persistent over a static tile list):
-//   tile      = 128 left rows (MMA M, TMEM lanes) x 64 left rows (MMA N) x all K
-//   operands  = planes laid out [plane][row][K] int8, K-major; TMA 3-D boxes (128 B of K x rows
-//               x 3 planes) with SWIZZLE_128B land one pipeline stage (48 KB A + 24 KB B)
-//   pipeline  = 3 smem stages, mbarrier full/empty ring; warp 0 lane 0 issues TMA, warp 1 lane 0
-//               issues tcgen05.mma, warps 2-5 run the epilogue (tcgen05.ld -> FP64 -> HBM)
+//   tile      = 128 left rows (MMA M, TMEM lanes) x BN left rows (MMA N) x all K;
+//               BN = 128 for Cosine / MSD, 64 for Pearson (six accumulators), see Cfg<>
+//   operands  = planes laid out [plane][row][K] int8, K-major; TMA 3-D boxes (BK bytes of K x rows,
+//               one plane per instruction) land one pipeline stage with SWIZZLE_128B (BK = 128,
+//               Pearson: 3 stages x 72 KB) or SWIZZLE_64B (BK = 64, Cosine / MSD: 4 stages x 48 KB)
+//   pipeline  = mbarrier full/empty ring; warp 0 lane 0 issues TMA, warp 1 lane 0 issues
+//               tcgen05.mma, warps 2-5 run the epilogue (tcgen05.ld -> FP64 -> HBM)
 //   MMAs      = the B planes of a stage are adjacent in shared memory in the order (X2, M, X), so
 //               products that share an A plane are ONE instruction with a wider N:
 //                 Pearson: M_I x [X2|M|X]_J (N=192), X_I x [M|X]_J (N=128), X2_I x M_J (N=64)
-//                 MSD    : M_I x [X2|M]_J (N=128), X_I x X_J, X2_I x M_J
-//                 Cosine : M_I x X2_J, X_I x X_J, X2_I x M_J
-//   TMEM      = 192 / 256 / 384 accumulator columns; Cosine and MSD double-buffer them so the
-//               epilogue of tile t overlaps the MMAs of tile t+1
-//   schedule  = block-triangular: tile (bi,bj) runs iff bj >= 2*bi and writes both S[i][j] and
-//               S[j][i] (the similarities are bit-symmetric, core/knn.go:205-208); a row-sharded
-//               handle runs every bj for its own row blocks and writes S[i][j] only.
+//                 MSD    : M_I x [X2|M]_J (N=256), then X2_I x M_J accumulated INTO the Syy columns
+//                          (only Sxx+Syy is needed), X_I x X_J (N=128)
+//                 Cosine : M_I x X2_J, X_I x X_J, X2_I x M_J (N=128 each)
+//   TMEM      = 384 accumulator columns in every mode
+//   schedule  = block-triangular: a tile runs iff it holds a pair (i, j) with j >= i and writes both
+//               S[i][j] and S[j][i] (the similarities are bit-symmetric, core/knn.go:205-208); a
+//               row-sharded handle runs every bj for its own row blocks and writes S[i][j] only.
+//               Tiles are rasterised in 1024 x 1024 supertiles and the CTAs stream K in lockstep
+//               (throttle in the TMA producer) so that shared operand rows hit in L2.
 #include <cuda.h>
 
 #include <cstdio>
@@ -37,16 +41,7 @@
 
 namespace {
 
-constexpr int BM = RS_TC_BM;   // 128
-constexpr int BN = RS_TC_BN;   // 64
-constexpr int BK = RS_TC_BK;   // 128 bytes of K per stage
-constexpr int STAGES = 3;
-constexpr int A_PLANE_BYTES = BM * BK;            // 16 KB
-constexpr int B_PLANE_BYTES = BN * BK;            // 8 KB
-constexpr int A_STAGE_BYTES = 3 * A_PLANE_BYTES;  // 48 KB
-constexpr int B_STAGE_BYTES = 3 * B_PLANE_BYTES;  // 24 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int BM = RS_TC_BM;   // 128 left rows per tile (MMA M, TMEM lanes)
 constexpr int NUM_THREADS = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
 constexpr int TMEM_COLS = 512;
 
@@ -55,20 +50,43 @@ constexpr int PL_X2 = 0, PL_M = 1, PL_X = 2;
 
 enum { TC_COSINE = 0, TC_MSD = 1, TC_PEARSON = 2, TC_COSUMS = 3 };
 
+// Per-mode tile shape.  Every tcgen05.mma reads its A slab (128 x 32 B) and B slab (N x 32 B) from
+// shared memory, so narrow instructions are shared-memory bound: 3 x N=64 (the first Cosine
+// kernel) measured 52 % of the MMA rate with the loads switched off, the wide Pearson mix 97 %
+// (profiles/r01_tensor_calibration.md).  Cosine and MSD therefore use BN = 128 (instructions of
+// N = 128 / 256) with 64-byte K blocks (SWIZZLE_64B) to keep four 48 KB stages in flight;
+// Pearson keeps BN = 64 (six accumulators = 384 TMEM columns) with 128-byte K blocks.
 template <int MODE> struct Cfg;
 template <> struct Cfg<TC_COSINE> {
-    static constexpr int ACC_COLS = 192, ACC_STAGES = 2;
-    static constexpr int C_SYY = 0, C_SXY = 64, C_SXX = 128, C_CNT = -1, C_SX = -1, C_SY = -1;
+    static constexpr int BN = 128, BK = 64, STAGES = 4;
+    static constexpr int ACC_COLS = 384, ACC_STAGES = 1;
+    static constexpr int C_SYY = 0, C_SXY = 128, C_SXX = 256, C_CNT = -1, C_SX = -1, C_SY = -1;
 };
 template <> struct Cfg<TC_MSD> {
-    static constexpr int ACC_COLS = 256, ACC_STAGES = 2;
-    static constexpr int C_SYY = 0, C_CNT = 64, C_SXY = 128, C_SXX = 192, C_SX = -1, C_SY = -1;
+    // C_SYY holds Sxx + Syy: both products accumulate into the same columns (only the sum is needed)
+    static constexpr int BN = 128, BK = 64, STAGES = 4;
+    static constexpr int ACC_COLS = 384, ACC_STAGES = 1;
+    static constexpr int C_SYY = 0, C_CNT = 128, C_SXY = 256, C_SXX = -1, C_SX = -1, C_SY = -1;
 };
 template <> struct Cfg<TC_PEARSON> {
+    static constexpr int BN = 64, BK = 128, STAGES = 3;
     static constexpr int ACC_COLS = 384, ACC_STAGES = 1;
     static constexpr int C_SYY = 0, C_CNT = 64, C_SY = 128, C_SX = 192, C_SXY = 256, C_SXX = 320;
 };
 template <> struct Cfg<TC_COSUMS> : Cfg<TC_PEARSON> {};
+
+template <int MODE> struct Geo {
+    using C = Cfg<MODE>;
+    static constexpr int BN = C::BN, BK = C::BK, STAGES = C::STAGES;
+    static constexpr int A_PLANE_BYTES = BM * BK;
+    static constexpr int B_PLANE_BYTES = BN * BK;
+    static constexpr int A_STAGE_BYTES = 3 * A_PLANE_BYTES;
+    static constexpr int B_STAGE_BYTES = 3 * B_PLANE_BYTES;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(SMEM_BYTES <= 227 * 1024, "pipeline does not fit in shared memory");
+    static_assert(C::ACC_COLS * C::ACC_STAGES <= TMEM_COLS, "accumulators do not fit in TMEM");
+};
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -177,15 +195,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, int32_t (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major SWIZZLE_128B shared-memory matrix descriptor (one 128-byte swizzle atom along K,
-// 8-row groups 1024 B apart), sm_100 descriptor version 1.
+// K-major shared-memory matrix descriptor, sm_100 descriptor version 1.  One swizzle atom along K
+// (BK = 128 B -> SWIZZLE_128B, BK = 64 B -> SWIZZLE_64B); 8-row groups are 8*BK bytes apart.
+template <int BK_>
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    static_assert(BK_ == 128 || BK_ == 64, "one swizzle atom per K block");
     uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address      bits [0,14)
-    d |= (uint64_t)0 << 16;                         // leading byte offset (unused: one atom along K)
-    d |= (uint64_t)(1024u >> 4) << 32;              // stride byte offset  bits [32,46)
-    d |= (uint64_t)1 << 46;                         // descriptor version  bits [46,48)
-    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B        bits [61,64)
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);            // start address      bits [0,14)
+    d |= (uint64_t)0 << 16;                                  // leading byte offset (unused: one atom along K)
+    d |= (uint64_t)((8u * BK_) >> 4) << 32;                  // stride byte offset  bits [32,46)
+    d |= (uint64_t)1 << 46;                                  // descriptor version  bits [46,48)
+    d |= (uint64_t)(BK_ == 128 ? 2 : 4) << 61;               // SWIZZLE_128B / SWIZZLE_64B  bits [61,64)
     return d;
 }
 // kind::i8 instruction descriptor: D=S32, A=B=signed int8, both K-major, M=128, N=n
@@ -206,7 +226,18 @@ struct TcArgs {
     const int32_t *row_sum;
     int32_t *cosums;        // TC_COSUMS: raw sums of rows [cos_row0, cos_row0+cos_nrows)
     int64_t cos_row0, cos_nrows;
+    int debug;              // RS_KNN_TC_DEBUG (timing experiments only): 1 = no TMA loads, 2 = no MMAs
+    // K-lockstep throttle (performance hint only, see the TMA producer): chunks of `sync_chunk` K
+    // blocks, a CTA may run at most `sync_slack` chunks ahead of the grid's average progress.
+    unsigned long long *progress;
+    int sync_chunk, sync_slack, sync_timeout;
 };
+
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // Pearson from exact integer sums.  With a-row count ca and sum sa (b: cb, sb) and n co-ratings:
 //   m  = sum (x-sa/ca)^2 = Mi/ca^2,  Mi = ca^2*Sxx - 2*ca*sa*Sx + n*sa^2          (integers)
@@ -232,6 +263,10 @@ template <int MODE, int CI, int CJ>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
     using C = Cfg<MODE>;
+    using G = Geo<MODE>;
+    constexpr int BN = G::BN, BK = G::BK, STAGES = G::STAGES;
+    constexpr int A_PLANE_BYTES = G::A_PLANE_BYTES, B_PLANE_BYTES = G::B_PLANE_BYTES;
+    constexpr int A_STAGE_BYTES = G::A_STAGE_BYTES, STAGE_BYTES = G::STAGE_BYTES;
     constexpr int CS = CI * CJ;
     const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
     const int ci = crank / CJ, cj = crank % CJ;
@@ -282,15 +317,35 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             constexpr int A_SLICE = BM / CJ, B_SLICE = BN / CI;   // rows this CTA loads (and multicasts)
+            // K-lockstep throttle.  Tiles that run at the same time share operand rows (supertile
+            // rasterisation), but a row block is tens of MB long in K, so the sharing only hits in
+            // L2 while the CTAs stream through K at the same position; left alone they drift apart
+            // and the DRAM traffic is 3-4x the ideal (profiles/r01_tensor_cos_v2_summary.txt).
+            // Every producer counts the K chunks it has issued in one global counter and does not
+            // start chunk g before the grid as a whole has issued (g - slack) chunks per CTA.  The
+            // wait is bounded and carries no data dependence: on a timeout the CTA just proceeds.
+            const int chunk = a.sync_chunk;
+            const unsigned long long n_ctas = gridDim.x;
+            long long g = 0;
             for (int t = cluster_id; t < a.num_tiles; t += n_clusters) {
                 const int2 tile = a.tiles[t];
                 const int row_a = (tile.x * CI + ci) * BM + cj * A_SLICE;
                 const int row_b = (tile.y * CJ + cj) * BN + ci * B_SLICE;
                 for (int kb = 0; kb < a.k_blocks; kb++) {
+                    if (chunk > 0 && kb % chunk == 0) {
+                        if (g > 0) atomicAdd(a.progress, 1ull);          // chunk g-1 is issued
+                        const long long need = (g - a.sync_slack) * (long long)n_ctas;
+                        if (need > 0 && (long long)ld_relaxed_gpu(a.progress) < need) {
+                            const long long t0 = clock64();
+                            while ((long long)ld_relaxed_gpu(a.progress) < need && clock64() - t0 < a.sync_timeout) {}
+                        }
+                        g++;
+                    }
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1u, 0);   // all my destinations freed the stage
                     const uint32_t sa = smem_base + stage * STAGE_BYTES + cj * A_SLICE * BK;
                     const uint32_t sb = smem_base + stage * STAGE_BYTES + A_STAGE_BYTES + ci * B_SLICE * BK;
                     const uint32_t fb = full_bar + 8 * stage;
+                    if (a.debug & 1) { mbar_arrive(fb); if (++stage == STAGES) { stage = 0; phase ^= 1u; } continue; }
                     mbar_arrive_expect_tx(fb, STAGE_BYTES);            // my own stage: slices from all peers
 #pragma unroll
                     for (int p = 0; p < 3; p++) {
@@ -301,6 +356,12 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
+            }
+            if (chunk > 0) {
+                // done: credit every chunk a CTA with the longest tile list would still issue
+                const long long cpt = (a.k_blocks + chunk - 1) / chunk;
+                const long long max_chunks = (long long)((a.num_tiles + n_clusters - 1) / n_clusters) * cpt;
+                atomicAdd(a.progress, (unsigned long long)(max_chunks - g + 1));
             }
         }
     } else if (warp == 1) {
@@ -320,27 +381,27 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
                     const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BK / 32; k++) {
+                    for (int k = 0; k < ((a.debug & 2) ? 0 : BK / 32); k++) {
                         const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
                         const uint32_t ko = (uint32_t)k * 32u;
-                        const uint64_t a_x2 = make_desc(sa + PL_X2 * A_PLANE_BYTES + ko);
-                        const uint64_t a_m = make_desc(sa + PL_M * A_PLANE_BYTES + ko);
-                        const uint64_t a_x = make_desc(sa + PL_X * A_PLANE_BYTES + ko);
-                        const uint64_t b_x2 = make_desc(sb + PL_X2 * B_PLANE_BYTES + ko);
-                        const uint64_t b_m = make_desc(sb + PL_M * B_PLANE_BYTES + ko);
-                        const uint64_t b_x = make_desc(sb + PL_X * B_PLANE_BYTES + ko);
+                        const uint64_t a_x2 = make_desc<BK>(sa + PL_X2 * A_PLANE_BYTES + ko);
+                        const uint64_t a_m = make_desc<BK>(sa + PL_M * A_PLANE_BYTES + ko);
+                        const uint64_t a_x = make_desc<BK>(sa + PL_X * A_PLANE_BYTES + ko);
+                        const uint64_t b_x2 = make_desc<BK>(sb + PL_X2 * B_PLANE_BYTES + ko);
+                        const uint64_t b_m = make_desc<BK>(sb + PL_M * B_PLANE_BYTES + ko);
+                        const uint64_t b_x = make_desc<BK>(sb + PL_X * B_PLANE_BYTES + ko);
                         if constexpr (MODE == TC_COSINE) {
-                            umma_i8(d0 + C::C_SYY, a_m, b_x2, make_idesc(64), accum);
-                            umma_i8(d0 + C::C_SXY, a_x, b_x, make_idesc(64), accum);
-                            umma_i8(d0 + C::C_SXX, a_x2, b_m, make_idesc(64), accum);
+                            umma_i8(d0 + C::C_SYY, a_m, b_x2, make_idesc(BN), accum);
+                            umma_i8(d0 + C::C_SXY, a_x, b_x, make_idesc(BN), accum);
+                            umma_i8(d0 + C::C_SXX, a_x2, b_m, make_idesc(BN), accum);
                         } else if constexpr (MODE == TC_MSD) {
-                            umma_i8(d0 + C::C_SYY, a_m, b_x2, make_idesc(128), accum);   // [Syy | count]
-                            umma_i8(d0 + C::C_SXY, a_x, b_x, make_idesc(64), accum);
-                            umma_i8(d0 + C::C_SXX, a_x2, b_m, make_idesc(64), accum);
+                            umma_i8(d0 + C::C_SYY, a_m, b_x2, make_idesc(2 * BN), accum);   // [Syy | count]
+                            umma_i8(d0 + C::C_SYY, a_x2, b_m, make_idesc(BN), 1u);          // Syy += Sxx
+                            umma_i8(d0 + C::C_SXY, a_x, b_x, make_idesc(BN), accum);
                         } else {
-                            umma_i8(d0 + C::C_SYY, a_m, b_x2, make_idesc(192), accum);   // [Syy | count | Sy]
-                            umma_i8(d0 + C::C_SX, a_x, b_m, make_idesc(128), accum);     // [Sx | Sxy]
-                            umma_i8(d0 + C::C_SXX, a_x2, b_m, make_idesc(64), accum);
+                            umma_i8(d0 + C::C_SYY, a_m, b_x2, make_idesc(3 * BN), accum);   // [Syy | count | Sy]
+                            umma_i8(d0 + C::C_SX, a_x, b_m, make_idesc(2 * BN), accum);     // [Sx | Sxy]
+                            umma_i8(d0 + C::C_SXX, a_x2, b_m, make_idesc(BN), accum);
                         }
                     }
                     // frees the smem stage (in every CTA that multicasts into it) once the MMAs are done
@@ -374,7 +435,7 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 int32_t v_syy[8], v_sxy[8], v_sxx[8], v_cnt[8], v_sx[8], v_sy[8];
                 tmem_ld8(tbase + C::C_SYY + c0, v_syy);
                 tmem_ld8(tbase + C::C_SXY + c0, v_sxy);
-                tmem_ld8(tbase + C::C_SXX + c0, v_sxx);
+                if (C::C_SXX >= 0) tmem_ld8(tbase + (C::C_SXX >= 0 ? C::C_SXX : 0) + c0, v_sxx);
                 if (C::C_CNT >= 0) tmem_ld8(tbase + (C::C_CNT >= 0 ? C::C_CNT : 0) + c0, v_cnt);
                 if (C::C_SX >= 0) {
                     tmem_ld8(tbase + (C::C_SX >= 0 ? C::C_SX : 0) + c0, v_sx);
@@ -403,8 +464,8 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         // core/sim.go:24  l / (sqrt(m) * sqrt(n)),  m = Sxx, n = Syy, l = Sxy
                         s[c] = (double)v_sxy[c] / (sqrt((double)v_sxx[c]) * sqrt((double)v_syy[c]));
                     } else if constexpr (MODE == TC_MSD) {
-                        // core/sim.go:43  1 / (sum/count + 1),  sum = Sxx - 2 Sxy + Syy (exact integer)
-                        const int32_t sum = v_sxx[c] - 2 * v_sxy[c] + v_syy[c];
+                        // core/sim.go:43  1 / (sum/count + 1),  sum = (Sxx + Syy) - 2 Sxy (exact integer)
+                        const int32_t sum = v_syy[c] - 2 * v_sxy[c];
                         s[c] = 1.0 / ((double)sum / (double)v_cnt[c] + 1.0);
                     } else {
                         long long cb = 0, sb = 0;
@@ -471,15 +532,16 @@ int32_t get_encode_fn(EncodeTiledFn *out) {
     return RS_OK;
 }
 
-int32_t make_map(const rs_knn *h, int box_rows, CUtensorMap *map) {
+int32_t make_map(const rs_knn *h, int box_k, int box_rows, CUtensorMap *map) {
     EncodeTiledFn enc;
     RS_TRY(get_encode_fn(&enc));
     const cuuint64_t dims[3] = {(cuuint64_t)h->tc_kpad, (cuuint64_t)h->tc_npad, 3};
     const cuuint64_t strides[2] = {(cuuint64_t)h->tc_kpad, (cuuint64_t)h->tc_kpad * (cuuint64_t)h->tc_npad};
-    const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};   // one plane per TMA instruction
+    const cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 1};   // one plane per TMA instruction
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->planes, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         rs_set_error("cuTensorMapEncodeTiled failed with CUresult %d (npad=%lld kpad=%lld)", (int)r,
@@ -492,9 +554,11 @@ int32_t make_map(const rs_knn *h, int box_rows, CUtensorMap *map) {
 template <int MODE, int CI, int CJ>
 int32_t launch_mode(rs_knn *h, const TcArgs &a) {
     constexpr int CS = CI * CJ;
+    using G = Geo<MODE>;
+    constexpr int SMEM_BYTES = G::SMEM_BYTES;
     CUtensorMap ma, mb;
-    RS_TRY(make_map(h, BM / CJ, &ma));
-    RS_TRY(make_map(h, BN / CI, &mb));
+    RS_TRY(make_map(h, G::BK, BM / CJ, &ma));
+    RS_TRY(make_map(h, G::BK, G::BN / CI, &mb));
     auto kern = sim_tensor_kernel<MODE, CI, CJ>;
     RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int sms = 148;
@@ -550,10 +614,17 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
     const int64_t re = cosums ? cos_row0 + cos_nrows : h->row_end;
     if (re <= rb) return RS_OK;
     const bool mirror = !cosums && rb == 0 && re == h->n_left;
-    // cluster shape: 2 x 4 tiles share their operand loads; small problems (fewer tiles than
-    // SMs) run unclustered so every SM gets a tile.  RS_KNN_TC_CLUSTER=1x1|1x2|2x2|2x4 overrides.
-    int ci = 2, cj = 4;
+    // cluster shape: the CI x CJ CTAs of a cluster share operand loads by TMA multicast.  Measured on
+    // the ML-20M item shape (profiles/r01_tensor_calibration.md): with the K-lockstep throttle the
+    // L2 already serves the sharing, 2x1 (B tile multicast) is worth ~6 % for Cosine / MSD, larger
+    // clusters lose to their own lockstep coupling, and Pearson is fastest unclustered.  Small
+    // problems run unclustered so every SM gets a tile.  RS_KNN_TC_CLUSTER=1x1|1x2|2x1|... overrides.
+    const int mode = cosums ? TC_COSUMS : (h->p.sim == RS_SIM_COSINE ? TC_COSINE : h->p.sim == RS_SIM_MSD ? TC_MSD : TC_PEARSON);
+    const int BN = (mode == TC_COSINE || mode == TC_MSD) ? Cfg<TC_COSINE>::BN : Cfg<TC_PEARSON>::BN;
+    const int BK = (mode == TC_COSINE || mode == TC_MSD) ? Cfg<TC_COSINE>::BK : Cfg<TC_PEARSON>::BK;
+    static_assert(Cfg<TC_COSINE>::BN == Cfg<TC_MSD>::BN && Cfg<TC_COSINE>::BK == Cfg<TC_MSD>::BK, "host tile geometry");
     const int64_t plain_tiles = ((re - rb + BM - 1) / BM) * ((h->n_left + BN - 1) / BN) / (mirror ? 2 : 1);
+    int ci = (mode == TC_COSINE || mode == TC_MSD) ? 2 : 1, cj = 1;
     if (plain_tiles < 4 * 148) { ci = 1; cj = 1; }
     if (const char *e = getenv("RS_KNN_TC_CLUSTER")) {
         if (!strcmp(e, "1x1")) { ci = 1; cj = 1; }
@@ -564,20 +635,21 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
         else if (!strcmp(e, "1x8")) { ci = 1; cj = 8; }
         else if (!strcmp(e, "2x1")) { ci = 2; cj = 1; }
     }
-    int sup_i = 8, sup_j = 16;   // supertile, in plain tiles
+    int sup_i = 8, sup_j = 1024 / BN;   // supertile (1024 x 1024 similarities), in plain tiles
     if (const char *e = getenv("RS_KNN_TC_SUP")) sscanf(e, "%d,%d", &sup_i, &sup_j);
     // tile list in units of cluster tiles (ci x cj plain tiles each)
     const int nbj = (int)((h->n_left + BN - 1) / BN);
     const int bi0 = (int)(rb / BM), bi1 = (int)((re + BM - 1) / BM);
-    const int64_t key[4] = {h->n_left, rb, re, (mirror ? 1 : 0) + 2 * (ci * 16 + cj) + 1024 * (sup_i * 4096 + sup_j)};
+    const int64_t key[4] = {h->n_left, rb, re,
+                            (mirror ? 1 : 0) + 2 * (ci * 16 + cj) + 1024 * (int64_t)(sup_i * 4096 + sup_j) + ((int64_t)BN << 40)};
     if (memcmp(key, h->tile_key, sizeof(key)) != 0) {
         // Rasterised in supertiles so concurrently running clusters touch few distinct row blocks.
         const int SUP_I = sup_i / ci > 0 ? sup_i / ci : 1, SUP_J = sup_j / cj > 0 ? sup_j / cj : 1;
         const int cbi0 = bi0 / ci, cbi1 = (bi1 + ci - 1) / ci, ncbj = (nbj + cj - 1) / cj;
         std::vector<int2> tiles;
         auto needed = [&](int cbi, int cbj) {
-            // mirror mode keeps a cluster tile iff any of its plain tiles has bj >= 2*bi
-            return !mirror || (cbj * cj + cj - 1) >= 2 * (cbi * ci);
+            // mirror mode keeps a cluster tile iff it holds a pair (i, j) with j >= i
+            return !mirror || (int64_t)(cbj * cj + cj) * BN > (int64_t)(cbi * ci) * BM;
         };
         for (int sbi = cbi0; sbi < cbi1; sbi += SUP_I)
             for (int sbj = 0; sbj < ncbj; sbj += SUP_J)
@@ -617,6 +689,14 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
     a.cosums = d_cosums;
     a.cos_row0 = cos_row0;
     a.cos_nrows = cos_nrows;
+    if (const char *e = getenv("RS_KNN_TC_DEBUG")) a.debug = atoi(e);
+    // K-lockstep throttle: only worth it when a row block does not fit in L2 many times over
+    a.progress = reinterpret_cast<unsigned long long *>(h->d_flags + 4);
+    a.sync_chunk = (a.k_blocks >= 256 && h->tile_count > 148) ? 32 : 0;
+    a.sync_slack = 1;
+    a.sync_timeout = 40000;   // clocks (~20 us): a hint, never a dependence
+    if (const char *e = getenv("RS_KNN_TC_SYNC")) sscanf(e, "%d,%d,%d", &a.sync_chunk, &a.sync_slack, &a.sync_timeout);
+    if (a.sync_chunk > 0) RS_CUDA(cudaMemsetAsync(a.progress, 0, 8, h->stream));
     int32_t rc;
     if (ci == 1 && cj == 1) rc = launch_shape<1, 1>(h, a, cosums);
     else if (ci == 1 && cj == 2) rc = launch_shape<1, 2>(h, a, cosums);
