@@ -61,15 +61,24 @@ __device__ __forceinline__ void stream_update(double *acc, int j, double ra, dou
     }
 }
 
-template <int SIM, bool SHRINK>
+// SYM: the full matrix is being computed, only columns j > i are visited (the run starts right
+// after i's own position in c's list) and the mirror pass fills j < i; otherwise (row shard) the
+// whole run is visited and the diagonal pair (i,i) is skipped by index.
+// Indices into the right CSR are kept in 32 bits inside the loop (nnz < 2^32 is checked at launch)
+// and the per-entry a-side terms are staged in shared memory, which halves the instructions per
+// column against the first version of this kernel (profiles/r01_stream_notes.md).
+template <int SIM, bool SHRINK, bool SYM>
 __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
     constexpr int NACC = SHRINK ? 4 : 3;
-    extern __shared__ double s_acc_all[];                    // [SW][NACC][JC]
+    extern __shared__ double s_acc_all[];                    // [SW][NACC][JC] accumulators, then [SW][32] a-side terms
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *acc = s_acc_all + (size_t)warp * NACC * JC;
+    double *s_ra = s_acc_all + (size_t)SW * NACC * JC + warp * 32;
     const int64_t Q = a.n_chunks;
     const int64_t n_items = (a.row_end - a.row_begin) * Q;
     const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
+    const int32_t *__restrict__ r_col = a.r_col;
+    const double *__restrict__ r_dev = a.r_dev;
 
     for (;;) {
         unsigned long long item = 0;
@@ -79,11 +88,10 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
         // items are ordered longest row first, so the critical path starts early
         const int64_t q = (int64_t)item % Q;
         const int32_t i = a.row_order[(int64_t)item / Q];
-        const int64_t j0 = q * JC;
-        if (a.symmetric && j0 + JC <= (int64_t)i) continue;  // every column of the chunk is < i
+        const int j0 = (int)(q * JC);
+        if (SYM && j0 + JC <= i) continue;  // every column of the chunk is < i
 
         for (int x = lane; x < NACC * JC; x += 32) acc[x] = 0.0;
-        __syncwarp();
 
         double ai = 0.0;
         if (SIM == RS_SIM_PEARSON) ai = a.pmeans[i];
@@ -91,10 +99,10 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
 
         const int64_t eb = a.l_ptr[i], ee = a.l_ptr[i + 1];
         for (int64_t x0 = eb; x0 < ee; x0 += 32) {
-            // each lane prepares one entry (c, x) of row i: its a-side term and the slice of c's list
+            // each lane prepares one entry (c, x) of row i: its a-side term and its run of c's list
             const int64_t e = x0 + lane;
             double ra = 0.0;
-            int64_t lo = 0, self = -1;
+            uint32_t lo = 0, self = 0xffffffffu;
             int n = 0;
             if (e < ee) {
                 const int32_t c = a.l_col[e];
@@ -104,63 +112,69 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
                 else ra = v;
                 const int64_t rp = a.r_ptr[c];
                 const int32_t *cpc = a.cp + (int64_t)c * (Q + 1) + q;
-                lo = rp + cpc[0];
+                int64_t lo64 = rp + cpc[0];
                 const int64_t hi = rp + cpc[1];
-                self = a.l2r[e];
-                if (a.symmetric && self + 1 > lo) lo = self + 1;                  // only j > i
-                n = hi > lo ? (int)(hi - lo) : 0;
+                const int64_t self64 = a.l2r[e];
+                if (SYM) { if (self64 + 1 > lo64) lo64 = self64 + 1; }            // only j > i
+                else self = (uint32_t)self64;
+                n = hi > lo64 ? (int)(hi - lo64) : 0;
+                lo = (uint32_t)lo64;
             }
+            __syncwarp();           // the previous batch has finished with acc and s_ra
+            s_ra[lane] = ra;
+            __syncwarp();
             const int lim = (ee - x0) < 32 ? (int)(ee - x0) : 32;
             // Columns are processed in order, G at a time: the (j, b-side) pairs of the first 32
             // raters of G consecutive columns are loaded up front (independent L2 requests in
             // flight), then applied column by column.
             for (int u0 = 0; u0 < lim; u0 += G) {
-                int jj[G];
+                int jj[G], nn[G];
                 double rbv[G];
 #pragma unroll
                 for (int g = 0; g < G; g++) {
                     const int u = u0 + g;                                           // < 32 always (G divides 32)
-                    const int n_u = __shfl_sync(0xffffffffu, n, u);
-                    const int64_t lo_u = __shfl_sync(0xffffffffu, lo, u);
-                    const int64_t self_u = __shfl_sync(0xffffffffu, self, u);
+                    nn[g] = __shfl_sync(0xffffffffu, n, u);                         // 0 for u >= lim
+                    const uint32_t lo_u = __shfl_sync(0xffffffffu, lo, u);
+                    uint32_t self_u = 0xffffffffu;
+                    if (!SYM) self_u = __shfl_sync(0xffffffffu, self, u);
                     jj[g] = -1;
                     rbv[g] = 0.0;
-                    if (u < lim && lane < n_u) {
-                        const int64_t idx = lo_u + lane;
-                        if (idx != self_u) {                                        // the diagonal pair (i,i)
-                            jj[g] = a.r_col[idx] - (int)j0;
-                            rbv[g] = a.r_dev[idx];                                  // jr | jr - meanB (core/sim.go:74)
+                    if (lane < nn[g]) {
+                        const uint32_t idx = lo_u + (uint32_t)lane;
+                        if (SYM || idx != self_u) {                                 // the diagonal pair (i,i)
+                            jj[g] = r_col[idx] - j0;
+                            rbv[g] = r_dev[idx];                                    // jr | jr - meanB (core/sim.go:74)
                         }
                     }
                 }
 #pragma unroll
                 for (int g = 0; g < G; g++) {
-                    const int u = u0 + g;
-                    const int n_u = __shfl_sync(0xffffffffu, n, u);
-                    if (u >= lim || n_u == 0) continue;                             // warp-uniform
-                    const double ra_u = __shfl_sync(0xffffffffu, ra, u);
+                    if (nn[g] == 0) continue;                                       // warp-uniform
+                    const double ra_u = s_ra[u0 + g];
                     const double raa_u = ra_u * ra_u;                               // core/sim.go:19 / :75
                     if (jj[g] >= 0) stream_update<SIM, SHRINK>(acc, jj[g], ra_u, raa_u, rbv[g]);
-                    if (n_u > 32) {                                                 // long slice: remaining raters
-                        const int64_t lo_u = __shfl_sync(0xffffffffu, lo, u);
-                        const int64_t self_u = __shfl_sync(0xffffffffu, self, u);
-                        for (int t = lane + 32; t < n_u; t += 32) {
-                            const int64_t idx = lo_u + t;
-                            if (idx == self_u) continue;
-                            stream_update<SIM, SHRINK>(acc, a.r_col[idx] - (int)j0, ra_u, raa_u, a.r_dev[idx]);
+                    if (nn[g] > 32) {                                               // long run: remaining raters
+                        const uint32_t lo_u = __shfl_sync(0xffffffffu, lo, u0 + g);
+                        uint32_t self_u = 0xffffffffu;
+                        if (!SYM) self_u = __shfl_sync(0xffffffffu, self, u0 + g);
+                        for (int t = lane + 32; t < nn[g]; t += 32) {
+                            const uint32_t idx = lo_u + (uint32_t)t;
+                            if (!SYM && idx == self_u) continue;
+                            stream_update<SIM, SHRINK>(acc, r_col[idx] - j0, ra_u, raa_u, r_dev[idx]);
                         }
                     }
                     __syncwarp();   // column c is complete before column c+1 touches the same j
                 }
             }
         }
+        __syncwarp();
 
         // epilogue: JC similarities of row i, coalesced
         double *out = a.sims + (int64_t)(i - a.row_begin) * a.ld_s + j0;
         for (int j = lane; j < JC; j += 32) {
-            const int64_t col = j0 + j;
+            const int64_t col = (int64_t)j0 + j;
             if (col >= a.n_left) break;
-            if (a.symmetric && col < i) continue;                                 // mirror pass writes it
+            if (SYM && col < i) continue;                                         // mirror pass writes it
             double s;
             if (SIM == RS_SIM_MSD) s = 1.0 / (acc[j] / acc[JC + j] + 1.0);        // core/sim.go:43
             else s = acc[2 * JC + j] / (sqrt(acc[j]) * sqrt(acc[JC + j]));        // core/sim.go:24 / :80
@@ -198,13 +212,21 @@ __global__ void symmetrize_kernel(double *__restrict__ s, int64_t ld, int32_t n,
 
 }  // namespace
 
-template <int SIM, bool SHRINK>
-static int32_t launch_stream(rs_knn *h, const StreamArgs &s, int grid) {
-    const int smem = SW * (SHRINK ? 4 : 3) * JC * (int)sizeof(double);
-    auto kern = sim_stream_kernel<SIM, SHRINK>;
+template <int SIM, bool SHRINK, bool SYM>
+static int32_t launch_stream_sym(rs_knn *h, const StreamArgs &s, int grid) {
+    const int smem = SW * ((SHRINK ? 4 : 3) * JC + 32) * (int)sizeof(double);
+    auto kern = sim_stream_kernel<SIM, SHRINK, SYM>;
     RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid, SW * 32, smem, h->stream>>>(s);
     return RS_OK;
+}
+template <int SIM, bool SHRINK>
+static int32_t launch_stream(rs_knn *h, const StreamArgs &s, int grid) {
+    if (h->nnz >= (int64_t)0xffffffffll) {
+        rs_set_error("stream path indexes the ratings with 32 bits (nnz=%lld)", (long long)h->nnz);
+        return RS_ERR_UNSUPPORTED;
+    }
+    return s.symmetric ? launch_stream_sym<SIM, SHRINK, true>(h, s, grid) : launch_stream_sym<SIM, SHRINK, false>(h, s, grid);
 }
 
 int32_t rs_sim_stream_launch(rs_knn *h) {
