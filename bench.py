@@ -429,6 +429,7 @@ def run_ours(args, rank, world, local_rank):
                 "predictions_per_sec": preds_all / e2e_s, "steps": e2e_steps},
         "gpu_launches": int(prof["total_launches"]),
         "kernel_ms": {"sim": sim_ms / args.steps, "predict": pred_ms / args.steps, "prep": prof["prep_ms"] / args.steps},
+        "corated_triples": prof["corated_triples"],
         "roofline": roof,
     }
     if world == 1 and not args.no_cpu_baseline:

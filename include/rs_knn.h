@@ -93,6 +93,8 @@ typedef struct rs_knn_profile {
     int64_t total_launches;    /* every kernel this library launched on the handle         */
     int32_t sim_path_used;     /* enum rs_sim_path actually taken by the last Fit          */
     int32_t reserved0;
+    double corated_triples;    /* sum over right rows of cnt*(cnt-1)/2 of the last Fit: the work of the
+                                * exact sparse path, input of the RS_PATH_AUTO model        */
 } rs_knn_profile;
 
 /* Thread-local message of the last error on this thread ("" if none). */

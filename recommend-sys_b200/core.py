@@ -55,7 +55,7 @@ class RsKnnParams(C.Structure):
 class RsKnnProfile(C.Structure):
     _fields_ = [("sim_kernel_ms", C.c_double), ("predict_kernel_ms", C.c_double), ("prep_ms", C.c_double),
                 ("sim_launches", C.c_int64), ("predict_launches", C.c_int64), ("total_launches", C.c_int64),
-                ("sim_path_used", C.c_int32), ("reserved0", C.c_int32)]
+                ("sim_path_used", C.c_int32), ("reserved0", C.c_int32), ("corated_triples", C.c_double)]
 
 
 ABI_SYMBOLS = [

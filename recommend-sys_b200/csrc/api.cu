@@ -77,6 +77,23 @@ bool tensor_eligible(const rs_knn *h) {
     return false;
 }
 
+// Fit path model.  Both paths are bit-exact for Cosine / MSD, so RS_PATH_AUTO takes the faster one.
+// The tensor path does dense work, N(N-1)/2 * 2*G*K int8 ops whatever the sparsity; the stream
+// path does one step per co-rated triple.  Rates measured on B200 (profiles/r01_path_model.md):
+// tensor ~2.0e15 op/s sustained (0.62-0.9 of the int8 roofline), stream 6e10-9e10 triples/s.  Dense
+// shapes (MovieLens-1M, 4.5 % filled) go to the tensor cores, sparse ones (MovieLens-20M, 0.5 %)
+// are faster as an exact sparse replay.
+bool tensor_faster(const rs_knn *h) {
+    const double n = (double)h->n_left, rows = (double)(h->row_end - h->row_begin);
+    const bool full = h->row_begin == 0 && h->row_end == h->n_left;
+    const double g = h->p.sim == RS_SIM_COSINE ? 3.0 : h->p.sim == RS_SIM_MSD ? 4.0 : 6.0;
+    const double pairs = full ? n * (n - 1.0) / 2.0 : rows * n;           // a row shard computes full rows
+    const double t_tensor = pairs * 2.0 * g * (double)h->n_right / 2.0e15 + 1e-4;
+    const double triples = full ? h->triples : 2.0 * h->triples * (rows / n);
+    const double t_stream = triples / 6.0e10 + 1e-4;
+    return t_tensor <= t_stream;
+}
+
 }  // namespace
 
 extern "C" {
@@ -232,13 +249,14 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
         if (!strcmp(force, "stream")) path = RS_PATH_STREAM;
         else if (!strcmp(force, "tensor")) path = RS_PATH_TENSOR;
     }
-    if (path == RS_PATH_AUTO) path = tensor_eligible(h) ? RS_PATH_TENSOR : RS_PATH_STREAM;
+    if (path == RS_PATH_AUTO) path = tensor_eligible(h) && tensor_faster(h) ? RS_PATH_TENSOR : RS_PATH_STREAM;
     if (path == RS_PATH_TENSOR && !tensor_eligible(h)) {
         rs_set_error("tensor path needs integer ratings in [-11,11] and Cosine/MSD (or Pearson in SUMS mode)");
         free_fit_state(h);
         return RS_ERR_UNSUPPORTED;
     }
     h->prof.sim_path_used = path;
+    h->prof.corated_triples = h->triples;
     rc = (path == RS_PATH_TENSOR) ? rs_prep_planes(h) : rs_prep_rt(h);
     if (rc != RS_OK) { free_fit_state(h); return rc; }
 
@@ -538,6 +556,7 @@ int32_t rs_knn_profile_reset(rs_knn *h) {
     int32_t path = h->prof.sim_path_used;
     h->prof = rs_knn_profile{};
     h->prof.sim_path_used = path;
+    h->prof.corated_triples = h->triples;
     return RS_OK;
 }
 

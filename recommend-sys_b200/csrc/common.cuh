@@ -91,6 +91,7 @@ struct rs_knn {
     int32_t *row_cnt = nullptr;   // ratings per left row and their integer sum (tensor path, Pearson)
     int32_t *row_sum = nullptr;
     int64_t max_row_cnt = 0;
+    double triples = 0.0;         // co-rated triples of the full matrix: sum over right rows of cnt*(cnt-1)/2
     double *right_bias = nullptr;
 
     // stream path: b-side term of every rating in right-CSR order (value, value - row mean, ...),

@@ -16,8 +16,7 @@
 
 namespace {
 
-constexpr int PRED_WARPS = 4;
-constexpr int PRED_CAP = 512;   // (key,pos) records per warp
+constexpr int PRED_CAP = 512;   // k <= PRED_CAP / 2 (register capacity of predict_select_kernel<8>)
 
 struct Rec {
     uint64_t key;
@@ -27,25 +26,6 @@ struct Rec {
 // a ranks before b: larger key first, then smaller position (= smaller id)
 __device__ __forceinline__ bool rec_before(uint64_t ka, uint32_t pa, uint64_t kb, uint32_t pb) {
     return ka > kb || (ka == kb && pa < pb);
-}
-
-// Bitonic sort of n_pad (power of two, >= 32) records into "before" order by one warp.
-__device__ void warp_bitonic(uint64_t *keys, uint32_t *pos, int n_pad, int lane) {
-    for (int size = 2; size <= n_pad; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            __syncwarp();
-            for (int t = lane; t < (n_pad >> 1); t += 32) {
-                int lo = 2 * t - (t & (stride - 1));
-                int hi = lo + stride;
-                bool up = ((lo & size) == 0);  // this run sorts into "before" order
-                uint64_t ka = keys[lo], kb = keys[hi];
-                uint32_t pa = pos[lo], pb = pos[hi];
-                bool swap = up ? rec_before(kb, pb, ka, pa) : rec_before(ka, pa, kb, pb);
-                if (swap) { keys[lo] = kb; keys[hi] = ka; pos[lo] = pb; pos[hi] = pa; }
-            }
-        }
-    }
-    __syncwarp();
 }
 
 
@@ -71,20 +51,20 @@ struct PredArgs {
 
 // =====================================================================================
 // Main predict kernel: selection, not sorting.  One warp per prediction:
-//   pass A  gather the similarity of every candidate, count the non-NaN ones (core/knn.go:95-99)
-//           and find their min / max;
-//   pass B  (only when more candidates than the register capacity CAP = 32*R) 256-bucket
-//           histogram of a monotone linear bucket of the similarity in shared memory, suffix
-//           scan -> boundary bucket: everything above it is certainly in the top k, everything
-//           below certainly not; refined (up to 3 levels) inside the boundary bucket when it is
-//           too full; genuine ties are taken in scan order = ascending inner id (canonical);
+//   pass A  gather the similarity of every candidate ONCE (4 independent gathers per lane in
+//           flight), map it to an order-preserving 64-bit key (0 = NaN, core/knn.go:95-99), park
+//           the keys in shared memory, count the valid ones and find the key range;
+//   pass B  (only when more candidates than the register capacity CAP = 32*R) radix selection:
+//           256-bucket histogram of (key - lo) >> shift in shared memory, suffix scan -> boundary
+//           bucket: everything above it is certainly in the top k, everything below certainly
+//           not; the window shrinks to the boundary bucket (8 more key bits per level) while it
+//           is too full; a one-value bucket that is still too full is a genuine tie and is taken
+//           in scan order = ascending inner id (canonical).  Integer compares only;
 //   pass C  compaction of the surviving <= CAP candidates into registers (R per lane);
 //   sort    one warp-wide bitonic network over CAP (key,pos) records in registers
 //           (strides < R in-register, >= R via __shfl_xor);
 //   reduce  the first min(k,valid) neighbours are accumulated sequentially in sorted order,
 //           exactly as core/knn.go:116-130 does.
-// A prediction whose boundary bucket still overflows after 3 levels is appended to an
-// overflow list and finished by the generic shared-memory kernel below.
 // =====================================================================================
 constexpr int SEL_WARPS = 8;
 
@@ -133,19 +113,16 @@ __device__ __forceinline__ void warp_sort_regs(uint64_t (&key)[R], uint32_t (&po
     }
 }
 
-__device__ __forceinline__ int sel_bucket(double s, double lo, double scale) {
-    int b = (int)((s - lo) * scale);   // monotone non-decreasing in s
-    return b > 255 ? 255 : (b < 0 ? 0 : b);
-}
+// order-preserving key of a similarity, 0 for NaN (rs_sim_key of any real value is >= 2^52 - 1)
+__device__ __forceinline__ uint64_t sim_key_or_zero(double s) { return (s == s) ? rs_sim_key(s) : 0ull; }
 
 template <int R>
-__global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs a, int32_t *overflow_list,
-                                                                        int32_t *overflow_count, int scap) {
+__global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs a, int scap) {
     constexpr int CAP = 32 * R;
     // per-warp staging of the gathered similarities: pass A gathers each candidate's similarity
     // from HBM/L2 once (4 independent gathers per lane in flight) and parks the first `scap` of
     // them here; the selection passes read them back instead of gathering again
-    extern __shared__ double s_stage[];
+    extern __shared__ unsigned long long s_stage[];
     __shared__ uint32_t s_hist[SEL_WARPS][256];
     __shared__ uint64_t s_key[SEL_WARPS][CAP];
     __shared__ uint32_t s_pos[SEL_WARPS][CAP];
@@ -154,7 +131,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
     uint32_t *hist = s_hist[warp];
     uint64_t *ckey = s_key[warp];
     uint32_t *cpos = s_pos[warp];
-    double *sbuf = s_stage + (size_t)warp * scap;
+    uint64_t *sbuf = reinterpret_cast<uint64_t *>(s_stage) + (size_t)warp * scap;
     const int64_t n_warps = (int64_t)gridDim.x * SEL_WARPS;
     const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -175,8 +152,8 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
         const int cnt = (int)(a.r_ptr[r + 1] - cb);        // a right row has at most n_left entries
         const int32_t *ids = a.r_col + cb;
 
-        // ---- pass A: gather once, count + range ----
-        double lo = __longlong_as_double(0x7ff0000000000000ll), hi = -lo;
+        // ---- pass A: gather once -> order-preserving 64-bit keys (0 = NaN / absent), count + range ----
+        uint64_t klo = ~0ull, khi = 0ull;
         int valid = 0;
         __syncwarp();   // the previous prediction has finished reading sbuf
         for (int e0 = 0; e0 < cnt; e0 += 128) {
@@ -192,40 +169,54 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int e = e0 + u * 32 + lane;
-                const double s = sv4[u];
-                if (e < scap) sbuf[e] = s;
-                if (s == s) { valid++; lo = fmin(lo, s); hi = fmax(hi, s); }
+                const double sv = sv4[u];
+                const uint64_t key = (sv == sv) ? rs_sim_key(sv) : 0ull;
+                if (e < scap) sbuf[e] = key;
+                if (key) { valid++; klo = key < klo ? key : klo; khi = key > khi ? key : khi; }
             }
         }
-        __syncwarp();
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             valid += __shfl_xor_sync(0xffffffffu, valid, o);
-            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            const uint64_t ol = __shfl_xor_sync(0xffffffffu, klo, o), oh = __shfl_xor_sync(0xffffffffu, khi, o);
+            klo = ol < klo ? ol : klo;
+            khi = oh > khi ? oh : khi;
         }
+        __syncwarp();
         if (valid <= a.min_k) {                            // core/knn.go:102-104 (note <=)
             if (lane == 0) a.out[p] = a.global_mean;
             continue;
         }
         const int num = a.k < valid ? a.k : valid;         // core/knn.go:111-114
 
-        // ---- pass B: narrow to <= CAP candidates that contain the top `num` ----
-        // selected  <=>  s > hi_sure  ||  (lo <= s <= hi && bucket(s) >= T)   [+ scan-order ties]
-        double hi_sure = __longlong_as_double(0x7ff0000000000000ll);  // +inf: nothing above yet
-        double scale = 0.0;
-        int T = 0;
-        int sure = 0;          // candidates already known to be in the top `num`
-        int tie_take = -1;     // >= 0: the interval is one value; take this many in scan order
-        bool overflow = false;
+        // ---- pass B: radix selection on the keys: narrow to <= CAP candidates holding the top `num` ----
+        // The window [klo, khi] is cut into <= 256 equal buckets ((key - klo) >> sh); the boundary
+        // bucket is the highest T with count(bucket >= T) >= need.  If everything from T upwards
+        // fits the register capacity the threshold is klo + (T << sh) and ONE compare selects;
+        // otherwise the window shrinks to bucket T (8 more key bits per level, so it terminates: a
+        // bucket of one key value that still does not fit is a genuine tie and is taken in scan
+        // order = ascending inner id, the canonical policy).
+        uint64_t thr = 1ull;       // take every key >= thr ...
+        uint64_t tie_key = 0ull;   // ... and, when tie_take >= 0, the first tie_take keys == tie_key (< thr)
+        int tie_take = -1;
         if (valid > CAP) {
-            for (int level = 0;; level++) {
+            int sure = 0;          // candidates above the window, already known to be in the top `num`
+            bool top_binade = true;
+            for (;;) {
+                // Keys are linear in the similarity inside one binade and logarithmic across binades,
+                // so the first window is the top binade only ([max/2, max], 2^52 key units): the top k
+                // of a neighbourhood almost always lie there and get 256 value-linear buckets.  If the
+                // window holds fewer than `need` they are all selected and the search goes on below it.
+                uint64_t wlo = klo;
+                if (top_binade && khi - klo > (1ull << 52)) wlo = khi - (1ull << 52);
+                top_binade = false;
+                const uint64_t width = khi - wlo;
+                const int sh = width < 256ull ? 0 : (64 - __clzll((long long)width)) - 8;
                 for (int x = lane; x < 256; x += 32) hist[x] = 0;
                 __syncwarp();
-                scale = (hi > lo) ? 256.0 / (hi - lo) : 0.0;
                 for (int e = lane; e < cnt; e += 32) {
-                    const double s = e < scap ? sbuf[e] : row[ids[e]];
-                    if (s >= lo && s <= hi) atomicAdd(&hist[sel_bucket(s, lo, scale)], 1u);
+                    const uint64_t key = e < scap ? sbuf[e] : sim_key_or_zero(row[ids[e]]);
+                    if (key >= wlo && key <= khi) atomicAdd(&hist[(uint32_t)((key - wlo) >> sh)], 1u);
                 }
                 __syncwarp();
                 // suffix counts: lane owns buckets [8*lane, 8*lane+8)
@@ -238,9 +229,14 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
                     const uint32_t v = __shfl_down_sync(0xffffffffu, above, o);
                     if (lane + o < 32) above += v;
                 }
+                const int in_window = (int)__shfl_sync(0xffffffffu, above, 0);
                 above -= mine;           // candidates in buckets of higher lanes
                 const int need = num - sure;
-                // the boundary bucket is the highest T with count(bucket >= T) >= need
+                if (in_window < need) {  // the whole window is selected; continue below it
+                    sure += in_window;
+                    khi = wlo - 1ull;
+                    continue;
+                }
                 int myT = -1;
                 uint32_t run = above, sure_here = 0, bd_here = 0;
 #pragma unroll
@@ -250,52 +246,33 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
                 }
                 const uint32_t has = __ballot_sync(0xffffffffu, myT >= 0);
                 const int src = 31 - __clz(has);           // highest lane that found it
-                T = __shfl_sync(0xffffffffu, myT, src);
+                const int T = __shfl_sync(0xffffffffu, myT, src);
                 const int sure_lvl = (int)__shfl_sync(0xffffffffu, sure_here, src);
                 const int bd = (int)__shfl_sync(0xffffffffu, bd_here, src);
-                if (sure + sure_lvl + bd <= CAP) break;    // compaction fits
-                // too many in the boundary bucket: refine inside it
-                double lo2 = __longlong_as_double(0x7ff0000000000000ll), hi2 = -lo2;
-                for (int e = lane; e < cnt; e += 32) {
-                    const double s = e < scap ? sbuf[e] : row[ids[e]];
-                    if (s >= lo && s <= hi && sel_bucket(s, lo, scale) == T) { lo2 = fmin(lo2, s); hi2 = fmax(hi2, s); }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    lo2 = fmin(lo2, __shfl_xor_sync(0xffffffffu, lo2, o));
-                    hi2 = fmax(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
-                }
+                const uint64_t b_lo = wlo + ((uint64_t)T << sh);
+                if (sure + sure_lvl + bd <= CAP) { thr = b_lo; break; }      // compaction fits
                 sure += sure_lvl;
-                hi_sure = hi2;            // everything above the boundary bucket is certain
-                lo = lo2; hi = hi2; T = 0; scale = 0.0;
-                if (lo2 == hi2) { tie_take = num - sure; break; }   // genuine ties: scan order
-                if (level == 2) { overflow = true; break; }
+                if (sh == 0) {             // one key value fills the bucket: genuine ties
+                    tie_key = b_lo;
+                    tie_take = num - sure;
+                    thr = b_lo + 1ull;
+                    break;
+                }
+                const uint64_t b_hi = b_lo + ((1ull << sh) - 1ull);
+                klo = b_lo;
+                khi = b_hi < khi ? b_hi : khi;
             }
-        }
-        const bool take_all = valid <= CAP;   // every valid candidate fits in the registers
-        if (overflow) {
-            if (lane == 0) overflow_list[atomicAdd(overflow_count, 1)] = (int32_t)p;
-            continue;
         }
 
         // ---- pass C: compaction (scan order = ascending inner id) ----
         int have = 0, ties_taken = 0;
         for (int base = 0; base < cnt; base += 32) {
             const int e = base + lane;
-            bool take = false, tie = false;
-            uint64_t key = 0;
-            if (e < cnt) {
-                const double s = e < scap ? sbuf[e] : row[ids[e]];
-                if (s == s) {
-                    key = rs_sim_key(s);
-                    if (take_all || s > hi_sure) take = true;
-                    else if (s >= lo && s <= hi) {
-                        if (tie_take >= 0) tie = true;
-                        else take = sel_bucket(s, lo, scale) >= T;
-                    }
-                }
-            }
+            uint64_t key = 0ull;
+            if (e < cnt) key = e < scap ? sbuf[e] : sim_key_or_zero(row[ids[e]]);
+            bool take = key >= thr;
             if (tie_take >= 0) {
+                const bool tie = key == tie_key;
                 const uint32_t tm = __ballot_sync(0xffffffffu, tie);
                 if (tie && ties_taken + __popc(tm & lt_mask) < tie_take) take = true;
                 ties_taken += __popc(tm);
@@ -361,122 +338,6 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
     }
 }
 
-// Generic shared-memory kernel: finishes the (rare) predictions on the overflow list.
-__global__ void __launch_bounds__(PRED_WARPS * 32) predict_kernel(PredArgs a, const int32_t *__restrict__ list,
-                                                                  const int32_t *__restrict__ list_count) {
-    __shared__ uint64_t s_keys[PRED_WARPS][PRED_CAP];
-    __shared__ uint32_t s_pos[PRED_WARPS][PRED_CAP];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint64_t *keys = s_keys[warp];
-    uint32_t *pos = s_pos[warp];
-    const int64_t n_warps = (int64_t)gridDim.x * PRED_WARPS;
-    const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
-
-    const int64_t n_work = list ? (int64_t)*list_count : a.n;
-    for (int64_t w = (int64_t)blockIdx.x * PRED_WARPS + warp; w < n_work; w += n_warps) {
-        const int64_t p = list ? (int64_t)list[w] : w;
-        const int32_t l = a.left[p], r = a.right[p];
-        if (a.nb_count && lane == 0) *a.nb_count = 0;
-        if (l < 0 || r < 0 || r >= a.n_right) {            // core/knn.go:89-91 (newID)
-            if (lane == 0) a.out[p] = a.global_mean;
-            continue;
-        }
-        if (l < a.row_begin || l >= a.row_end) {           // not in this shard: flagged as NaN
-            if (lane == 0) a.out[p] = nan_v;
-            continue;
-        }
-        const double *row = a.sims + (l - a.row_begin) * a.ld_s;
-        const int64_t cb = a.r_ptr[r], ce = a.r_ptr[r + 1];
-        const int keep = a.k < PRED_CAP / 2 ? a.k : PRED_CAP / 2;
-
-        // ---- gather + filter; keep the best `keep` so far in keys[0..have) ----
-        int have = 0;        // records currently buffered (warp-uniform)
-        int64_t valid = 0;   // non-NaN candidates seen (core/knn.go:95-99)
-        uint64_t thr_key = 0;  // once a sort has happened: records not before (thr) are dropped
-        uint32_t thr_pos = 0xffffffffu;
-        bool have_thr = false;
-        for (int64_t base = cb; base < ce; base += 32) {
-            const int64_t x = base + lane;
-            bool ok = false;
-            uint64_t key = 0;
-            if (x < ce) {
-                const double s = row[a.r_col[x]];
-                ok = (s == s);
-                key = rs_sim_key(s);
-            }
-            const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
-            valid += __popc(okmask);
-            const uint32_t pp = (uint32_t)(x - cb);
-            bool take = ok && (!have_thr || rec_before(key, pp, thr_key, thr_pos));
-            const uint32_t tmask = __ballot_sync(0xffffffffu, take);
-            if (take) {
-                int slot = have + __popc(tmask & ((1u << lane) - 1u));
-                keys[slot] = key;
-                pos[slot] = pp;
-            }
-            have += __popc(tmask);
-            if (have > PRED_CAP - 32) {
-                // buffer nearly full: sort, keep the best `keep`, remember the threshold
-                int n_pad = PRED_CAP;
-                __syncwarp();
-                for (int t = have + lane; t < n_pad; t += 32) { keys[t] = 0; pos[t] = 0xffffffffu; }
-                warp_bitonic(keys, pos, n_pad, lane);
-                have = keep;
-                thr_key = keys[keep - 1];
-                thr_pos = pos[keep - 1];
-                have_thr = true;
-                __syncwarp();
-            }
-        }
-        if (valid <= (int64_t)a.min_k) {                   // core/knn.go:102-104 (note <=)
-            if (lane == 0) a.out[p] = a.global_mean;
-            continue;
-        }
-        int n_pad = 32;
-        while (n_pad < have) n_pad <<= 1;
-        __syncwarp();
-        for (int t = have + lane; t < n_pad; t += 32) { keys[t] = 0; pos[t] = 0xffffffffu; }
-        warp_bitonic(keys, pos, n_pad, lane);
-
-        int num = a.k;                                     // core/knn.go:111-114
-        if ((int64_t)num > valid) num = (int)valid;
-        if (num > have) num = have;                        // only when k > PRED_CAP/2 (rejected by the host)
-
-        // ---- weighted mean over the first `num`, sequential in sorted order ----
-        double wsum = 0.0, wrat = 0.0;
-        for (int b0 = 0; b0 < num; b0 += 32) {
-            const int t = b0 + lane;
-            double s = 0.0, adj = 0.0;
-            int32_t id = -1;
-            if (t < num) {
-                const int64_t x = cb + pos[t];
-                id = a.r_col[x];
-                s = row[id];
-                double rating = a.r_val[x];
-                if (a.knn_type == RS_KNN_CENTERED) rating -= a.means[id];                       // core/knn.go:121
-                else if (a.knn_type == RS_KNN_ZSCORE) rating = (rating - a.means[id]) / a.stddevs[id];
-                else if (a.knn_type == RS_KNN_BASELINE) rating -= a.bias[id];
-                adj = rating;
-                if (a.nb_ids && t < a.nb_cap) { a.nb_ids[t] = id; a.nb_sims[t] = s; }
-            }
-            const int lim = (num - b0) < 32 ? (num - b0) : 32;
-            for (int q = 0; q < lim; q++) {
-                const double sq = __shfl_sync(0xffffffffu, s, q);
-                const double aq = __shfl_sync(0xffffffffu, adj, q);
-                wsum += sq;                                // core/knn.go:117
-                wrat += sq * aq;                           // core/knn.go:127
-            }
-        }
-        if (lane == 0) {
-            double pred = wrat / wsum;                     // core/knn.go:131
-            if (a.knn_type == RS_KNN_CENTERED) pred += a.means[l];
-            else if (a.knn_type == RS_KNN_BASELINE) pred += a.bias[l];
-            else if (a.knn_type == RS_KNN_ZSCORE) { pred *= a.stddevs[l]; pred += a.means[l]; }
-            a.out[p] = pred;
-            if (a.nb_count) *a.nb_count = num < a.nb_cap ? num : a.nb_cap;
-        }
-    }
-}
 
 // ---------------- per-row top-k from the resident matrix ----------------
 constexpr int TOPK_THREADS = 256;
@@ -558,10 +419,10 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_rows_kernel(const double *_
 }  // namespace
 
 template <int R>
-static int32_t launch_select(const PredArgs &a, int32_t *ovf, unsigned blocks, size_t smem, int scap, cudaStream_t st) {
+static int32_t launch_select(const PredArgs &a, unsigned blocks, size_t smem, int scap, cudaStream_t st) {
     auto kern = predict_select_kernel<R>;
     RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, SEL_WARPS * 32, smem, st>>>(a, ovf + 1, ovf, scap);
+    kern<<<blocks, SEL_WARPS * 32, smem, st>>>(a, scap);
     return RS_OK;
 }
 
@@ -584,19 +445,6 @@ int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
     a.global_mean = h->global_mean; a.n_right = h->n_right;
     a.k = h->p.k; a.min_k = h->p.min_k; a.knn_type = h->p.knn_type;
     a.nb_ids = d_nb_ids; a.nb_sims = d_nb_sims; a.nb_count = d_nb_count; a.nb_cap = nb_cap;
-    // overflow list: [0] = count, [1..n] = prediction indices
-    if ((size_t)(n + 1) * 4 > h->ovf_bytes) {
-        RS_CUDA(cudaStreamSynchronize(h->stream));
-        if (h->ovf) rs_cached_free(h->device, h->ovf, h->ovf_bytes);
-        h->ovf = nullptr;
-        h->ovf_bytes = 0;
-        const size_t want = (size_t)(n + 1) * 4 + (size_t)n;  // 25 % headroom
-        size_t got = 0;
-        RS_TRY(rs_cached_malloc(h->device, &h->ovf, want, &got));
-        h->ovf_bytes = got;
-    }
-    int32_t *ovf = reinterpret_cast<int32_t *>(h->ovf);
-    RS_CUDA(cudaMemsetAsync(ovf, 0, 4, h->stream));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     int64_t blocks = (n + SEL_WARPS - 1) / SEL_WARPS;
@@ -612,13 +460,11 @@ int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
     const int64_t per_sm = smem ? (int64_t)(200 * 1024) / (int64_t)(smem + 16 * 1024) : 8;
     if (blocks > (int64_t)sms * (per_sm > 0 ? per_sm : 1)) blocks = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
     // register capacity of the selection kernel: room for k plus a boundary bucket
-    if (h->p.k <= 44) RS_TRY(launch_select<2>(a, ovf, (unsigned)blocks, smem, scap, h->stream));
-    else if (h->p.k <= 104) RS_TRY(launch_select<4>(a, ovf, (unsigned)blocks, smem, scap, h->stream));
-    else RS_TRY(launch_select<8>(a, ovf, (unsigned)blocks, smem, scap, h->stream));
-    // the generic kernel drains the overflow list (normally empty: a handful of warps exit at once)
-    predict_kernel<<<(unsigned)sms, PRED_WARPS * 32, 0, h->stream>>>(a, ovf + 1, ovf);
+    if (h->p.k <= 44) RS_TRY(launch_select<2>(a, (unsigned)blocks, smem, scap, h->stream));
+    else if (h->p.k <= 104) RS_TRY(launch_select<4>(a, (unsigned)blocks, smem, scap, h->stream));
+    else RS_TRY(launch_select<8>(a, (unsigned)blocks, smem, scap, h->stream));
     h->prof.predict_launches++;
-    h->prof.total_launches += 2;
+    h->prof.total_launches += 1;
     RS_CUDA(cudaGetLastError());
     return RS_OK;
 }

@@ -9,6 +9,8 @@
 // CUB (ships with the CUDA toolkit) is used for the radix sorts and scans only.
 #include <cub/cub.cuh>
 
+#include <cstring>
+
 #include "common.cuh"
 
 int32_t rs_dev_alloc(rs_knn *h, void **out, size_t bytes) {
@@ -298,6 +300,19 @@ int bits_for(int32_t n) {
                                                 (int)(n), 0, end_bit, st));                                  \
     } while (0)
 
+// sum over right rows of cnt*(cnt-1)/2 = co-rated triples (i < j, common right id): the work of the
+// stream path, used by the Fit path model (api.cu)
+__global__ void triples_kernel(const int32_t *__restrict__ rcount, int32_t nr, unsigned long long *out) {
+    unsigned long long acc = 0;
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nr; c += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long n = (unsigned long long)rcount[c];
+        acc += n * (n - (n ? 1 : 0)) / 2;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, const double *d_rating,
                       const double *d_left_bias, const double *d_right_bias) {
     cudaStream_t st = h->stream;
@@ -321,14 +336,18 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     RS_TRY(rs_alloc(h, &h->d_flags, 8));
     RS_CUDA(cudaMemsetAsync(lcount, 0, ((size_t)nl + 1) * 4, st));
     RS_CUDA(cudaMemsetAsync(rcount, 0, ((size_t)nr + 1) * 4, st));
-    RS_CUDA(cudaMemsetAsync(h->d_flags, 0, 16, st));
+    RS_CUDA(cudaMemsetAsync(h->d_flags, 0, 32, st));
 
     iota_validate_kernel<<<blocks_for(nnz), T, 0, st>>>(d_left, d_right, d_rating, nnz, nl, nr, idx, lcount,
                                                        rcount, h->d_flags);
-    h->prof.total_launches++;
+    triples_kernel<<<148, T, 0, st>>>(rcount, nr, reinterpret_cast<unsigned long long *>(h->d_flags + 6));
+    h->prof.total_launches += 2;
     int32_t flags = 0;
-    RS_CUDA(cudaMemcpyAsync(&flags, h->d_flags, 4, cudaMemcpyDeviceToHost, st));
+    int32_t fl8[8] = {0};
+    RS_CUDA(cudaMemcpyAsync(fl8, h->d_flags, 32, cudaMemcpyDeviceToHost, st));
     RS_CUDA(cudaStreamSynchronize(st));
+    flags = fl8[0];
+    { unsigned long long t; memcpy(&t, fl8 + 6, 8); h->triples = (double)t; }
     if (flags & FLAG_BAD_ID) {
         rs_set_error("rating rows contain inner ids outside [0,n_left) x [0,n_right)");
         return RS_ERR_INVALID;
