@@ -23,13 +23,14 @@ and raises if the library or a device is missing.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from pathlib import Path
 
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-_LIB_KNN = _PKG / "librs_knn_b200.so"
+_LIB_KNN = Path(os.environ.get("RS_KNN_LIB", _PKG / "librs_knn_b200.so"))   # RS_KNN_LIB: an alternative build
 _LIB_HOST = _PKG / "librs_host.so"
 
 RS_OK = 0

@@ -34,8 +34,12 @@ enum { RS_CLASS_INT8 = 0, RS_CLASS_TABLE = 1 };
 constexpr int RS_INT8_BIAS = 12;
 
 // Column-chunk width of the streaming similarity kernel (threads * bytes per thread).
-constexpr int RS_STREAM_WARPS = 8;   // warps per CTA, each an independent (row, column-chunk) work item
-constexpr int RS_STREAM_JC = 256;    // columns per work item (3 x 256 doubles of accumulators per warp)
+// Streaming similarity kernel: warps per CTA, each an independent (row, column-chunk) work item.
+// The chunk width (rs_knn::stream_jc, 128 or 256 columns = 3 x JC doubles of accumulators per
+// warp) is chosen per Fit: 128 gives small problems enough work items to balance the SMs
+// (MovieLens-1M shape: 1.6 ms vs 2.2 ms), 256 halves the per-chunk walk of the row on large sparse
+// ones (MovieLens-20M item shape: 85 ms vs 128 ms); profiles/r01_stream_notes.md.
+constexpr int RS_STREAM_WARPS = 8;
 
 // Tensor-core similarity kernel tile: 128 left rows (MMA M) x 64 left rows (MMA N),
 // K blocked by 128 bytes (one SWIZZLE_128B atom) per pipeline stage.
@@ -99,6 +103,7 @@ struct rs_knn {
     double *r_dev = nullptr;
     int32_t *cp = nullptr;
     int32_t n_chunks = 0;
+    int32_t stream_jc = 256;
     int64_t *l2r = nullptr;
     int32_t *row_order = nullptr;  // left rows sorted by descending length
     // int8 planes X, X^2, M of the left matrix, [3][n_pad][k_pad], K-major (tensor path)

@@ -9,6 +9,7 @@
 // CUB (ships with the CUDA toolkit) is used for the radix sorts and scans only.
 #include <cub/cub.cuh>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -475,7 +476,9 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
 
 int32_t rs_prep_rt(rs_knn *h) {
     cudaStream_t st = h->stream;
-    h->n_chunks = (int32_t)(((int64_t)h->n_left + RS_STREAM_JC - 1) / RS_STREAM_JC);
+    h->stream_jc = h->n_left < 8192 ? 128 : 256;
+    if (const char *e = getenv("RS_KNN_STREAM_JC")) h->stream_jc = atoi(e) == 128 ? 128 : 256;
+    h->n_chunks = (int32_t)(((int64_t)h->n_left + h->stream_jc - 1) / h->stream_jc);
     RS_TRY(rs_alloc(h, &h->r_dev, (size_t)h->nnz));
     RS_TRY(rs_alloc(h, &h->l2r, (size_t)h->nnz));
     RS_TRY(rs_alloc(h, &h->cp, (size_t)h->n_right * ((size_t)h->n_chunks + 1)));
@@ -483,7 +486,7 @@ int32_t rs_prep_rt(rs_knn *h) {
         h->r_ptr, h->r_col, h->r_val, h->n_right, h->p.sim, h->pmeans, h->left_bias, h->right_bias, h->global_bias,
         h->r_dev);
     build_cp_kernel<<<blocks_for((int64_t)h->n_right * (h->n_chunks + 1)), T, 0, st>>>(
-        h->r_ptr, h->r_col, h->n_right, h->n_chunks, RS_STREAM_JC, h->cp);
+        h->r_ptr, h->r_col, h->n_right, h->n_chunks, h->stream_jc, h->cp);
     build_l2r_kernel<<<blocks_for((int64_t)h->n_right * 32), T, 0, st>>>(h->l_ptr, h->l_col, h->r_ptr, h->r_col,
                                                                         h->n_right, h->l2r);
     h->prof.total_launches += 3;

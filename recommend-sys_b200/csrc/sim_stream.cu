@@ -4,7 +4,7 @@
 // row i the reference walks i's entries in ascending right id c and, for every other left row
 // j that also rated c, adds one term to each of three running sums — in that order.
 //
-// Mapping ("column walk"): one WARP owns a work item (row i, chunk of JC consecutive columns j)
+// Mapping ("column walk"): one WARP owns a work item (row i, chunk of JC = 128 or 256 consecutive columns j)
 // and keeps that chunk's accumulators in shared memory.  It walks row i's entries in ascending
 // c; for each c the raters of c that fall in the chunk are a CONTIGUOUS slice of c's id-sorted
 // list in the right CSR (chunk pointers `cp`, precomputed), so the lanes read (j, b-side term)
@@ -16,12 +16,14 @@
 //
 // Bound: shared-memory RMW bandwidth (6 accesses per triple, random banks) and L2 reads of
 // 12 B per triple; see DESIGN.md and profiles/.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int SW = RS_STREAM_WARPS;        // warps per CTA, each an independent work item
-constexpr int JC = RS_STREAM_JC;           // columns per work item
 
 struct StreamArgs {
     const int64_t *l_ptr;
@@ -47,7 +49,7 @@ struct StreamArgs {
 
 constexpr int G = 8;   // columns whose first 32 raters are loaded together (must divide 32)
 
-template <int SIM, bool SHRINK>
+template <int SIM, bool SHRINK, int JC>
 __device__ __forceinline__ void stream_update(double *acc, int j, double ra, double raa, double rb) {
     if (SIM == RS_SIM_MSD) {
         const double d = ra - rb;
@@ -67,7 +69,7 @@ __device__ __forceinline__ void stream_update(double *acc, int j, double ra, dou
 // Indices into the right CSR are kept in 32 bits inside the loop (nnz < 2^32 is checked at launch)
 // and the per-entry a-side terms are staged in shared memory, which halves the instructions per
 // column against the first version of this kernel (profiles/r01_stream_notes.md).
-template <int SIM, bool SHRINK, bool SYM>
+template <int SIM, bool SHRINK, bool SYM, int JC>
 __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
     constexpr int NACC = SHRINK ? 4 : 3;
     extern __shared__ double s_acc_all[];                    // [SW][NACC][JC] accumulators, then [SW][32] a-side terms
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
                     if (nn[g] == 0) continue;                                       // warp-uniform
                     const double ra_u = s_ra[u0 + g];
                     const double raa_u = ra_u * ra_u;                               // core/sim.go:19 / :75
-                    if (jj[g] >= 0) stream_update<SIM, SHRINK>(acc, jj[g], ra_u, raa_u, rbv[g]);
+                    if (jj[g] >= 0) stream_update<SIM, SHRINK, JC>(acc, jj[g], ra_u, raa_u, rbv[g]);
                     if (nn[g] > 32) {                                               // long run: remaining raters
                         const uint32_t lo_u = __shfl_sync(0xffffffffu, lo, u0 + g);
                         uint32_t self_u = 0xffffffffu;
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
                         for (int t = lane + 32; t < nn[g]; t += 32) {
                             const uint32_t idx = lo_u + (uint32_t)t;
                             if (!SYM && idx == self_u) continue;
-                            stream_update<SIM, SHRINK>(acc, r_col[idx] - j0, ra_u, raa_u, r_dev[idx]);
+                            stream_update<SIM, SHRINK, JC>(acc, r_col[idx] - j0, ra_u, raa_u, r_dev[idx]);
                         }
                     }
                     __syncwarp();   // column c is complete before column c+1 touches the same j
@@ -212,13 +214,18 @@ __global__ void symmetrize_kernel(double *__restrict__ s, int64_t ld, int32_t n,
 
 }  // namespace
 
-template <int SIM, bool SHRINK, bool SYM>
-static int32_t launch_stream_sym(rs_knn *h, const StreamArgs &s, int grid) {
+template <int SIM, bool SHRINK, bool SYM, int JC>
+static int32_t launch_stream_jc(rs_knn *h, const StreamArgs &s, int grid) {
     const int smem = SW * ((SHRINK ? 4 : 3) * JC + 32) * (int)sizeof(double);
-    auto kern = sim_stream_kernel<SIM, SHRINK, SYM>;
+    auto kern = sim_stream_kernel<SIM, SHRINK, SYM, JC>;
     RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid, SW * 32, smem, h->stream>>>(s);
     return RS_OK;
+}
+template <int SIM, bool SHRINK, bool SYM>
+static int32_t launch_stream_sym(rs_knn *h, const StreamArgs &s, int grid) {
+    if (h->stream_jc == 128) return launch_stream_jc<SIM, SHRINK, SYM, 128>(h, s, grid);
+    return launch_stream_jc<SIM, SHRINK, SYM, 256>(h, s, grid);
 }
 template <int SIM, bool SHRINK>
 static int32_t launch_stream(rs_knn *h, const StreamArgs &s, int grid) {

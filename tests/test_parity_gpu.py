@@ -68,6 +68,25 @@ def test_sims_bit_exact_ml100k(ml100k, sim, user_based):
     assert bits_equal(got, got.T)                            # core/knn.go:205-208
 
 
+# ---- both chunk widths of the stream kernel (128 for small matrices, 256 for large ones) ----
+@pytest.mark.parametrize("jc", ["128", "256"])
+@pytest.mark.parametrize("sim", ["cosine", "msd", "pearson"])
+def test_sims_bit_exact_both_chunk_widths(ml100k, sim, jc, monkeypatch):
+    monkeypatch.setenv("RS_KNN_STREAM_JC", jc)
+    est, ref = fit_pair(ml100k["u3_base"], sim, "basic", False, extra={"simPath": "stream"})
+    got, want = est.Sims, ref.sims()
+    assert np.isnan(np.diag(got)).all()
+    assert bits_equal(got, want)
+    # a row shard takes the non-symmetric code path (whole runs, diagonal skipped by index)
+    n = got.shape[0]
+    b, e = n // 3, n // 3 + 200
+    part = rs.NewKNN(rs.Parameters({"sim": SIMS[sim], "userBased": False, "simPath": "stream",
+                                    "rowBegin": b, "rowEnd": e}))
+    u, i, r = split(ml100k["u3_base"])
+    part.Fit(rs.NewTrainSet(rs.NewRawSet(u, i, r)))
+    assert bits_equal(part.Sims, want[b:e])
+
+
 # ---- Predict: 4 KNN types, default config of the reference's tests (user-based MSD k=40) ----
 @pytest.mark.parametrize("knn_type", ["basic", "centered", "zscore", "baseline"])
 def test_predict_bit_exact_default_config(ml100k, knn_type):
