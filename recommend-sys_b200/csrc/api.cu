@@ -305,7 +305,7 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
     return RS_OK;
 }
 
-static int32_t scratch_get(rs_knn *h, int slot, size_t bytes, void **out) {
+int32_t rs_scratch_get(rs_knn *h, int slot, size_t bytes, void **out) {
     if (h->scratch.size() <= (size_t)slot) {
         h->scratch.resize(slot + 1, nullptr);
         h->scratch_bytes.resize(slot + 1, 0);
@@ -336,18 +336,18 @@ int32_t rs_knn_fit(rs_knn *h, const int32_t *left, const int32_t *right, const d
     }
     // persistent device staging (grow-only): a refit of the same size allocates nothing
     void *d_left, *d_right, *d_rating, *d_lb = nullptr, *d_rb = nullptr;
-    RS_TRY(scratch_get(h, 7, (size_t)nnz * 4, &d_left));
-    RS_TRY(scratch_get(h, 8, (size_t)nnz * 4, &d_right));
-    RS_TRY(scratch_get(h, 9, (size_t)nnz * 8, &d_rating));
+    RS_TRY(rs_scratch_get(h, 7, (size_t)nnz * 4, &d_left));
+    RS_TRY(rs_scratch_get(h, 8, (size_t)nnz * 4, &d_right));
+    RS_TRY(rs_scratch_get(h, 9, (size_t)nnz * 8, &d_rating));
     RS_CUDA(cudaMemcpyAsync(d_left, left, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
     RS_CUDA(cudaMemcpyAsync(d_right, right, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
     RS_CUDA(cudaMemcpyAsync(d_rating, rating, (size_t)nnz * 8, cudaMemcpyHostToDevice, h->stream));
     if (left_bias) {
-        RS_TRY(scratch_get(h, 10, (size_t)n_left * 8, &d_lb));
+        RS_TRY(rs_scratch_get(h, 10, (size_t)n_left * 8, &d_lb));
         RS_CUDA(cudaMemcpyAsync(d_lb, left_bias, (size_t)n_left * 8, cudaMemcpyHostToDevice, h->stream));
     }
     if (right_bias) {
-        RS_TRY(scratch_get(h, 11, (size_t)n_right * 8, &d_rb));
+        RS_TRY(rs_scratch_get(h, 11, (size_t)n_right * 8, &d_rb));
         RS_CUDA(cudaMemcpyAsync(d_rb, right_bias, (size_t)n_right * 8, cudaMemcpyHostToDevice, h->stream));
     }
     RS_TRY(rs_knn_fit_device(h, (const int32_t *)d_left, (const int32_t *)d_right, (const double *)d_rating, nnz,
@@ -401,9 +401,9 @@ int32_t rs_knn_predict_batch(rs_knn *h, const int32_t *left, const int32_t *righ
         return RS_ERR_INVALID;
     }
     void *dl, *dr, *dout;
-    RS_TRY(scratch_get(h, 0, (size_t)n * 4, &dl));
-    RS_TRY(scratch_get(h, 1, (size_t)n * 4, &dr));
-    RS_TRY(scratch_get(h, 2, (size_t)n * 8, &dout));
+    RS_TRY(rs_scratch_get(h, 0, (size_t)n * 4, &dl));
+    RS_TRY(rs_scratch_get(h, 1, (size_t)n * 4, &dr));
+    RS_TRY(rs_scratch_get(h, 2, (size_t)n * 8, &dout));
     RS_CUDA(cudaMemcpyAsync(dl, left, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
     RS_CUDA(cudaMemcpyAsync(dr, right, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
     RS_TRY(rs_knn_predict_batch_device(h, (const int32_t *)dl, (const int32_t *)dr, n, (double *)dout));
@@ -421,12 +421,12 @@ int32_t rs_knn_predict_neighbors(rs_knn *h, int32_t left, int32_t right, int32_t
         return RS_ERR_INVALID;
     }
     void *dl, *dr, *dout, *dids, *dsims, *dcnt;
-    RS_TRY(scratch_get(h, 0, 4, &dl));
-    RS_TRY(scratch_get(h, 1, 4, &dr));
-    RS_TRY(scratch_get(h, 2, 8, &dout));
-    RS_TRY(scratch_get(h, 3, (size_t)cap * 4, &dids));
-    RS_TRY(scratch_get(h, 4, (size_t)cap * 8, &dsims));
-    RS_TRY(scratch_get(h, 5, 4, &dcnt));
+    RS_TRY(rs_scratch_get(h, 0, 4, &dl));
+    RS_TRY(rs_scratch_get(h, 1, 4, &dr));
+    RS_TRY(rs_scratch_get(h, 2, 8, &dout));
+    RS_TRY(rs_scratch_get(h, 3, (size_t)cap * 4, &dids));
+    RS_TRY(rs_scratch_get(h, 4, (size_t)cap * 8, &dsims));
+    RS_TRY(rs_scratch_get(h, 5, 4, &dcnt));
     RS_CUDA(cudaMemcpyAsync(dl, &left, 4, cudaMemcpyHostToDevice, h->stream));
     RS_CUDA(cudaMemcpyAsync(dr, &right, 4, cudaMemcpyHostToDevice, h->stream));
     RS_CUDA(cudaMemsetAsync(dcnt, 0, 4, h->stream));
@@ -487,8 +487,8 @@ int32_t rs_knn_topk(rs_knn *h, int32_t k, int32_t *idx, double *sim) {
     }
     const int64_t rows = h->row_end - h->row_begin;
     void *di, *ds;
-    RS_TRY(scratch_get(h, 3, (size_t)rows * k * 4, &di));
-    RS_TRY(scratch_get(h, 4, (size_t)rows * k * 8, &ds));
+    RS_TRY(rs_scratch_get(h, 3, (size_t)rows * k * 4, &di));
+    RS_TRY(rs_scratch_get(h, 4, (size_t)rows * k * 8, &ds));
     RS_TRY(rs_knn_topk_device(h, k, (int32_t *)di, (double *)ds));
     RS_CUDA(cudaMemcpyAsync(idx, di, (size_t)rows * k * 4, cudaMemcpyDeviceToHost, h->stream));
     RS_CUDA(cudaMemcpyAsync(sim, ds, (size_t)rows * k * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -510,7 +510,7 @@ int32_t rs_knn_cosums(rs_knn *h, int64_t row0, int64_t nrows, int32_t *out) {
     if (!h->planes) RS_TRY(rs_prep_planes(h));
     void *d;
     const size_t bytes = (size_t)nrows * (size_t)h->n_left * 6 * 4;
-    RS_TRY(scratch_get(h, 6, bytes, &d));
+    RS_TRY(rs_scratch_get(h, 6, bytes, &d));
     RS_TRY(rs_sim_tensor_launch(h, (int32_t *)d, row0, nrows));
     RS_CUDA(cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, h->stream));
     RS_CUDA(cudaStreamSynchronize(h->stream));

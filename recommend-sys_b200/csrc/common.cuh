@@ -131,6 +131,9 @@ int32_t rs_cached_malloc(int device, void **out, size_t bytes, size_t *got);
 void rs_cached_free(int device, void *p, size_t bytes);
 void rs_cache_trim(void);
 
+// ---- api.cu: grow-only per-handle device scratch (slot-indexed) ----
+extern "C" int32_t rs_scratch_get(rs_knn *h, int slot, size_t bytes, void **out);
+
 // ---- prep.cu ----
 int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, const double *d_rating,
                       const double *d_left_bias, const double *d_right_bias);

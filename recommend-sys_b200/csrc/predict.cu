@@ -10,6 +10,8 @@
 //      core/knn.go:116-130 does, so the prediction is bit-identical to the restated
 //      reference under the canonical policy.
 // HBM-bound by design: per prediction C*(4 B id + 8 B rating + 8 B similarity [+ 8 B mean/bias]).
+#include <cub/cub.cuh>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -30,6 +32,8 @@ __device__ __forceinline__ bool rec_before(uint64_t ka, uint32_t pa, uint64_t kb
 
 
 struct PredArgs {
+    const int32_t *perm;   // optional processing order (test pairs grouped by left row), else identity
+    unsigned long long *work;   // dynamic work counter: warps grab PRED_GRAB consecutive positions
     const int32_t *left, *right;
     int64_t n;
     double *out;
@@ -67,6 +71,7 @@ struct PredArgs {
 //           exactly as core/knn.go:116-130 does.
 // =====================================================================================
 constexpr int SEL_WARPS = 8;
+constexpr int PRED_GRAB = 4;   // consecutive positions a warp takes per visit to the work counter
 
 template <int R>
 __device__ __forceinline__ void ce_regs(uint64_t (&key)[R], uint32_t (&pos)[R], int i, int j, bool up) {
@@ -132,11 +137,21 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
     uint64_t *ckey = s_key[warp];
     uint32_t *cpos = s_pos[warp];
     uint64_t *sbuf = reinterpret_cast<uint64_t *>(s_stage) + (size_t)warp * scap;
-    const int64_t n_warps = (int64_t)gridDim.x * SEL_WARPS;
     const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
     const uint32_t lt_mask = (1u << lane) - 1u;
 
-    for (int64_t p = (int64_t)blockIdx.x * SEL_WARPS + warp; p < a.n; p += n_warps) {
+    // Positions are handed out in order from one counter, so the predictions in flight are always
+    // a contiguous window of the (row-grouped) order however unevenly long they take — with a
+    // static stride the warps drift apart and the window grows past L2 (137 GB of DRAM reads per
+    // 4 M predictions on the MovieLens-20M shape, profiles/r01_predict_ml20m_summary.txt).
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.work, (unsigned long long)PRED_GRAB);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((int64_t)base >= a.n) break;
+        const int64_t w_end = (int64_t)base + PRED_GRAB < a.n ? (int64_t)base + PRED_GRAB : a.n;
+    for (int64_t w = (int64_t)base; w < w_end; w++) {
+        const int64_t p = a.perm ? (int64_t)a.perm[w] : w;
         const int32_t l = a.left[p], r = a.right[p];
         if (a.nb_count && lane == 0) *a.nb_count = 0;
         if (l < 0 || r < 0 || r >= a.n_right) {            // core/knn.go:89-91 (newID)
@@ -336,6 +351,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
             if (a.nb_count) *a.nb_count = num < a.nb_cap ? num : a.nb_cap;
         }
     }
+    }
 }
 
 
@@ -418,6 +434,11 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_rows_kernel(const double *_
 
 }  // namespace
 
+__global__ void iota_kernel(int32_t *out, int32_t n) {
+    const int32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < n) out[x] = x;
+}
+
 template <int R>
 static int32_t launch_select(const PredArgs &a, unsigned blocks, size_t smem, int scap, cudaStream_t st) {
     auto kern = predict_select_kernel<R>;
@@ -445,9 +466,39 @@ int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
     a.global_mean = h->global_mean; a.n_right = h->n_right;
     a.k = h->p.k; a.min_k = h->p.min_k; a.knn_type = h->p.knn_type;
     a.nb_ids = d_nb_ids; a.nb_sims = d_nb_sims; a.nb_count = d_nb_count; a.nb_cap = nb_cap;
+    // Large batches are processed grouped by left row: the gathers of one prediction all fall in
+    // ONE row of the similarity matrix (N x 8 B), so test pairs of the same row, run by neighbouring
+    // warps at the same time, find that row in L2 instead of fetching it from HBM once per pair
+    // (MovieLens-20M item shape: 150 test pairs per row, 5.7 GB matrix).  Stable radix sort of
+    // (left id, index) — CUB, plumbing — and the kernel walks the permutation.
+    a.perm = nullptr;
+    if (n >= 65536 && (size_t)(h->row_end - h->row_begin) * (size_t)h->ld_s * 8 > ((size_t)64 << 20) &&
+        !getenv("RS_KNN_PRED_NOSORT")) {
+        void *keys_out, *iota, *perm, *tmp;
+        RS_TRY(rs_scratch_get(h, 12, (size_t)n * 4, &keys_out));
+        RS_TRY(rs_scratch_get(h, 13, (size_t)n * 4, &iota));
+        RS_TRY(rs_scratch_get(h, 14, (size_t)n * 4, &perm));
+        size_t need = 0;
+        int bits = 1;
+        while ((1ll << bits) < (long long)h->n_left && bits < 31) bits++;
+        RS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, d_left, (int32_t *)keys_out, (int32_t *)iota,
+                                                (int32_t *)perm, (int)n, 0, bits, h->stream));
+        RS_TRY(rs_scratch_get(h, 15, need + 256, &tmp));
+        iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((int32_t *)iota, (int32_t)n);
+        RS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, need, d_left, (int32_t *)keys_out, (int32_t *)iota,
+                                                (int32_t *)perm, (int)n, 0, bits, h->stream));
+        a.perm = (const int32_t *)perm;
+        h->prof.total_launches += 1;   // own kernels only
+    }
+    {
+        void *work;
+        RS_TRY(rs_scratch_get(h, 16, 8, &work));
+        RS_CUDA(cudaMemsetAsync(work, 0, 8, h->stream));
+        a.work = reinterpret_cast<unsigned long long *>(work);
+    }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    int64_t blocks = (n + SEL_WARPS - 1) / SEL_WARPS;
+    int64_t blocks = (n + SEL_WARPS * PRED_GRAB - 1) / (SEL_WARPS * PRED_GRAB);
     const int64_t cap = (int64_t)sms * 8;   // resident CTAs; warps stride over the predictions
     if (blocks > cap) blocks = cap;
     // staging capacity per warp (similarities parked in shared memory between the passes)
