@@ -129,7 +129,9 @@ def load_peaks():
 def cpu_reference_step(ob, ots, test, sim, knn_type, user_based, k, cores, rows=None, n_pred=None):
     """One step of the reference's CPU algorithm (restated in oracle/): returns (seconds_fit,
     seconds_predict, rows_fitted, n_predicted)."""
-    knn = ob.KNN(sim=sim, knn_type=knn_type, user_based=user_based, k=k, n_jobs=cores, tie_policy="go")
+    # config 3 (PearsonBaseline + KNNBaseline) uses ALS baselines on both arms (BASELINE.json configs[2])
+    knn = ob.KNN(sim=sim, knn_type=knn_type, user_based=user_based, k=k, n_jobs=cores, tie_policy="go",
+                 baseline="als" if sim == "pearson_baseline" else "sgd")
     t0 = time.perf_counter()
     knn.fit(ots, rows=rows)
     t1 = time.perf_counter()
@@ -273,7 +275,8 @@ def run_ours(args, rank, world, local_rank):
     d_lb = d_rb = None
     global_bias = 0.0
     if knn_type == "baseline" or sim == "pearson_baseline":
-        bl = rs.NewBaseLine(rs.Parameters({}))
+        bl = rs.NewBaseLine(rs.Parameters({"baseline": "als" if sim == "pearson_baseline" else "sgd",
+                                           "device": local_rank}))
         bl.Fit(train)
         lb, rbias = (bl.userBias, bl.itemBias) if user_based else (bl.itemBias, bl.userBias)
         global_bias = float(bl.globalBias)
@@ -333,6 +336,8 @@ def run_ours(args, rank, world, local_rank):
     sim_obj = {"cosine": rs.Cosine, "msd": rs.MSD, "pearson": rs.Pearson, "pearson_baseline": rs.PearsonBaseline}[sim]
     params = {"sim": sim_obj, "userBased": user_based, "k": k, "device": local_rank,
               "pearsonMode": args.pearson_mode, "simPath": args.sim_path}
+    if sim == "pearson_baseline":
+        params["baseline"] = "als"      # device ALS baselines inside the timed e2e Fit
     if shard:
         params.update({"rowBegin": rb, "rowEnd": re})
     e2e_test = test

@@ -169,6 +169,19 @@ int32_t rs_knn_cosums(rs_knn *h, int64_t row0, int64_t nrows, int32_t *out);
 int32_t rs_knn_means(rs_knn *h, double *out);
 int32_t rs_knn_stddevs(rs_knn *h, double *out);
 
+/* EXTENSION (BASELINE.json config 3 "ALS baselines") — an alternative to
+ * BaseLine.Fit (core/base.go:135-163), whose sequential SGD stays on the host: alternating least
+ * squares baseline estimates computed on `device` (-1 = current) from the inner-id COO (host
+ * pointers, dataset order), Surprise-style
+ *     b_i = sum_{u in R(i)} (r_ui - mu - b_u) / (reg_i + |R(i)|),  then  b_u likewise,  n_epochs times,
+ * mu = global_mean.  Writes user_bias[n_users], item_bias[n_items]; pass them (and mu as
+ * global_bias) to rs_knn_fit for KNNBaseline / PearsonBaseline.  Selected from the host API with
+ * Parameters["baseline"] = "als" (defaults regU 15, regI 10, nEpochs 10).  Parity unpinned: the
+ * reference has no ALS; checked against oracle/knn_oracle.c:or_baseline_als bit for bit. */
+int32_t rs_baseline_als(int32_t device, const int32_t *users, const int32_t *items, const double *ratings,
+                        int64_t nnz, int32_t n_users, int32_t n_items, double global_mean, double reg_u,
+                        double reg_i, int32_t n_epochs, double *user_bias, double *item_bias);
+
 int32_t rs_knn_profile_get(rs_knn *h, rs_knn_profile *out);
 int32_t rs_knn_profile_reset(rs_knn *h);
 /* Destroyed handles park their device memory in a process-wide cache (estimator copies are

@@ -37,7 +37,8 @@ class Params(C.Structure):
     _fields_ = [("sim", C.c_int), ("knn_type", C.c_int), ("user_based", C.c_int), ("k", C.c_int),
                 ("min_k", C.c_int), ("n_jobs", C.c_int), ("tie_policy", C.c_int),
                 ("reg", C.c_double), ("lr", C.c_double), ("n_epochs", C.c_int),
-                ("shrinkage", C.c_double)]
+                ("shrinkage", C.c_double), ("baseline_als", C.c_int), ("als_epochs", C.c_int),
+                ("reg_u", C.c_double), ("reg_i", C.c_double)]
 
 
 _lib = None
@@ -92,6 +93,8 @@ def lib():
     L.or_knn_topk.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, p32, pd]
     L.or_knn_pair_sums.argtypes = [C.c_void_p, C.c_int64, C.c_int64, p64]
     L.or_baseline_fit.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, pd, pd, pd]
+    L.or_baseline_als.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, pd, pd]
+    L.or_baseline_als.restype = None
     L.or_rmse.restype = C.c_double
     L.or_rmse.argtypes = [pd, pd, C.c_int64]
     L.or_mae.restype = C.c_double
@@ -155,14 +158,27 @@ class TrainSet:
         return ub, ib, gb.value
 
 
+def _baseline_als(self, reg_u=15.0, reg_i=10.0, n_epochs=10):
+    """EXTENSION (parity unpinned): ALS baselines, the checker of rs_baseline_als."""
+    ub = np.zeros(self.user_count, dtype=np.float64)
+    ib = np.zeros(self.item_count, dtype=np.float64)
+    lib().or_baseline_als(self.h, reg_u, reg_i, n_epochs, _p(ub, C.c_double), _p(ib, C.c_double))
+    return ub, ib, self.global_mean
+
+
+TrainSet.baseline_als = _baseline_als
+
+
 class KNN:
     def __init__(self, sim="msd", knn_type="basic", user_based=True, k=40, min_k=1, n_jobs=1,
-                 tie_policy="canonical", reg=0.02, lr=0.005, n_epochs=20, shrinkage=0.0):
+                 tie_policy="canonical", reg=0.02, lr=0.005, n_epochs=20, shrinkage=0.0, baseline="sgd",
+                 reg_u=15.0, reg_i=10.0, als_epochs=10):
         p = Params()
         lib().or_params_default(C.byref(p))
         p.sim, p.knn_type, p.user_based = SIM[sim], KNN_TYPE[knn_type], int(user_based)
         p.k, p.min_k, p.n_jobs, p.tie_policy = k, min_k, n_jobs, TIE[tie_policy]
         p.reg, p.lr, p.n_epochs, p.shrinkage = reg, lr, n_epochs, shrinkage
+        p.baseline_als, p.als_epochs, p.reg_u, p.reg_i = int(baseline == "als"), als_epochs, reg_u, reg_i
         self.params = p
         self.h = lib().or_knn_new(C.byref(p))
         self.train = None

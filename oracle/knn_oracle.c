@@ -447,6 +447,52 @@ void or_baseline_fit(const or_trainset *t, double reg, double lr, int n_epochs,
 }
 
 /* =====================================================================================
+ * ALS baselines — EXTENSION (BASELINE.json config 3 names "ALS baselines"; the reference only
+ * has the sequential SGD above, so this has no reference counterpart: PARITY UNPINNED, this
+ * function is the definition the device kernel (csrc/baseline.cu) is checked against).
+ * Koren's alternating least squares as popularised by Surprise's `baseline_only`:
+ *     repeat n_epochs:  b_i = sum_{u in R(i)} (r_ui - mu - b_u) / (reg_i + |R(i)|)   for every item
+ *                       b_u = sum_{i in R(u)} (r_ui - mu - b_i) / (reg_u + |R(u)|)   for every user
+ * with mu = the global mean.  Summation order (fixed so the result is reproducible bit for bit):
+ * a row's terms, in dataset order, are dealt round-robin to 32 partial sums (term t goes to
+ * partial t % 32, each partial accumulated sequentially), then combined by the butterfly
+ * p[l] += p[l ^ 16], ^8, ^4, ^2, ^1 — exactly what one warp does with __shfl_xor.
+ * ===================================================================================== */
+static double als_row_sum(const or_idrating *row, int64_t len, double mu, const double *other) {
+    double part[32];
+    for (int l = 0; l < 32; l++) part[l] = 0.0;
+    for (int64_t t = 0; t < len; t++) {
+        double term = (row[t].rating - mu) - other[row[t].id];
+        part[t & 31] += term;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        double nxt[32];
+        for (int l = 0; l < 32; l++) nxt[l] = part[l] + part[l ^ o];
+        for (int l = 0; l < 32; l++) part[l] = nxt[l];
+    }
+    return part[0];
+}
+
+void or_baseline_als(or_trainset *t, double reg_u, double reg_i, int n_epochs, double *user_bias,
+                     double *item_bias) {
+    /* private adjacency in dataset order (KNN.Fit sorts the shared lists in place, core/data.go:236-243) */
+    or_idrating **ur, **ir, *ustore, *istore;
+    int64_t *ulen, *ilen;
+    build_adjacency(t->n, t->user_count, t->iu, t->ii, t->ratings, &ur, &ulen, &ustore);
+    build_adjacency(t->n, t->item_count, t->ii, t->iu, t->ratings, &ir, &ilen, &istore);
+    const double mu = t->global_mean;
+    for (int64_t u = 0; u < t->user_count; u++) user_bias[u] = 0.0;
+    for (int64_t i = 0; i < t->item_count; i++) item_bias[i] = 0.0;
+    for (int epoch = 0; epoch < n_epochs; epoch++) {
+        for (int64_t i = 0; i < t->item_count; i++)
+            item_bias[i] = als_row_sum(ir[i], ilen[i], mu, user_bias) / (reg_i + (double)ilen[i]);
+        for (int64_t u = 0; u < t->user_count; u++)
+            user_bias[u] = als_row_sum(ur[u], ulen[u], mu, item_bias) / (reg_u + (double)ulen[u]);
+    }
+    free(ur); free(ulen); free(ustore); free(ir); free(ilen); free(istore);
+}
+
+/* =====================================================================================
  * KNN — core/knn.go.
  * ===================================================================================== */
 struct or_knn {
@@ -467,6 +513,7 @@ void or_params_default(or_params *p) {
     p->sim = OR_SIM_MSD; p->knn_type = OR_KNN_BASIC; p->user_based = 1; p->k = 40; p->min_k = 1;
     p->n_jobs = 1; p->tie_policy = OR_TIE_CANONICAL; p->reg = 0.02; p->lr = 0.005; p->n_epochs = 20;
     p->shrinkage = 0.0;
+    p->baseline_als = 0; p->als_epochs = 10; p->reg_u = 15.0; p->reg_i = 10.0;
 }
 
 or_knn *or_knn_new(const or_params *p) {
@@ -595,7 +642,12 @@ static void knn_fit_impl(or_knn *k, or_trainset *t, int64_t row0, int64_t row1, 
     if (k->p.knn_type == OR_KNN_BASELINE || k->p.sim == OR_SIM_PEARSON_BASELINE) {  /* core/knn.go:179-187 */
         k->user_bias = (double *)malloc((size_t)(t->user_count + 1) * sizeof(double));
         k->item_bias = (double *)malloc((size_t)(t->item_count + 1) * sizeof(double));
-        or_baseline_fit(t, k->p.reg, k->p.lr, k->p.n_epochs, k->user_bias, k->item_bias, &k->global_bias);
+        if (k->p.baseline_als) {
+            or_baseline_als(t, k->p.reg_u, k->p.reg_i, k->p.als_epochs, k->user_bias, k->item_bias);
+            k->global_bias = t->global_mean;
+        } else {
+            or_baseline_fit(t, k->p.reg, k->p.lr, k->p.n_epochs, k->user_bias, k->item_bias, &k->global_bias);
+        }
         if (k->p.knn_type == OR_KNN_BASELINE) k->bias = user_based ? k->user_bias : k->item_bias;
     }
     /* core/knn.go:190 → core/data.go:236-243: in-place sort.Sort of every left row by id */

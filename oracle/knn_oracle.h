@@ -64,6 +64,10 @@ typedef struct {
     double lr;          /* baseline   (Parameters["lr"],        default 0.005, core/base.go:138) */
     int n_epochs;       /* baseline   (Parameters["nEpochs"],   default 20,   core/base.go:139) */
     double shrinkage;   /* PearsonBaseline extension only (not in the reference)               */
+    int baseline_als;   /* EXTENSION: 1 = ALS baselines (or_baseline_als) instead of the SGD           */
+    int als_epochs;     /*            default 10                                                       */
+    double reg_u;       /*            default 15                                                       */
+    double reg_i;       /*            default 10                                                       */
 } or_params;
 
 void or_params_default(or_params *p);
@@ -120,6 +124,9 @@ void or_knn_topk(const or_knn *k, int kk, int64_t row0, int64_t row1, int32_t *i
 void or_knn_pair_sums(const or_knn *k, int64_t a, int64_t b, int64_t out[6]);
 
 /* ---- BaseLine (core/base.go:108-163) ---- */
+/* EXTENSION, parity unpinned: ALS baselines (see knn_oracle.c) — the checker of rs_baseline_als. */
+void or_baseline_als(or_trainset *t, double reg_u, double reg_i, int n_epochs, double *user_bias,
+                     double *item_bias);
 void or_baseline_fit(const or_trainset *t, double reg, double lr, int n_epochs,
                      double *user_bias, double *item_bias, double *global_bias);
 

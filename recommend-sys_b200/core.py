@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "rs_knn_destroy", "rs_knn_set_stream", "rs_knn_fit", "rs_knn_fit_device", "rs_knn_predict_batch",
     "rs_knn_predict_batch_device", "rs_knn_predict_neighbors", "rs_knn_sims_rows", "rs_knn_topk",
     "rs_knn_topk_device", "rs_knn_cosums", "rs_knn_means", "rs_knn_stddevs", "rs_knn_profile_get",
-    "rs_knn_profile_reset", "rs_knn_synchronize", "rs_knn_trim_cache",
+    "rs_knn_profile_reset", "rs_knn_synchronize", "rs_knn_trim_cache", "rs_baseline_als",
 ]
 
 _knn_lib = None
@@ -105,6 +105,7 @@ def knn_lib():
     for name in ABI_SYMBOLS:
         if name != "rs_last_error":
             getattr(L, name).restype = i32
+    L.rs_baseline_als.argtypes = [i32, vp, vp, vp, i64, i32, i32, dbl, dbl, dbl, i32, vp, vp]
     _knn_lib = L
     return L
 
@@ -535,6 +536,19 @@ class BaseLine(Base):
         self.trainSet = trainSet
         self.userBias = np.zeros(trainSet.UserCount, dtype=np.float64)
         self.itemBias = np.zeros(trainSet.ItemCount, dtype=np.float64)
+        if self.Params.GetString("baseline", "sgd") == "als":
+            # EXTENSION (BASELINE.json config 3): ALS baselines on the device, rs_baseline_als
+            iu = np.ascontiguousarray(trainSet.innerUsers, dtype=np.int32)
+            ii = np.ascontiguousarray(trainSet.innerItems, dtype=np.int32)
+            rr = np.ascontiguousarray(trainSet.Ratings, dtype=np.float64)
+            _check(knn_lib().rs_baseline_als(self.Params.GetInt("device", -1), _ptr(iu), _ptr(ii), _ptr(rr),
+                                             len(rr), trainSet.UserCount, trainSet.ItemCount,
+                                             trainSet.GlobalMean, self.Params.GetFloat64("regU", 15.0),
+                                             self.Params.GetFloat64("regI", 10.0),
+                                             self.Params.GetInt("nEpochs", 10), _ptr(self.userBias),
+                                             _ptr(self.itemBias)))
+            self.globalBias = trainSet.GlobalMean
+            return
         gb = C.c_double(0.0)
         host_lib().rs_host_baseline_sgd(_ptr(trainSet.innerUsers), _ptr(trainSet.innerItems),
                                         _ptr(trainSet.Ratings), trainSet.Length(), trainSet.UserCount,
@@ -566,7 +580,8 @@ class KNN(Base):
     (Sims is materialised from the device on demand)."""
 
     # extra Parameters keys understood by the device path (SURVEY.md §5 "Config / flags")
-    _DEVICE_KEYS = ("device", "pearsonMode", "simPath", "store", "topk", "rowBegin", "rowEnd", "shrinkage")
+    _DEVICE_KEYS = ("device", "pearsonMode", "simPath", "store", "topk", "rowBegin", "rowEnd", "shrinkage",
+                    "baseline", "regU", "regI")
 
     def __init__(self, knn_type, params=None):
         super().__init__(params)

@@ -111,3 +111,23 @@ def test_tie_policies_agree_without_ties(ml100k):
     pg, pc = go.predict_batch(u, i), ca.predict_batch(u, i)
     close = np.isclose(pg, pc, rtol=1e-12, atol=0)
     assert close.mean() > 0.9   # SURVEY hazard 1: ~3.5 % of cosine predictions straddle a tie
+
+
+def test_als_baselines_extension_matches_numpy():
+    """EXTENSION, parity unpinned: the oracle's ALS baselines (fixed 32-way summation order) against a
+    plain numpy restatement of the same recurrences (different summation order -> 1e-12)."""
+    rng = np.random.RandomState(7)
+    n = 30000
+    u, i = rng.randint(0, 400, n), rng.randint(0, 300, n)
+    _, first = np.unique(u * 1000 + i, return_index=True)
+    u, i = u[first], i[first]
+    r = rng.randint(1, 6, len(u)).astype(np.float64)
+    ts = ob.TrainSet(u, i, r)
+    ub, ib, mu = ts.baseline_als(reg_u=15.0, reg_i=10.0, n_epochs=10)
+    iu, ii = ts.inner_users(), ts.inner_items()
+    cu, ci = np.bincount(iu, minlength=ts.user_count), np.bincount(ii, minlength=ts.item_count)
+    bu, bi = np.zeros(ts.user_count), np.zeros(ts.item_count)
+    for _ in range(10):
+        bi = np.bincount(ii, weights=r - mu - bu[iu], minlength=ts.item_count) / (10.0 + ci)
+        bu = np.bincount(iu, weights=r - mu - bi[ii], minlength=ts.user_count) / (15.0 + cu)
+    assert np.abs(ub - bu).max() < 1e-12 and np.abs(ib - bi).max() < 1e-12

@@ -235,6 +235,33 @@ def test_pearson_baseline_extension(ml100k):
         assert bits_equal(est.PredictBatch(tu, ti), ref.predict_batch(tu, ti))
 
 
+def test_als_baselines_extension(ml100k):
+    """EXTENSION, parity unpinned (no ALS in the reference): device ALS baselines are bit-identical to
+    the oracle's restatement, and KNNBaseline + PearsonBaseline built on them match end to end."""
+    u, i, r = split(ml100k["u4_base"])
+    ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
+    bl = rs.NewBaseLine(rs.Parameters({"baseline": "als"}))
+    bl.Fit(ts)
+    ots = ob.TrainSet(u, i, r)
+    ub, ib, mu = ots.baseline_als()
+    assert bits_equal(bl.userBias, ub) and bits_equal(bl.itemBias, ib) and bl.globalBias == mu
+    # non-default hyper-parameters
+    bl2 = rs.NewBaseLine(rs.Parameters({"baseline": "als", "regU": 3.0, "regI": 7.5, "nEpochs": 4}))
+    bl2.Fit(ts)
+    ub2, ib2, _ = ots.baseline_als(reg_u=3.0, reg_i=7.5, n_epochs=4)
+    assert bits_equal(bl2.userBias, ub2) and bits_equal(bl2.itemBias, ib2)
+    est = rs.NewKNNBaseLine(rs.Parameters({"sim": rs.PearsonBaseline, "userBased": False, "baseline": "als",
+                                           "shrinkage": 100.0}))
+    est.Fit(ts)
+    ref = ob.KNN(sim="pearson_baseline", knn_type="baseline", user_based=False, n_jobs=8, baseline="als",
+                 shrinkage=100.0).fit(ob.TrainSet(u, i, r))
+    assert bits_equal(est.Sims, ref.sims())
+    tu, ti, _ = split(ml100k["u4_test"])
+    assert bits_equal(est.PredictBatch(tu, ti), ref.predict_batch(tu, ti, n_threads=8))
+    with pytest.raises(rs.core.RsError):
+        rs.core._check(rs.core.knn_lib().rs_baseline_als(-1, None, None, None, 0, 1, 1, 0.0, 1.0, 1.0, 1, None, None))
+
+
 def test_errors_are_loud():
     left = np.array([0, 0, 1], dtype=np.int32)
     right = np.array([0, 0, 1], dtype=np.int32)
