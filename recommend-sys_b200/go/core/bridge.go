@@ -132,6 +132,18 @@ func (d *deviceKNN) fit(left, right []int32, rating []float64, nLeft, nRight int
 	runtime.KeepAlive(rating)
 }
 
+// baselineALS is the EXTENSION behind Parameters["baseline"] = "als" (BASELINE.json config 3): ALS
+// baseline estimates computed on the device instead of BaseLine.Fit's sequential SGD
+// (core/base.go:135-163).  Returns (userBias, itemBias); the global bias is the global mean.
+func baselineALS(device int, users, items []int32, rating []float64, nUsers, nItems int, globalMean,
+	regU, regI float64, nEpochs int) ([]float64, []float64) {
+	ub, ib := make([]float64, nUsers), make([]float64, nItems)
+	check(C.rs_baseline_als(C.int32_t(device), i32(users), i32(items), f64(rating), C.int64_t(len(rating)),
+		C.int32_t(nUsers), C.int32_t(nItems), C.double(globalMean), C.double(regU), C.double(regI),
+		C.int32_t(nEpochs), f64(ub), f64(ib)))
+	return ub, ib
+}
+
 func (d *deviceKNN) predictBatch(left, right []int32) []float64 {
 	out := make([]float64, len(left))
 	check(C.rs_knn_predict_batch(d.h, i32(left), i32(right), C.int64_t(len(left)), f64(out)))

@@ -70,7 +70,19 @@ func (K *KNN) Fit(trainSet TrainSet) {
 	isPB := simEnum(sim) == simEnum(PearsonBaseline)
 	if K.KNNType == baseline || isPB {
 		baseLine := NewBaseLine(K.Params) // core/knn.go:179-187: sequential SGD stays on the host
-		baseLine.Fit(trainSet)
+		if K.Params.GetString("baseline", "sgd") == "als" { // EXTENSION: ALS baselines on the device
+			iu, ii := make([]int32, trainSet.Length()), make([]int32, trainSet.Length())
+			for i := 0; i < trainSet.Length(); i++ {
+				iu[i] = int32(trainSet.ConvertUserID(trainSet.Users[i]))
+				ii[i] = int32(trainSet.ConvertItemID(trainSet.Items[i]))
+			}
+			baseLine.userBias, baseLine.itemBias = baselineALS(K.Params.GetInt("device", -1), iu, ii,
+				trainSet.Ratings, trainSet.UserCount, trainSet.ItemCount, trainSet.GlobalMean,
+				K.Params.GetFloat64("regU", 15), K.Params.GetFloat64("regI", 10), K.Params.GetInt("nEpochs", 10))
+			baseLine.globalBias = trainSet.GlobalMean
+		} else {
+			baseLine.Fit(trainSet)
+		}
 		if K.userBased {
 			leftBias, rightBias = baseLine.userBias, baseLine.itemBias
 		} else {

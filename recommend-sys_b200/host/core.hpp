@@ -136,6 +136,8 @@ struct Estimator {  // core/base.go:8-12
     virtual std::unique_ptr<Estimator> Clone() const = 0;  // stands in for the gob Copy (core/eval.go:29-30)
 };
 
+inline void rs_check(int32_t rc);
+
 // core/base.go:108-163
 struct BaseLine : Estimator {
     std::vector<double> userBias, itemBias;
@@ -146,6 +148,14 @@ struct BaseLine : Estimator {
         trainSet = &t;
         userBias.assign(t.UserCount, 0.0);
         itemBias.assign(t.ItemCount, 0.0);
+        if (Params.GetString("baseline", "sgd") == "als") {   // EXTENSION: ALS baselines on the device
+            rs_check(rs_baseline_als(Params.GetInt("device", -1), t.innerUsers.data(), t.innerItems.data(),
+                                     t.Ratings.data(), (int64_t)t.Length(), t.UserCount, t.ItemCount, t.GlobalMean,
+                                     Params.GetFloat64("regU", 15.0), Params.GetFloat64("regI", 10.0),
+                                     Params.GetInt("nEpochs", 10), userBias.data(), itemBias.data()));
+            globalBias = t.GlobalMean;
+            return;
+        }
         rs_host_baseline_sgd(t.innerUsers.data(), t.innerItems.data(), t.Ratings.data(), (int64_t)t.Length(), t.UserCount,
                              t.ItemCount, Params.GetFloat64("reg", 0.02), Params.GetFloat64("lr", 0.005),
                              Params.GetInt("nEpochs", 20), userBias.data(), itemBias.data(), &globalBias);
