@@ -349,3 +349,46 @@ def test_ml1m_shape_properties():
     sel = np.where((ii >= 1000) & (ii < 1256))[0][:2000]
     want = ref.predict_batch(test.Users[sel], test.Items[sel], n_threads=8)
     assert bits_equal(pred[sel], want)
+
+
+def test_ml20m_shape_properties():
+    """BASELINE.json's target shape (item-based Pearson, k=40, MovieLens-20M: 138,493 x 26,744, 20 M
+    ratings) at FULL size: size-independent properties of the 5.7 GB similarity matrix checked on
+    slabs, plus an oracle slab of 48 rows x all N and the predictions that fall inside it."""
+    d = rs.core.synth_ratings(138_493, 26_744, 20_400_000, 0x5EED0003)
+    n_test = 400_000
+    train = rs.NewTrainSet(d.SubSet(np.arange(n_test, d.Length())))
+    test = d.SubSet(np.arange(n_test))
+    est = rs.NewKNNWithMean(rs.Parameters({"sim": rs.Pearson, "userBased": False, "k": 40}))
+    est.Fit(train)
+    n = train.ItemCount
+    h = est._h
+    a0, b0, m = 5000, 20000, 512
+    A = h.sims_rows(a0, m)
+    B = h.sims_rows(b0, m)
+    assert A.shape == (m, n)
+    assert np.isnan(A[np.arange(m), a0 + np.arange(m)]).all()             # diagonal unset (core/knn.go:202)
+    assert bits_equal(A[:, b0:b0 + m], B[:, a0:a0 + m].T)                 # Sims[i][j] == Sims[j][i] (core/knn.go:205-208)
+    assert bits_equal(A[:, a0:a0 + m], A[:, a0:a0 + m].T)
+    fin = A[np.isfinite(A)]
+    assert fin.min() >= -1.0000001 and fin.max() <= 1.0000001
+    # oracle slab (rows r0..r0+48 x all N)
+    r0, r1 = 5000, 5048
+    ots = ob.TrainSet(train.Users, train.Items, train.Ratings)
+    ref = ob.KNN(sim="pearson", knn_type="centered", user_based=False, n_jobs=16).fit(ots, rows=(r0, r1))
+    want = ref.sims(copy=False)[r0:r1]
+    assert bits_equal(A[r0 - a0:r1 - a0], want)
+    pred = test.Predict(est)
+    assert len(pred) == n_test
+    ii = train.convert_items(test.Items)
+    sel = np.where((ii >= r0) & (ii < r1))[0][:500]
+    assert len(sel) > 50
+    assert bits_equal(pred[sel], ref.predict_batch(test.Users[sel], test.Items[sel], n_threads=16))
+    # the dense tensor path agrees bit for bit with the sparse replay on Cosine at this size
+    cos_t = rs.NewKNN(rs.Parameters({"sim": rs.Cosine, "userBased": False, "simPath": "tensor"}))
+    cos_t.Fit(train)
+    T1 = cos_t._h.sims_rows(a0, 256)
+    cos_t.Close()
+    cos_s = rs.NewKNN(rs.Parameters({"sim": rs.Cosine, "userBased": False, "simPath": "stream"}))
+    cos_s.Fit(train)
+    assert bits_equal(T1, cos_s._h.sims_rows(a0, 256))
