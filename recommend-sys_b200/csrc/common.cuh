@@ -46,6 +46,7 @@ constexpr int RS_STREAM_WARPS = 8;
 constexpr int RS_TC_BM = 128;
 constexpr int RS_TC_BN = 64;
 constexpr int RS_TC_BK = 128;
+constexpr int RS_TC_KBLK = 256;   // bytes of K per block of the K-blocked plane layout [plane][K/256][row][256]
 
 struct rs_knn {
     rs_knn_params p{};
@@ -106,7 +107,7 @@ struct rs_knn {
     int32_t stream_jc = 256;
     int64_t *l2r = nullptr;
     int32_t *row_order = nullptr;  // left rows sorted by descending length
-    // int8 planes X, X^2, M of the left matrix, [3][n_pad][k_pad], K-major (tensor path)
+    // int8 planes X^2, M, X of the left matrix, [3][k_pad / 256][n_pad][256] (tensor path)
     int8_t *planes = nullptr;
     int64_t tc_npad = 0, tc_kpad = 0;
 

@@ -257,18 +257,20 @@ __global__ void build_l2r_kernel(const int64_t *__restrict__ l_ptr, const int32_
 }
 
 
-// planes[p][row][col]: p=0 rating^2, p=1 mask, p=2 rating (the order the MMAs of sim_tensor.cu
-// rely on: B planes adjacent in shared memory as X2 | M | X); K-major int8
+// planes[p][col / kblk][row][col % kblk]: p=0 rating^2, p=1 mask, p=2 rating (the order the MMAs of
+// sim_tensor.cu rely on: B planes adjacent in shared memory as X2 | M | X); int8, K-blocked so that
+// the TMA box of one (plane, K block, row range) is one contiguous run of bytes
 __global__ void scatter_planes_kernel(const int64_t *__restrict__ l_ptr, const int32_t *__restrict__ l_col,
                                       const uint8_t *__restrict__ l_code, int32_t n_left, int64_t npad,
-                                      int64_t kpad, int8_t *__restrict__ planes) {
+                                      int64_t kpad, int32_t kblk, int8_t *__restrict__ planes) {
     int32_t row = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     int lane = threadIdx.x & 31;
     if (row >= n_left) return;
     int64_t plane = npad * kpad;
     for (int64_t x = l_ptr[row] + lane; x < l_ptr[row + 1]; x += 32) {
         int v = (int)l_code[x] - RS_INT8_BIAS;
-        int64_t o = (int64_t)row * kpad + l_col[x];
+        const int32_t col = l_col[x];
+        int64_t o = ((int64_t)(col / kblk) * npad + row) * kblk + (col % kblk);
         planes[o] = (int8_t)(v * v);
         planes[plane + o] = 1;
         planes[2 * plane + o] = (int8_t)v;
@@ -521,14 +523,15 @@ int32_t rs_prep_rt(rs_knn *h) {
 
 int32_t rs_prep_planes(rs_knn *h) {
     cudaStream_t st = h->stream;
+    const int32_t kblk = RS_TC_KBLK;
     h->tc_npad = ((int64_t)h->n_left + RS_TC_BM - 1) / RS_TC_BM * RS_TC_BM;
-    h->tc_kpad = ((int64_t)h->n_right + RS_TC_BK - 1) / RS_TC_BK * RS_TC_BK;
+    h->tc_kpad = ((int64_t)h->n_right + RS_TC_KBLK - 1) / RS_TC_KBLK * RS_TC_KBLK;
     size_t bytes = 3 * (size_t)h->tc_npad * (size_t)h->tc_kpad;
     RS_TRY(rs_alloc(h, &h->planes, bytes));
     RS_CUDA(cudaMemsetAsync(h->planes, 0, bytes, st));
     scatter_planes_kernel<<<blocks_for((int64_t)h->n_left * 32), T, 0, st>>>(h->l_ptr, h->l_col, h->l_code,
                                                                             h->n_left, h->tc_npad, h->tc_kpad,
-                                                                            h->planes);
+                                                                            kblk, h->planes);
     h->prof.total_launches++;
     RS_CUDA(cudaGetLastError());
     return RS_OK;

@@ -14,8 +14,8 @@
 // Kernel shape (one CTA per SM, persistent over a static tile list):
 //   tile      = 128 left rows (MMA M, TMEM lanes) x BN left rows (MMA N) x all K;
 //               BN = 128 for Cosine / MSD, 64 for Pearson (six accumulators), see Cfg<>
-//   operands  = planes laid out [plane][row][K] int8, K-major; TMA 3-D boxes (BK bytes of K x rows,
-//               one plane per instruction) land one pipeline stage with SWIZZLE_128B (BK = 128,
+//   operands  = planes laid out K-blocked, [plane][K / 256][row][256] int8 (see tma_load_box);
+//               TMA 4-D boxes (BK bytes of K x rows, one plane per instruction) land one pipeline stage with SWIZZLE_128B (BK = 128,
 //               Pearson: 3 stages x 72 KB) or SWIZZLE_64B (BK = 64, Cosine / MSD: 4 stages x 48 KB)
 //   pipeline  = mbarrier full/empty ring; warp 0 lane 0 issues TMA, warp 1 lane 0 issues
 //               tcgen05.mma, warps 2-5 run the epilogue (tcgen05.ld -> FP64 -> HBM)
@@ -126,22 +126,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2,
-                                            uint32_t bar) {
+// Operand boxes: the planes are stored K-BLOCKED, [plane][K / 256][row][256 bytes of K] (RS_TC_KBLK), so
+// the rows of a tile are contiguous 256-byte pieces (one DRAM page / TLB entry serves a tile's rows
+// instead of one per row: +30 % on the Netflix shape, whose rows are 480 KB apart otherwise) while a
+// row piece still holds the next K blocks of the same row, which the 256-byte L2 promotion of the
+// tensor map prefetches.  Tensor map dims {256, rows, K / 256, planes}; a box is BK bytes x rows at
+// coordinates {k % 256, row, k / 256, plane}.
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *map, int row, int k, int plane,
+                                             uint32_t bar) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], "
-        "[%5];" ::"r"(dst),
-        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
+        "[%6];" ::"r"(dst),
+        "l"(map), "r"(k & (RS_TC_KBLK - 1)), "r"(row), "r"(k / RS_TC_KBLK), "r"(plane), "r"(bar)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2,
-                                               uint32_t bar, uint16_t cta_mask) {
+__device__ __forceinline__ void tma_load_box_mc(uint32_t dst, const CUtensorMap *map, int row, int k, int plane,
+                                                uint32_t bar, uint16_t cta_mask) {
     // the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and each of them
     // gets the complete_tx on its own mbarrier at the same offset
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
-        "[%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dst),
-        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "h"(cta_mask)
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%2, %3, %4, %5}], [%6], %7;" ::"r"(dst),
+        "l"(map), "r"(k & (RS_TC_KBLK - 1)), "r"(row), "r"(k / RS_TC_KBLK), "r"(plane), "r"(bar), "h"(cta_mask)
         : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -349,10 +355,10 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     mbar_arrive_expect_tx(fb, STAGE_BYTES);            // my own stage: slices from all peers
 #pragma unroll
                     for (int p = 0; p < 3; p++) {
-                        if (CJ > 1) tma_load_3d_mc(sa + p * A_PLANE_BYTES, &map_a, kb * BK, row_a, p, fb, mask_a);
-                        else tma_load_3d(sa + p * A_PLANE_BYTES, &map_a, kb * BK, row_a, p, fb);
-                        if (CI > 1) tma_load_3d_mc(sb + p * B_PLANE_BYTES, &map_b, kb * BK, row_b, p, fb, mask_b);
-                        else tma_load_3d(sb + p * B_PLANE_BYTES, &map_b, kb * BK, row_b, p, fb);
+                        if (CJ > 1) tma_load_box_mc(sa + p * A_PLANE_BYTES, &map_a, row_a, kb * BK, p, fb, mask_a);
+                        else tma_load_box(sa + p * A_PLANE_BYTES, &map_a, row_a, kb * BK, p, fb);
+                        if (CI > 1) tma_load_box_mc(sb + p * B_PLANE_BYTES, &map_b, row_b, kb * BK, p, fb, mask_b);
+                        else tma_load_box(sb + p * B_PLANE_BYTES, &map_b, row_b, kb * BK, p, fb);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -512,6 +518,265 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
 }
 
+// =================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2) for Cosine / MSD.
+//
+// The single-CTA kernel above is bound by operand delivery for Cosine / MSD: a 128 x 128 tile needs
+// 128 A rows + 128 B rows (x 3 planes) per K block.  Here the two CTAs of a cluster (two SMs of one
+// TPC) compute ONE 256 x 128 tile with M = 256 instructions issued by the even CTA: each SM stages
+// its own 128 A rows and only HALF of the B rows (64) — the tensor cores read the other half from
+// the peer's shared memory — i.e. 192 instead of 256 operand rows per 128 x 128 outputs and half
+// the B shared-memory reads per SM.  Stages are 36 KB, six of them in flight.
+//   barriers  full[s]  : lives in the even CTA; both CTAs' TMA loads complete_tx on it, the even
+//                        CTA's producer posts the expected bytes of both
+//             empty[s] : one per CTA; tcgen05.commit.cta_group::2 multicast to both
+//             tfull    : one per CTA (commit multicast) -> each CTA's epilogue reads ITS 128 TMEM lanes
+//             tempty   : even CTA only, 256 arrivals (both epilogues; the odd one arrives remotely)
+// Accumulator columns: Cosine [Syy | Sxy | Sxx], MSD [Syy+Sxx | count | Sxy] (N = 128 each; the wide
+// N = 256 combination of the single-CTA kernel is not available because the pair splits B by rows).
+namespace pair {
+
+constexpr int P_BN = 128, P_BK = 64, P_STAGES = 6;
+constexpr int P_A_PLANE = BM * P_BK;              // 8 KB  (128 rows of this CTA)
+constexpr int P_B_PLANE = (P_BN / 2) * P_BK;      // 4 KB  (this CTA's 64 of the 128 B rows)
+constexpr int P_A_STAGE = 3 * P_A_PLANE, P_B_STAGE = 3 * P_B_PLANE;
+constexpr int P_STAGE = P_A_STAGE + P_B_STAGE;    // 36 KB
+constexpr int P_SMEM = P_STAGES * P_STAGE + 1024 + 256;
+static_assert(P_SMEM <= 227 * 1024, "pair pipeline does not fit in shared memory");
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;       // shared::cluster address of the same offset in the even CTA
+
+__device__ __forceinline__ void tma_load_box_2sm(uint32_t dst, const CUtensorMap *map, int row, int k, int plane,
+                                                 uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, "
+        "%4, %5}], [%6];" ::"r"(dst),
+        "l"(map), "r"(k & (RS_TC_KBLK - 1)), "r"(row), "r"(k / RS_TC_KBLK), "r"(plane), "r"(leader_bar)
+        : "memory");
+}
+__device__ __forceinline__ void umma_i8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on `bar` in BOTH CTAs
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// kind::i8 instruction descriptor for the pair: D=S32, A=B=signed int8, K-major, M=256, N=n
+__host__ __device__ constexpr uint32_t make_idesc_2sm(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+sim_tensor_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
+    static_assert(MODE == TC_COSINE || MODE == TC_MSD, "pair kernel: Cosine / MSD");
+    constexpr int C_SYY = 0, C_B = 128, C_C = 256;   // Cosine: Syy, Sxy, Sxx   MSD: Syy+Sxx, count, Sxy
+    const int rank = (int)cluster_ctarank();         // 0 = even CTA = MMA issuer
+    const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = smem_base + P_STAGES * P_STAGE;
+    const uint32_t full_bar = bars;                      // P_STAGES x 8 B (used in the even CTA)
+    const uint32_t empty_bar = bars + 8 * P_STAGES;      // P_STAGES x 8 B
+    const uint32_t tfull_bar = bars + 16 * P_STAGES;     // 8 B
+    const uint32_t tempty_bar = tfull_bar + 8;           // 8 B (used in the even CTA)
+    const uint32_t tmem_slot = tempty_bar + 8;
+    uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t *tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t *>(smem_gen + P_STAGES * P_STAGE + 16 * P_STAGES + 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < P_STAGES; s++) {
+            mbar_init(full_bar + 8 * s, 1);
+            mbar_init(empty_bar + 8 * s, 1);
+        }
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 256);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // both CTAs' barriers and TMEM exist before anyone signals or issues
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ======================= TMA producer (both CTAs) =======================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int chunk = a.sync_chunk;
+            const unsigned long long n_ctas = gridDim.x;
+            long long g = 0;
+            for (int t = pair_id; t < a.num_tiles; t += n_pairs) {
+                const int2 tile = a.tiles[t];
+                const int row_a = (tile.x * 2 + rank) * BM;                  // my 128 of the tile's 256 A rows
+                const int row_b = tile.y * P_BN + rank * (P_BN / 2);          // my 64 of the tile's 128 B rows
+                for (int kb = 0; kb < a.k_blocks; kb++) {
+                    if (chunk > 0 && kb % chunk == 0) {                       // K-lockstep throttle (see above)
+                        if (g > 0) atomicAdd(a.progress, 1ull);
+                        const long long need = (g - a.sync_slack) * (long long)n_ctas;
+                        if (need > 0 && (long long)ld_relaxed_gpu(a.progress) < need) {
+                            const long long t0 = clock64();
+                            while ((long long)ld_relaxed_gpu(a.progress) < need && clock64() - t0 < a.sync_timeout) {}
+                        }
+                        g++;
+                    }
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1u, 0);
+                    const uint32_t sa = smem_base + stage * P_STAGE;
+                    const uint32_t sb = sa + P_A_STAGE;
+                    const uint32_t fb = (full_bar + 8 * stage) & PEER_MASK;    // the even CTA's barrier
+                    if (rank == 0) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * P_STAGE);
+#pragma unroll
+                    for (int p = 0; p < 3; p++) {
+                        tma_load_box_2sm(sa + p * P_A_PLANE, &map_a, row_a, kb * P_BK, p, fb);
+                        tma_load_box_2sm(sb + p * P_B_PLANE, &map_b, row_b, kb * P_BK, p, fb);
+                    }
+                    if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+            if (chunk > 0) {
+                const long long cpt = (a.k_blocks + chunk - 1) / chunk;
+                const long long max_chunks = (long long)((a.num_tiles + n_pairs - 1) / n_pairs) * cpt;
+                atomicAdd(a.progress, (unsigned long long)(max_chunks - g + 1));
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer (even CTA only) =======================
+        if (lane == 0 && rank == 0) {
+            int stage = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int t = pair_id; t < a.num_tiles; t += n_pairs) {
+                mbar_wait(tempty_bar, acc_phase ^ 1u, 1);            // both epilogues drained the accumulators
+                tc_fence_after();
+                const uint32_t d0 = tmem_base;
+                for (int kb = 0; kb < a.k_blocks; kb++) {
+                    mbar_wait(full_bar + 8 * stage, phase, 2);       // both CTAs' bytes have landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * P_STAGE;
+                    const uint32_t sb = sa + P_A_STAGE;
+#pragma unroll
+                    for (int k = 0; k < P_BK / 32; k++) {
+                        const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+                        const uint32_t ko = (uint32_t)k * 32u;
+                        const uint64_t a_x2 = make_desc<P_BK>(sa + PL_X2 * P_A_PLANE + ko);
+                        const uint64_t a_m = make_desc<P_BK>(sa + PL_M * P_A_PLANE + ko);
+                        const uint64_t a_x = make_desc<P_BK>(sa + PL_X * P_A_PLANE + ko);
+                        const uint64_t b_x2 = make_desc<P_BK>(sb + PL_X2 * P_B_PLANE + ko);
+                        const uint64_t b_m = make_desc<P_BK>(sb + PL_M * P_B_PLANE + ko);
+                        const uint64_t b_x = make_desc<P_BK>(sb + PL_X * P_B_PLANE + ko);
+                        if constexpr (MODE == TC_COSINE) {
+                            umma_i8_2sm(d0 + C_SYY, a_m, b_x2, make_idesc_2sm(P_BN), accum);   // Syy
+                            umma_i8_2sm(d0 + C_B, a_x, b_x, make_idesc_2sm(P_BN), accum);      // Sxy
+                            umma_i8_2sm(d0 + C_C, a_x2, b_m, make_idesc_2sm(P_BN), accum);     // Sxx
+                        } else {
+                            umma_i8_2sm(d0 + C_SYY, a_m, b_x2, make_idesc_2sm(P_BN), accum);   // Syy
+                            umma_i8_2sm(d0 + C_SYY, a_x2, b_m, make_idesc_2sm(P_BN), 1u);      //  += Sxx
+                            umma_i8_2sm(d0 + C_B, a_m, b_m, make_idesc_2sm(P_BN), accum);      // count
+                            umma_i8_2sm(d0 + C_C, a_x, b_x, make_idesc_2sm(P_BN), accum);      // Sxy
+                        }
+                    }
+                    umma_commit_2sm(empty_bar + 8 * stage);          // frees the stage in both CTAs
+                    if (kb == a.k_blocks - 1) umma_commit_2sm(tfull_bar);
+                    if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
+                }
+                acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ======================= epilogue (both CTAs: own 128 TMEM lanes) =======================
+        const int q = warp & 3;
+        const int r_in_tile = q * 32 + lane;
+        uint32_t acc_phase = 0;
+        const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
+        const uint32_t tempty_leader = tempty_bar & PEER_MASK;
+        for (int t = pair_id; t < a.num_tiles; t += n_pairs) {
+            const int2 tile = a.tiles[t];
+            const int64_t i = ((int64_t)tile.x * 2 + rank) * BM + r_in_tile;
+            const int64_t j0 = (int64_t)tile.y * P_BN;
+            mbar_wait(tfull_bar, acc_phase, 3);
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+            const bool row_ok = (i < a.n_left) && (i >= a.row_begin) && (i < a.row_end);
+#pragma unroll 1
+            for (int c0 = 0; c0 < P_BN; c0 += 8) {
+                int32_t v_a[8], v_b[8], v_c[8];
+                tmem_ld8(tbase + C_SYY + c0, v_a);
+                tmem_ld8(tbase + C_B + c0, v_b);
+                tmem_ld8(tbase + C_C + c0, v_c);
+                tmem_ld_wait();
+                double s[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const int64_t j = j0 + c0 + c;
+                    if constexpr (MODE == TC_COSINE) {
+                        // core/sim.go:24  l / (sqrt(m) * sqrt(n)),  m = Sxx, n = Syy, l = Sxy
+                        s[c] = (double)v_b[c] / (sqrt((double)v_c[c]) * sqrt((double)v_a[c]));
+                    } else {
+                        // core/sim.go:43  1 / (sum/count + 1),  sum = (Sxx + Syy) - 2 Sxy (exact integer)
+                        const int32_t sum = v_a[c] - 2 * v_c[c];
+                        s[c] = 1.0 / ((double)sum / (double)v_b[c] + 1.0);
+                    }
+                    if (j == i) s[c] = nan_v;   // diagonal stays unset (core/knn.go:202)
+                }
+                if (row_ok) {
+                    double *o = a.sims + (i - a.row_begin) * a.ld_s + j0 + c0;
+                    if (j0 + c0 + 8 <= a.n_left) {
+#pragma unroll
+                        for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2 *>(o + c) = make_double2(s[c], s[c + 1]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) if (j0 + c0 + c < a.n_left) o[c] = s[c];
+                    }
+                }
+                if (a.mirror && i < a.n_left) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const int64_t j = j0 + c0 + c;
+                        if (j < a.n_left) a.sims[j * a.ld_s + i] = s[c];
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(tempty_leader);    // 2 x 128 arrivals release the accumulators of the pair
+            acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // no CTA leaves while its peer may still read its shared memory / signal it
+    tc_fence_after();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace pair
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -535,14 +800,15 @@ int32_t get_encode_fn(EncodeTiledFn *out) {
 int32_t make_map(const rs_knn *h, int box_k, int box_rows, CUtensorMap *map) {
     EncodeTiledFn enc;
     RS_TRY(get_encode_fn(&enc));
-    const cuuint64_t dims[3] = {(cuuint64_t)h->tc_kpad, (cuuint64_t)h->tc_npad, 3};
-    const cuuint64_t strides[2] = {(cuuint64_t)h->tc_kpad, (cuuint64_t)h->tc_kpad * (cuuint64_t)h->tc_npad};
-    const cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 1};   // one plane per TMA instruction
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->planes, dims, strides, box, estr,
+    // [plane][K / 256][row][256 bytes of K]
+    const cuuint64_t dims[4] = {(cuuint64_t)RS_TC_KBLK, (cuuint64_t)h->tc_npad, (cuuint64_t)(h->tc_kpad / RS_TC_KBLK), 3};
+    const cuuint64_t strides[3] = {(cuuint64_t)RS_TC_KBLK, (cuuint64_t)h->tc_npad * (cuuint64_t)RS_TC_KBLK,
+                                   (cuuint64_t)h->tc_kpad * (cuuint64_t)h->tc_npad};
+    const cuuint32_t box[4] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 1, 1};   // one plane, one K block per instruction
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, h->planes, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         rs_set_error("cuTensorMapEncodeTiled failed with CUresult %d (npad=%lld kpad=%lld)", (int)r,
                      (long long)h->tc_npad, (long long)h->tc_kpad);
@@ -592,6 +858,42 @@ int32_t launch_mode(rs_knn *h, const TcArgs &a) {
     return RS_OK;
 }
 
+template <int MODE>
+int32_t launch_pair(rs_knn *h, const TcArgs &a) {
+    CUtensorMap ma, mb;
+    RS_TRY(make_map(h, pair::P_BK, BM, &ma));
+    RS_TRY(make_map(h, pair::P_BK, pair::P_BN / 2, &mb));
+    auto kern = pair::sim_tensor_pair_kernel<MODE>;
+    RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::P_SMEM));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = pair::P_SMEM;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n_pairs = sms / 2;
+    cfg.gridDim = dim3((unsigned)(n_pairs * 2));
+    int max_clusters = 0;
+    RS_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+    if (max_clusters < 1) {
+        rs_set_error("a CTA pair of the tensor kernel does not fit on this device");
+        return RS_ERR_CUDA;
+    }
+    if (n_pairs > max_clusters) n_pairs = max_clusters;   // persistent: one resident wave
+    if (n_pairs > a.num_tiles) n_pairs = a.num_tiles;
+    cfg.gridDim = dim3((unsigned)(n_pairs * 2));
+    RS_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, a));
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
 template <int CI, int CJ>
 int32_t launch_shape(rs_knn *h, const TcArgs &a, bool cosums) {
     if (cosums) return launch_mode<TC_COSUMS, CI, CJ>(h, a);
@@ -626,8 +928,14 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
     const int64_t plain_tiles = ((re - rb + BM - 1) / BM) * ((h->n_left + BN - 1) / BN) / (mirror ? 2 : 1);
     int ci = (mode == TC_COSINE || mode == TC_MSD) ? 2 : 1, cj = 1;
     if (plain_tiles < 4 * 148) { ci = 1; cj = 1; }
+    // Cosine / MSD on large problems: the cta_group::2 pair kernel (256 x 128 tiles = the 2x1 cluster
+    // tile of the list below).  RS_KNN_TC_PAIR=0|1 overrides.
+    bool use_pair = (mode == TC_COSINE || mode == TC_MSD) && ci == 2 && cj == 1;
+    if (const char *e = getenv("RS_KNN_TC_PAIR")) use_pair = (mode == TC_COSINE || mode == TC_MSD) && atoi(e) != 0;
+    if (use_pair) { ci = 2; cj = 1; }
     if (const char *e = getenv("RS_KNN_TC_CLUSTER")) {
-        if (!strcmp(e, "1x1")) { ci = 1; cj = 1; }
+        if (use_pair) {}
+        else if (!strcmp(e, "1x1")) { ci = 1; cj = 1; }
         else if (!strcmp(e, "1x2")) { ci = 1; cj = 2; }
         else if (!strcmp(e, "2x2")) { ci = 2; cj = 2; }
         else if (!strcmp(e, "2x4")) { ci = 2; cj = 4; }
@@ -698,7 +1006,8 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
     if (const char *e = getenv("RS_KNN_TC_SYNC")) sscanf(e, "%d,%d,%d", &a.sync_chunk, &a.sync_slack, &a.sync_timeout);
     if (a.sync_chunk > 0) RS_CUDA(cudaMemsetAsync(a.progress, 0, 8, h->stream));
     int32_t rc;
-    if (ci == 1 && cj == 1) rc = launch_shape<1, 1>(h, a, cosums);
+    if (use_pair) rc = mode == TC_COSINE ? launch_pair<TC_COSINE>(h, a) : launch_pair<TC_MSD>(h, a);
+    else if (ci == 1 && cj == 1) rc = launch_shape<1, 1>(h, a, cosums);
     else if (ci == 1 && cj == 2) rc = launch_shape<1, 2>(h, a, cosums);
     else if (ci == 1 && cj == 4) rc = launch_shape<1, 4>(h, a, cosums);
     else if (ci == 1 && cj == 8) rc = launch_shape<1, 8>(h, a, cosums);

@@ -42,9 +42,20 @@ def test_cosums_bit_exact(ml100k, user_based):
                 assert np.array_equal(got[r, c].astype(np.int64), want), (row0 + r, int(c))
 
 
+# kernel variants: the single-CTA kernel (small problems), 2x1 / 1x2 multicast clusters, and the
+# cta_group::2 CTA-pair kernel (the default on large Cosine / MSD problems) — forced here on ml-100k
+VARIANTS = {"single": {"RS_KNN_TC_PAIR": "0", "RS_KNN_TC_CLUSTER": "1x1"},
+            "cluster2x1": {"RS_KNN_TC_PAIR": "0", "RS_KNN_TC_CLUSTER": "2x1"},
+            "cluster1x2": {"RS_KNN_TC_PAIR": "0", "RS_KNN_TC_CLUSTER": "1x2"},
+            "pair": {"RS_KNN_TC_PAIR": "1"}}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
 @pytest.mark.parametrize("user_based", [True, False])
 @pytest.mark.parametrize("sim", ["cosine", "msd"])
-def test_tensor_sims_bit_exact(ml100k, sim, user_based):
+def test_tensor_sims_bit_exact(ml100k, sim, user_based, variant, monkeypatch):
+    for k, v in VARIANTS[variant].items():
+        monkeypatch.setenv(k, v)
     est, ref, _ = _fit(ml100k["u1_base"], sim, user_based)
     assert est.Profile()["sim_path_used"] == rs.core.RS_SIM_PATH["tensor"]
     got, want = est.Sims, ref.sims()
@@ -69,9 +80,11 @@ def test_tensor_predict_bit_exact(ml100k):
     assert bits_equal(est.PredictBatch(u, i), ref.predict_batch(u, i, n_threads=8))
 
 
-def test_tensor_row_shard(ml100k):
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_tensor_row_shard(ml100k, pair, monkeypatch):
     from recommend_sys_b200.shard import shard_rows
 
+    monkeypatch.setenv("RS_KNN_TC_PAIR", pair)
     u, i, r = split(ml100k["u1_base"])
     ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
     full = rs.NewKNN(rs.Parameters({"sim": rs.MSD, "userBased": False, "simPath": "tensor"}))
@@ -106,7 +119,9 @@ def test_tensor_rejects_non_integer_ratings():
     h.close()
 
 
-def test_tensor_tiny_and_odd_shapes():
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_tensor_tiny_and_odd_shapes(pair, monkeypatch):
+    monkeypatch.setenv("RS_KNN_TC_PAIR", pair)
     rng = np.random.RandomState(5)
     for n_users, n_items, nnz in ((3, 5, 9), (130, 70, 2000), (257, 129, 5000)):
         cells = rng.choice(n_users * n_items, nnz, replace=False)
