@@ -106,6 +106,7 @@ struct rs_knn {
     int32_t n_chunks = 0;
     int32_t stream_jc = 256;
     int64_t *l2r = nullptr;
+    int32_t *perm_lr = nullptr, *perm_rl = nullptr, *perm_tmp = nullptr;  // CSR position -> input row (arena, valid until the next Fit)
     int32_t *row_order = nullptr;  // left rows sorted by descending length
     // int8 planes X^2, M, X of the left matrix, [3][k_pad / 256][n_pad][256] (tensor path)
     int8_t *planes = nullptr;

@@ -238,22 +238,17 @@ __global__ void build_cp_kernel(const int64_t *__restrict__ r_ptr, const int32_t
     cp[t] = (int32_t)(lo - b);
 }
 
-// l2r[e] for the left-CSR entry e = (i, c): position of (c, i) in the right CSR
-__global__ void build_l2r_kernel(const int64_t *__restrict__ l_ptr, const int32_t *__restrict__ l_col,
-                                 const int64_t *__restrict__ r_ptr, const int32_t *__restrict__ r_col,
-                                 int32_t n_right, int64_t *__restrict__ l2r) {
-    const int32_t c = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    if (c >= n_right) return;
-    for (int64_t x = r_ptr[c] + lane; x < r_ptr[c + 1]; x += 32) {
-        const int32_t j = r_col[x];
-        int64_t lo = l_ptr[j], hi = l_ptr[j + 1];
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (l_col[mid] < c) lo = mid + 1; else hi = mid;
-        }
-        l2r[lo] = x;
-    }
+// l2r[e] for the left-CSR entry e = (i, c): position of (c, i) in the right CSR.  Both CSRs are
+// permutations of the input rows (perm_lr[e] / perm_rl[x] = original row index), so
+// l2r = inverse(perm_rl) o perm_lr: one scatter and one gather, no search.
+__global__ void invert_perm_kernel(const int32_t *__restrict__ perm, int64_t n, int32_t *__restrict__ inv) {
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < n) inv[perm[x]] = (int32_t)x;
+}
+__global__ void compose_l2r_kernel(const int32_t *__restrict__ perm_lr, const int32_t *__restrict__ inv_rl, int64_t n,
+                                   int64_t *__restrict__ l2r) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) l2r[e] = inv_rl[perm_lr[e]];
 }
 
 
@@ -362,16 +357,22 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     h->rating_class = (flags & FLAG_NOT_INT8) ? RS_CLASS_TABLE : RS_CLASS_INT8;
 
     const int lb = bits_for(nl), rb = bits_for(nr);
-    // stable LSD sorts: perm_l = by left (dataset order inside a row), perm_r = by right
-    RS_SORT_PAIRS(d_left, keys_a, idx, perm_l, nnz, lb);
+    // stable LSD sorts: perm_l = by left (dataset order inside a row) — only needed when row
+    // statistics must be summed in dataset order (non-integer ratings, or z-score's stddevs; integer
+    // means are exact in any order) —, perm_r = by right
+    const bool need_dataset_order = h->rating_class != RS_CLASS_INT8 || h->p.knn_type == RS_KNN_ZSCORE;
+    if (need_dataset_order) RS_SORT_PAIRS(d_left, keys_a, idx, perm_l, nnz, lb);
     RS_SORT_PAIRS(d_right, keys_a, idx, perm_r, nnz, rb);
     // (left, right asc): stable sort by left of the right-sorted sequence
     gather_keys_kernel<<<blocks_for(nnz), T, 0, st>>>(d_left, perm_r, nnz, keys_a);
     RS_SORT_PAIRS(keys_a, keys_b, perm_r, perm_lr, nnz, lb);
-    // (right, left asc)
-    gather_keys_kernel<<<blocks_for(nnz), T, 0, st>>>(d_right, perm_l, nnz, keys_a);
-    RS_SORT_PAIRS(keys_a, keys_b, perm_l, perm_rl, nnz, rb);
+    // (right, left asc): stable sort by right of the (left, right asc) sequence
+    gather_keys_kernel<<<blocks_for(nnz), T, 0, st>>>(d_right, perm_lr, nnz, keys_a);
+    RS_SORT_PAIRS(keys_a, keys_b, perm_lr, perm_rl, nnz, rb);
     h->prof.total_launches += 2;  // own kernels only; CUB's sort/scan kernels are not counted
+    h->perm_lr = perm_lr;         // kept for the stream tables (rs_prep_rt); keys_b is free from here on
+    h->perm_rl = perm_rl;
+    h->perm_tmp = keys_b;
 
     // row pointers
     RS_TRY(rs_alloc(h, &h->l_ptr, (size_t)nl + 1));
@@ -400,8 +401,8 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
                                                     h->d_flags);
     gather_csr_kernel<<<blocks_for(nnz), T, 0, st>>>(perm_rl, d_right, d_left, d_rating, nnz, h->r_col, h->r_val,
                                                     nullptr);
-    gather_val_kernel<<<blocks_for(nnz), T, 0, st>>>(perm_l, d_rating, nnz, h->ld_val);
-    h->prof.total_launches += 3;
+    if (need_dataset_order) gather_val_kernel<<<blocks_for(nnz), T, 0, st>>>(perm_l, d_rating, nnz, h->ld_val);
+    h->prof.total_launches += need_dataset_order ? 3 : 2;
 
     // rating codes + value table
     RS_TRY(rs_alloc(h, &h->lut, 256));
@@ -489,9 +490,9 @@ int32_t rs_prep_rt(rs_knn *h) {
         h->r_dev);
     build_cp_kernel<<<blocks_for((int64_t)h->n_right * (h->n_chunks + 1)), T, 0, st>>>(
         h->r_ptr, h->r_col, h->n_right, h->n_chunks, h->stream_jc, h->cp);
-    build_l2r_kernel<<<blocks_for((int64_t)h->n_right * 32), T, 0, st>>>(h->l_ptr, h->l_col, h->r_ptr, h->r_col,
-                                                                        h->n_right, h->l2r);
-    h->prof.total_launches += 3;
+    invert_perm_kernel<<<blocks_for(h->nnz), T, 0, st>>>(h->perm_rl, h->nnz, h->perm_tmp);
+    compose_l2r_kernel<<<blocks_for(h->nnz), T, 0, st>>>(h->perm_lr, h->perm_tmp, h->nnz, h->l2r);
+    h->prof.total_launches += 4;
     // rows of every possible shard ordered longest first: a stable descending sort of the row
     // lengths inside the shard keeps the order deterministic
     {
