@@ -126,6 +126,8 @@ def host_lib():
     L.rs_host_synth_ratings.restype = C.c_int64
     L.rs_host_synth_ratings.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p,
                                         C.c_void_p]
+    L.rs_host_convert_dense.restype = None
+    L.rs_host_convert_dense.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     _host_lib = L
     return L
 
@@ -358,11 +360,8 @@ def _convert(table, raw):
     raw = np.ascontiguousarray(raw, dtype=np.int64)
     if table[0] == "dense":
         dense = table[1]
-        ok = (raw >= 0) & (raw < len(dense) - 1)
-        if ok.all():
-            return dense[raw]
-        out = np.full(len(raw), newID, dtype=np.int32)
-        out[ok] = dense[raw[ok]]
+        out = np.empty(len(raw), dtype=np.int32)
+        host_lib().rs_host_convert_dense(_ptr(dense), len(dense) - 1, _ptr(raw), len(raw), _ptr(out))
         return out
     _, uniq, inner = table
     pos = np.clip(np.searchsorted(uniq, raw), 0, len(uniq) - 1)

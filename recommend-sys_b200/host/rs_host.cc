@@ -147,4 +147,11 @@ int64_t rs_host_synth_ratings(int32_t n_users, int32_t n_items, int64_t nnz_targ
     return w;
 }
 
+void rs_host_convert_dense(const int32_t *table, int64_t n_table, const int64_t *raw, int64_t n, int32_t *inner_out) {
+    for (int64_t x = 0; x < n; x++) {
+        const int64_t r = raw[x];
+        inner_out[x] = (r >= 0 && r < n_table) ? table[r] : -1;     // -1 = newID (core/data.go:129)
+    }
+}
+
 }  // extern "C"

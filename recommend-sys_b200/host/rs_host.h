@@ -23,6 +23,10 @@ void rs_host_baseline_sgd(const int32_t *inner_user, const int32_t *inner_item, 
                           int64_t n, int32_t n_users, int32_t n_items, double reg, double lr,
                           int32_t n_epochs, double *user_bias, double *item_bias, double *global_bias);
 
+/* Batch ConvertUserID / ConvertItemID (core/data.go:157-183) through a dense raw -> inner table
+ * (table[raw] = inner id or -1; raw ids outside [0, n_table) are new ids = -1). */
+void rs_host_convert_dense(const int32_t *table, int64_t n_table, const int64_t *raw, int64_t n, int32_t *inner_out);
+
 /* Deterministic synthetic rating matrices of the BASELINE.json shapes:
  * unique (user,item) pairs, heavy-tailed degrees, integer ratings 1..5 with a MovieLens-like
  * marginal, rows emitted in a seeded shuffled order.  Returns the number of ratings written
