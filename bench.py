@@ -392,7 +392,9 @@ def run_ours(args, rank, world, local_rank):
         roof = {"bound": "tensor", "achieved": ops / (sim_step_ms / 1e3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                 "frac": ops / (sim_step_ms / 1e3) / 1e12 / tpeak, "traffic": None,
                 "peak_source": f"2 x {peak_src} bf16 burst (int8 is not in MEASURED_PEAKS.json)",
-                "kernel": "sim_tensor_kernel", "ms_per_launch": sim_launch_ms,
+                "kernel": ("sim_tensor_pair_kernel" if sim in ("cosine", "msd") and
+                           (n_left / 128.0) * (n_left / 128.0) / 2 >= 4 * 148 else "sim_tensor_kernel"),
+                "ms_per_launch": sim_launch_ms,
                 "launches_per_step": launches_per_step,
                 "note": ("algorithmic int8 ops of the rank's unordered pairs / time of all similarity launches of "
                          "one Fit" + ("; a row shard computes full rows (2x the algorithmic ops) and the time "
