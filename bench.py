@@ -235,7 +235,7 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
 
     import recommend_sys_b200 as rs
-    from recommend_sys_b200.shard import allgather_topk, shard_rows
+    from recommend_sys_b200.shard import allgather_partial_topk, allgather_topk, shard_rows, union_topk_device
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback "
@@ -243,8 +243,12 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     users, items, nnz, n_test, sim, knn_type, user_based, k = WORKLOADS[args.workload]
-    shard = args.shard_rows and world > 1
-    train, test = make_data(args.workload, fold=0 if shard else rank)
+    # top-k-only workloads (config 4: no test set, the N x N matrix would not fit) run as SYMMETRIC
+    # SLABS: every pair is computed once, the slabs are dealt round-robin over the ranks, and one
+    # all-gather + union assembles the neighbour lists (also the single-GPU form of this workload)
+    sym = n_test == 0
+    shard = (args.shard_rows and world > 1) and not sym
+    train, test = make_data(args.workload, fold=0 if (shard or sym) else rank)
     n_left = train.UserCount if user_based else train.ItemCount
     n_right = train.ItemCount if user_based else train.UserCount
     left = train.innerUsers if user_based else train.innerItems
@@ -262,7 +266,8 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.Stream(device=dev)   # a dedicated (non-default) stream for the whole bench
     torch.cuda.set_stream(stream)
     h = rs.core._Handle(sim=sim, knn_type=knn_type, k=k, device=local_rank, row_begin=rb, row_end=re,
-                        store="topk" if (shard and not n_test) else "matrix", topk=k,
+                        store="topk" if sym else "matrix", topk=k,
+                        shard_count=world if sym else 0, shard_index=rank if sym else 0,
                         pearson_mode=args.pearson_mode, sim_path=args.sim_path)
     h.set_stream(stream.cuda_stream)
 
@@ -287,8 +292,8 @@ def run_ours(args, rank, world, local_rank):
     d_tr = torch.from_numpy(t_right).to(dev) if n_pred else None
     d_out = torch.empty(max(1, n_pred), dtype=torch.float64, device=dev)
     rows_local = (re - rb) if shard else n_left
-    d_tk_i = torch.empty((rows_local, k), dtype=torch.int32, device=dev) if shard else None
-    d_tk_s = torch.empty((rows_local, k), dtype=torch.float64, device=dev) if shard else None
+    d_tk_i = torch.empty((rows_local, k), dtype=torch.int32, device=dev) if (shard or sym) else None
+    d_tk_s = torch.empty((rows_local, k), dtype=torch.float64, device=dev) if (shard or sym) else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step_device():
@@ -300,6 +305,11 @@ def run_ours(args, rank, world, local_rank):
         if shard:
             h.topk_device(k, d_tk_i.data_ptr(), d_tk_s.data_ptr())
             allgather_topk(d_tk_i, d_tk_s, n_left, k)
+        if sym:
+            h.topk_device(k, d_tk_i.data_ptr(), d_tk_s.data_ptr())
+            if world > 1:
+                return union_topk_device(*allgather_partial_topk(d_tk_i, d_tk_s))
+            return d_tk_i, d_tk_s
 
     def barrier():
         if world > 1:
@@ -340,6 +350,8 @@ def run_ours(args, rank, world, local_rank):
         params["baseline"] = "als"      # device ALS baselines inside the timed e2e Fit
     if shard:
         params.update({"rowBegin": rb, "rowEnd": re})
+    if sym:
+        params.update({"store": "topk", "topk": k, "shardCount": world, "shardIndex": rank})
     e2e_test = test
     if shard and n_test:
         e2e_test = test.SubSet(np.where(mine)[0])
@@ -348,6 +360,10 @@ def run_ours(args, rank, world, local_rank):
         est = ctor(rs.Parameters(params))
         est.Fit(train)
         out = e2e_test.Predict(est) if n_test else None
+        if sym:     # the result of a top-k-only Fit is the neighbour lists: united across ranks, read to the host
+            est._h.topk_device(k, d_tk_i.data_ptr(), d_tk_s.data_ptr())
+            li, ls = (union_topk_device(*allgather_partial_topk(d_tk_i, d_tk_s)) if world > 1 else (d_tk_i, d_tk_s))
+            out = (li.cpu(), ls.cpu())
         est.Close()
         return out
 
@@ -362,6 +378,8 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- reduce over ranks: max time, summed units ----
     pairs_rank = n_left * (n_left - 1) / 2 if not shard else (re - rb) * (n_left - 1) / 2.0
+    if sym:
+        pairs_rank = n_left * (n_left - 1) / 2.0 / world      # every pair once, slabs dealt round-robin
     red = torch.tensor([total_ms, e2e_s, prof["sim_kernel_ms"], prof["predict_kernel_ms"]], dtype=torch.float64,
                        device=dev)
     units = torch.tensor([pairs_rank, float(n_pred)], dtype=torch.float64, device=dev)
@@ -398,7 +416,8 @@ def run_ours(args, rank, world, local_rank):
                 "launches_per_step": launches_per_step,
                 "note": ("algorithmic int8 ops of the rank's unordered pairs / time of all similarity launches of "
                          "one Fit" + ("; a row shard computes full rows (2x the algorithmic ops) and the time "
-                                      "includes the per-slab top-k selection" if shard else ""))}
+                                      "includes the per-slab top-k selection" if shard else
+                                      "; includes the per-slab transpose and top-k merges" if sym else ""))}
     else:
         emitted = pairs_rank + n_left * 512  # block-triangle incl. the diagonal chunks
         alg_bytes = len(left) * 12 + emitted * 8
@@ -421,18 +440,22 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": "similarity_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong" if shard else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong" if (shard or (sym and world > 1)) else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "predictions_per_sec": preds_all / (ms_per_step / 1e3),
         "config": {"workload": args.workload, "shape": f"{users}x{items}", "train_ratings": train.Length(),
                    "test_pairs": int(preds_all), "sim": sim, "knn_type": knn_type, "user_based": user_based, "k": k,
                    "tie_policy": "canonical", "pearson_mode": args.pearson_mode,
                    "sim_path": {0: "auto", 1: "tensor", 2: "stream"}[prof["sim_path_used"]],
                    "l2": "flushed between timed iterations (256 MiB write)",
-                   "parallelism": ("row-sharded + NCCL all-gather of neighbour lists" if shard
+                   "parallelism": ("symmetric slabs dealt round-robin + NCCL all-gather and union of partial "
+                                   "neighbour lists" if (sym and world > 1) else
+                                   "symmetric slabs, single GPU" if sym else
+                                   "row-sharded + NCCL all-gather of neighbour lists" if shard
                                    else ("one fold per GPU, no collective" if world > 1 else "single GPU"))},
         "clocks": clock_info,
         "e2e": {"value": pairs_all / e2e_s, "unit": "pairs/s", "ms_per_step": e2e_s * 1e3,
-                "h2d_bytes_per_step": int(len(left) * 16 + n_pred * 8), "d2h_bytes_per_step": int(n_pred * 8),
+                "h2d_bytes_per_step": int(len(left) * 16 + n_pred * 8),
+                "d2h_bytes_per_step": int(n_pred * 8 + (n_left * k * 12 if sym else 0)),
                 "predictions_per_sec": preds_all / e2e_s, "steps": e2e_steps},
         "gpu_launches": int(prof["total_launches"]),
         "kernel_ms": {"sim": sim_ms / args.steps, "predict": pred_ms / args.steps, "prep": prof["prep_ms"] / args.steps},

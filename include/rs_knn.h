@@ -80,6 +80,15 @@ typedef struct rs_knn_params {
     int64_t row_begin;    /* shard of left rows this handle owns: [row_begin,row_end);    */
     int64_t row_end;      /*   0,0 = all rows.  One handle per GPU when row-sharding.     */
     double shrinkage;     /* PearsonBaseline extension: (n-1)/(n-1+shrinkage), 0 = off    */
+    int32_t shard_count;  /* RS_STORE_TOPK only.  0 (default): the handle computes the full rows of */
+    int32_t shard_index;  /*   [row_begin,row_end) and keeps their lists.  >= 1: SYMMETRIC SLABS — the */
+                          /*   left rows are cut into slabs, the handle computes the slabs           */
+                          /*   shard_index, shard_index + shard_count, ... and of each only the part  */
+                          /*   right of the diagonal; every pair {i,j} it computes feeds the list of  */
+                          /*   row i AND of row j, so no pair is computed twice (half the work) and  */
+                          /*   the handle holds PARTIAL lists for ALL n_left rows: complete when      */
+                          /*   shard_count == 1, else to be united across the shard_count handles     */
+                          /*   with rs_knn_topk_union_device after an all-gather.                      */
 } rs_knn_params;
 
 /* Per-handle counters since creation / the last rs_knn_profile_reset: device time of the
@@ -181,6 +190,13 @@ int32_t rs_knn_stddevs(rs_knn *h, double *out);
 int32_t rs_baseline_als(int32_t device, const int32_t *users, const int32_t *items, const double *ratings,
                         int64_t nnz, int32_t n_users, int32_t n_items, double global_mean, double reg_u,
                         double reg_i, int32_t n_epochs, double *user_bias, double *item_bias);
+
+/* Unites the partial neighbour lists of `n_lists` shards (device pointers, layout
+ * [n_lists][n_rows][k], idx -1 = empty) into the final top-k lists [n_rows][k] (similarity desc, id
+ * asc), on `cuda_stream`.  Every (row, neighbour) pair must occur in at most one partial list —
+ * which is what symmetric-slab handles (shard_count >= 1) produce.  n_lists * k <= 2048. */
+int32_t rs_knn_topk_union_device(int32_t n_lists, int64_t n_rows, int32_t k, const int32_t *d_idx_all,
+                                 const double *d_sim_all, int32_t *d_idx, double *d_sim, void *cuda_stream);
 
 int32_t rs_knn_profile_get(rs_knn *h, rs_knn_profile *out);
 int32_t rs_knn_profile_reset(rs_knn *h);

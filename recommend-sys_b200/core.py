@@ -50,7 +50,8 @@ class RsKnnParams(C.Structure):
     _fields_ = [("sim", C.c_int32), ("knn_type", C.c_int32), ("k", C.c_int32), ("min_k", C.c_int32),
                 ("device", C.c_int32), ("pearson_mode", C.c_int32), ("sim_path", C.c_int32),
                 ("store", C.c_int32), ("topk", C.c_int32), ("reserved0", C.c_int32),
-                ("row_begin", C.c_int64), ("row_end", C.c_int64), ("shrinkage", C.c_double)]
+                ("row_begin", C.c_int64), ("row_end", C.c_int64), ("shrinkage", C.c_double),
+                ("shard_count", C.c_int32), ("shard_index", C.c_int32)]
 
 
 class RsKnnProfile(C.Structure):
@@ -65,6 +66,7 @@ ABI_SYMBOLS = [
     "rs_knn_predict_batch_device", "rs_knn_predict_neighbors", "rs_knn_sims_rows", "rs_knn_topk",
     "rs_knn_topk_device", "rs_knn_cosums", "rs_knn_means", "rs_knn_stddevs", "rs_knn_profile_get",
     "rs_knn_profile_reset", "rs_knn_synchronize", "rs_knn_trim_cache", "rs_baseline_als",
+    "rs_knn_topk_union_device",
 ]
 
 _knn_lib = None
@@ -106,6 +108,7 @@ def knn_lib():
         if name != "rs_last_error":
             getattr(L, name).restype = i32
     L.rs_baseline_als.argtypes = [i32, vp, vp, vp, i64, i32, i32, dbl, dbl, dbl, i32, vp, vp]
+    L.rs_knn_topk_union_device.argtypes = [i32, i64, i32, vp, vp, vp, vp, vp]
     _knn_lib = L
     return L
 
@@ -399,13 +402,15 @@ class _Handle:
     """Thin RAII wrapper of rs_knn* (in Go: an unexported field + Close()/finalizer)."""
 
     def __init__(self, sim="msd", knn_type="basic", k=40, min_k=1, device=-1, pearson_mode="exact",
-                 sim_path="auto", store="matrix", topk=0, row_begin=0, row_end=0, shrinkage=0.0):
+                 sim_path="auto", store="matrix", topk=0, row_begin=0, row_end=0, shrinkage=0.0,
+                 shard_count=0, shard_index=0):
         L = knn_lib()
         p = RsKnnParams()
         _check(L.rs_knn_params_default(C.byref(p)))
         p.sim, p.knn_type, p.k, p.min_k, p.device = RS_SIM[sim], RS_KNN_TYPE[knn_type], k, min_k, device
         p.pearson_mode, p.sim_path, p.store = RS_PEARSON_MODE[pearson_mode], RS_SIM_PATH[sim_path], RS_STORE[store]
         p.topk, p.row_begin, p.row_end, p.shrinkage = topk or k, row_begin, row_end, shrinkage
+        p.shard_count, p.shard_index = shard_count, shard_index
         self.params = p
         self.h = C.c_void_p()
         _check(L.rs_knn_create(C.byref(p), C.byref(self.h)))
@@ -580,7 +585,7 @@ class KNN(Base):
 
     # extra Parameters keys understood by the device path (SURVEY.md §5 "Config / flags")
     _DEVICE_KEYS = ("device", "pearsonMode", "simPath", "store", "topk", "rowBegin", "rowEnd", "shrinkage",
-                    "baseline", "regU", "regI")
+                    "baseline", "regU", "regI", "shardCount", "shardIndex")
 
     def __init__(self, knn_type, params=None):
         super().__init__(params)
@@ -632,7 +637,9 @@ class KNN(Base):
                           store=self.Params.GetString("store", "matrix"),
                           topk=self.Params.GetInt("topk", 0),
                           row_begin=self.Params.GetInt("rowBegin", 0), row_end=self.Params.GetInt("rowEnd", 0),
-                          shrinkage=self.Params.GetFloat64("shrinkage", 0.0))
+                          shrinkage=self.Params.GetFloat64("shrinkage", 0.0),
+                          shard_count=self.Params.GetInt("shardCount", 0),
+                          shard_index=self.Params.GetInt("shardIndex", 0))
         self._h.fit(left, right, trainSet.Ratings, n_left, n_right, trainSet.GlobalMean, left_bias, right_bias,
                     global_bias)
         self._userBased = userBased

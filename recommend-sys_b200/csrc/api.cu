@@ -239,6 +239,14 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
         return RS_ERR_INVALID;
     }
     const int64_t rows = h->row_end - h->row_begin;
+    if (h->p.shard_count < 0 || (h->p.shard_count >= 1 && (h->p.shard_index < 0 || h->p.shard_index >= h->p.shard_count))) {
+        rs_set_error("shard_index %d outside [0, shard_count=%d)", h->p.shard_index, h->p.shard_count);
+        return RS_ERR_INVALID;
+    }
+    if (h->p.shard_count >= 1 && (h->p.store != RS_STORE_TOPK || rows != n_left)) {
+        rs_set_error("symmetric slabs (shard_count >= 1) need RS_STORE_TOPK and no row_begin/row_end");
+        return RS_ERR_INVALID;
+    }
 
     RS_CUDA(cudaEventRecord(h->ev_a, h->stream));
     int32_t rc = rs_prep_build(h, d_left, d_right, d_rating, d_left_bias, d_right_bias);
@@ -272,6 +280,53 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
             rc = rs_symmetrize_launch(h);
             if (rc != RS_OK) { free_fit_state(h); return rc; }
         }
+    } else if (h->p.shard_count >= 1) {
+        // top-k only, SYMMETRIC SLABS (see rs_knn_params::shard_count): slab s = rows [s*m, s*m+m);
+        // of each slab only the part right of the diagonal is computed, the slab feeds the lists of
+        // its own rows, its transpose the lists of the rows below it.  Half the similarity work of
+        // full rows, and the slabs of a multi-GPU job are dealt round-robin so every rank gets the
+        // same share of the triangle.
+        const int32_t k = h->p.topk > 0 ? h->p.topk : h->p.k;
+        const int64_t n = n_left;
+        int64_t m = (int64_t)(6ll << 30) / (h->ld_s * 8);        // ~6 GiB slab + the same for its transpose
+        if (const char *e = getenv("RS_KNN_SLAB_ROWS")) m = atoll(e);   // tests: many slabs on a small matrix
+        if (m < 256) m = 256;
+        m = m / 256 * 256;
+        if (m > n) m = (n + 15) / 16 * 16;
+        const int64_t ld_t = m;
+        double *tbuf = nullptr;
+        RS_TRY(rs_alloc(h, &h->sims, (size_t)m * (size_t)h->ld_s));
+        RS_TRY(rs_alloc(h, &tbuf, (size_t)n * (size_t)ld_t));
+        RS_TRY(rs_alloc(h, &h->topk_idx, (size_t)n * k));
+        RS_TRY(rs_alloc(h, &h->topk_sim, (size_t)n * k));
+        h->topk_rows = n;
+        RS_CUDA(cudaMemsetAsync(h->topk_idx, 0xFF, (size_t)n * k * 4, h->stream));   // -1 = empty
+        RS_CUDA(cudaMemsetAsync(h->topk_sim, 0xFF, (size_t)n * k * 8, h->stream));   // NaN
+        RS_CUDA(cudaEventRecord(h->ev_b, h->stream));
+        const int64_t n_slabs = (n + m - 1) / m;
+        h->force_sym = true;
+        for (int64_t sl = h->p.shard_index; sl < n_slabs; sl += h->p.shard_count) {
+            const int64_t r0 = sl * m, r1 = r0 + m < n ? r0 + m : n;
+            h->row_begin = r0;
+            h->row_end = r1;
+            h->col_begin = r0;
+            if (path == RS_PATH_STREAM) {
+                // the stream kernel skips whole column chunks left of the diagonal: unset = NaN
+                rc = cudaMemsetAsync(h->sims, 0xFF, (size_t)(r1 - r0) * (size_t)h->ld_s * 8, h->stream) == cudaSuccess
+                         ? RS_OK : RS_ERR_CUDA;
+                if (rc == RS_OK) rc = rs_sim_stream_launch(h);
+            } else {
+                rc = rs_sim_tensor_launch(h, nullptr, 0, 0);
+            }
+            if (rc == RS_OK) rc = rs_topk_slab_launch(h, r0, (int32_t)(r1 - r0), tbuf, ld_t, k);
+            if (rc != RS_OK) break;
+        }
+        h->force_sym = false;
+        h->col_begin = 0;
+        h->row_begin = 0;
+        h->row_end = n;
+        if (rc != RS_OK) { free_fit_state(h); return rc; }
+        RS_CUDA(cudaEventRecord(h->ev_c, h->stream));
     } else {
         // top-k only: similarity rows are produced slab by slab and reduced to neighbour
         // lists; the N x N matrix never exists in HBM.
@@ -283,6 +338,7 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
         RS_TRY(rs_alloc(h, &h->sims, (size_t)slab * (size_t)h->ld_s));
         RS_TRY(rs_alloc(h, &h->topk_idx, (size_t)rows * k));
         RS_TRY(rs_alloc(h, &h->topk_sim, (size_t)rows * k));
+        h->topk_rows = rows;
         RS_CUDA(cudaEventRecord(h->ev_b, h->stream));
         const int64_t rb = h->row_begin, re = h->row_end;
         for (int64_t r0 = rb; r0 < re; r0 += slab) {
@@ -465,7 +521,7 @@ int32_t rs_knn_topk_device(rs_knn *h, int32_t k, int32_t *d_idx, double *d_sim) 
         rs_set_error("rs_knn_topk: not fitted or null argument");
         return RS_ERR_INVALID;
     }
-    const int64_t rows = h->row_end - h->row_begin;
+    const int64_t rows = h->p.store == RS_STORE_TOPK ? h->topk_rows : h->row_end - h->row_begin;
     if (h->p.store == RS_STORE_TOPK) {
         const int32_t kk = h->p.topk > 0 ? h->p.topk : h->p.k;
         if (k != kk) {
@@ -485,7 +541,7 @@ int32_t rs_knn_topk(rs_knn *h, int32_t k, int32_t *idx, double *sim) {
         rs_set_error("rs_knn_topk: not fitted or bad argument");
         return RS_ERR_INVALID;
     }
-    const int64_t rows = h->row_end - h->row_begin;
+    const int64_t rows = h->p.store == RS_STORE_TOPK ? h->topk_rows : h->row_end - h->row_begin;
     void *di, *ds;
     RS_TRY(rs_scratch_get(h, 3, (size_t)rows * k * 4, &di));
     RS_TRY(rs_scratch_get(h, 4, (size_t)rows * k * 8, &ds));

@@ -62,6 +62,9 @@ struct rs_knn {
     int32_t n_left = 0, n_right = 0;
     int64_t nnz = 0;
     int64_t row_begin = 0, row_end = 0;  // resolved shard
+    int64_t col_begin = 0;               // symmetric slabs: similarity tiles left of this column are not needed
+    bool force_sym = false;              // symmetric slabs: compute only j > i although the rows are a slab
+    int64_t topk_rows = 0;               // rows covered by topk_idx / topk_sim
     double global_mean = 0.0, global_bias = 0.0;
     int rating_class = RS_CLASS_INT8;
     int n_codes = 0;
@@ -74,7 +77,7 @@ struct rs_knn {
     // cached tensor-path tile list
     void *tile_buf = nullptr;
     size_t tile_buf_bytes = 0;
-    int64_t tile_key[4] = {-1, -1, -1, -1};
+    int64_t tile_key[5] = {-1, -1, -1, -1, -1};
     int32_t tile_count = 0;
 
     // CSR of the left rows, entries ascending by right id (core/data.go:236-243)
@@ -158,6 +161,7 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
 int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_right, int64_t n, double *d_out,
                           int32_t *d_nb_ids, double *d_nb_sims, int32_t *d_nb_count, int32_t nb_cap);
 int32_t rs_topk_launch(rs_knn *h, int32_t k, int32_t *d_idx, double *d_sim);
+int32_t rs_topk_slab_launch(rs_knn *h, int64_t g0, int32_t m, double *tbuf, int64_t ld_t, int32_t k);
 
 // order-preserving map double -> uint64 (larger similarity = larger key); -0.0 folded to +0.0
 __host__ __device__ inline uint64_t rs_sim_key(double s) {

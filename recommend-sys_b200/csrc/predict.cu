@@ -432,6 +432,142 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_rows_kernel(const double *_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Symmetric top-k slabs (RS_STORE_TOPK with shard_count >= 1).  A slab holds the rows
+// [g0, g0+m) of the similarity matrix, of which only the entries right of the diagonal are used;
+// each unordered pair {i, j} therefore feeds TWO neighbour lists: row i (through the slab) and row j
+// (through the slab's transpose), and no pair is computed twice.
+//   mode 0: src = slab,      block r <-> global row g0 + r, columns (g, n_cols), id = column
+//   mode 1: src = transpose, block r <-> global row g0 + r, columns [0, min(m, r)), id = g0 + column
+// The running list of the row (k entries, -1 = empty) is merged in: it seeds the candidate buffer.
+__global__ void __launch_bounds__(TOPK_THREADS) topk_merge_kernel(const double *__restrict__ src, int64_t ld,
+                                                                  int64_t g0, int32_t n_cols, int32_t m, int mode,
+                                                                  int32_t k, int32_t *__restrict__ idx,
+                                                                  double *__restrict__ sim) {
+    __shared__ uint64_t keys[TOPK_CAP];
+    __shared__ uint32_t pos[TOPK_CAP];
+    __shared__ int s_have;
+    __shared__ uint64_t s_thr_key;
+    __shared__ uint32_t s_thr_pos;
+    const int64_t r = blockIdx.x;
+    const int64_t g = g0 + r;
+    const double *row = src + r * ld;
+    int32_t clo, chi;
+    uint32_t id_off;
+    if (mode == 0) { clo = (int32_t)g + 1; chi = n_cols; id_off = 0; }
+    else { clo = 0; chi = r < m ? (int32_t)r : m; id_off = (uint32_t)g0; }
+    if (chi <= clo) return;                                   // nothing new for this row: the list stays
+    if (threadIdx.x == 0) { s_have = 0; s_thr_key = 0; s_thr_pos = 0xffffffffu; }
+    __syncthreads();
+    // seed with the running list; it is stored best first, so a FULL list gives the threshold right
+    // away (its last entry): almost every new candidate of a later slab is rejected by one compare
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const int32_t id = idx[g * k + t];
+        if (id >= 0) {
+            const int slot = atomicAdd(&s_have, 1);
+            keys[slot] = rs_sim_key(sim[g * k + t]);
+            pos[slot] = (uint32_t)id;
+        }
+    }
+    bool have_thr = idx[g * k + (k - 1)] >= 0;
+    if (have_thr && threadIdx.x == 0) {
+        s_thr_key = rs_sim_key(sim[g * k + (k - 1)]);
+        s_thr_pos = (uint32_t)idx[g * k + (k - 1)];
+    }
+    __syncthreads();
+    for (int32_t base = clo; base < chi; base += TOPK_THREADS) {
+        const int32_t j = base + threadIdx.x;
+        bool take = false;
+        uint64_t key = 0;
+        if (j < chi) {
+            const double s = row[j];
+            if (s == s) {
+                key = rs_sim_key(s);
+                take = !have_thr || rec_before(key, (uint32_t)j + id_off, s_thr_key, s_thr_pos);
+            }
+        }
+        if (take) {
+            int slot = atomicAdd(&s_have, 1);
+            keys[slot] = key;
+            pos[slot] = (uint32_t)j + id_off;
+        }
+        __syncthreads();
+        if (s_have > TOPK_CAP - TOPK_THREADS) {
+            const int have = s_have;
+            for (int t = have + threadIdx.x; t < TOPK_CAP; t += blockDim.x) { keys[t] = 0; pos[t] = 0xffffffffu; }
+            block_bitonic(keys, pos, TOPK_CAP);
+            if (threadIdx.x == 0) {
+                s_have = k;
+                s_thr_key = keys[k - 1];
+                s_thr_pos = pos[k - 1];
+            }
+            have_thr = true;
+            __syncthreads();
+        }
+    }
+    const int have = s_have;
+    int n_pad = 32;
+    while (n_pad < have) n_pad <<= 1;
+    for (int t = have + threadIdx.x; t < n_pad; t += blockDim.x) { keys[t] = 0; pos[t] = 0xffffffffu; }
+    block_bitonic(keys, pos, n_pad);
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const int64_t o = g * k + t;
+        if (t < have) { idx[o] = (int32_t)pos[t]; sim[o] = rs_key_sim(keys[t]); }
+        else { idx[o] = -1; sim[o] = __longlong_as_double(0x7ff8000000000001ll); }
+    }
+}
+
+// T[(c - c0)][r] = S[r][c] for r in [0, m), c in [c0, n): 32 x 32 tiles through shared memory
+__global__ void transpose_slab_kernel(const double *__restrict__ s, int64_t ld_s, int32_t m, int64_t c0, int32_t n,
+                                      double *__restrict__ t, int64_t ld_t) {
+    __shared__ double tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.y * 32, c_base = c0 + (int64_t)blockIdx.x * 32;
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int64_t r = r0 + y, c = c_base + threadIdx.x;
+        tile[y][threadIdx.x] = (r < m && c < n) ? s[r * ld_s + c] : 0.0;
+    }
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int64_t c = c_base + y, r = r0 + threadIdx.x;
+        if (c < n && r < m) t[(c - c0) * ld_t + r] = tile[threadIdx.x][y];
+    }
+}
+
+// Final neighbour lists from the partial lists of several ranks: out[row] = top k of the union of
+// lists[l][row][*] (every (row, neighbour) pair occurs in exactly one partial list).
+__global__ void __launch_bounds__(TOPK_THREADS) topk_union_kernel(const int32_t *__restrict__ idx_all,
+                                                                  const double *__restrict__ sim_all, int32_t n_lists,
+                                                                  int64_t n_rows, int32_t k, int32_t *__restrict__ idx,
+                                                                  double *__restrict__ sim) {
+    __shared__ uint64_t keys[TOPK_CAP];
+    __shared__ uint32_t pos[TOPK_CAP];
+    __shared__ int s_have;
+    const int64_t g = blockIdx.x;
+    if (threadIdx.x == 0) s_have = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_lists * k; t += blockDim.x) {
+        const int64_t o = ((int64_t)(t / k) * n_rows + g) * k + (t % k);
+        const int32_t id = idx_all[o];
+        if (id >= 0) {
+            const int slot = atomicAdd(&s_have, 1);
+            keys[slot] = rs_sim_key(sim_all[o]);
+            pos[slot] = (uint32_t)id;
+        }
+    }
+    __syncthreads();
+    const int have = s_have;
+    int n_pad = 32;
+    while (n_pad < have) n_pad <<= 1;
+    for (int t = have + threadIdx.x; t < n_pad; t += blockDim.x) { keys[t] = 0; pos[t] = 0xffffffffu; }
+    block_bitonic(keys, pos, n_pad);
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const int64_t o = g * k + t;
+        if (t < have) { idx[o] = (int32_t)pos[t]; sim[o] = rs_key_sim(keys[t]); }
+        else { idx[o] = -1; sim[o] = __longlong_as_double(0x7ff8000000000001ll); }
+    }
+}
+
 }  // namespace
 
 __global__ void iota_kernel(int32_t *out, int32_t n) {
@@ -532,3 +668,44 @@ int32_t rs_topk_launch(rs_knn *h, int32_t k, int32_t *d_idx, double *d_sim) {
     RS_CUDA(cudaGetLastError());
     return RS_OK;
 }
+
+// Symmetric slab: merge the slab rows [g0, g0+m) (entries right of the diagonal) and their transpose
+// into the running neighbour lists of all rows >= g0 (see topk_merge_kernel).
+int32_t rs_topk_slab_launch(rs_knn *h, int64_t g0, int32_t m, double *tbuf, int64_t ld_t, int32_t k) {
+    if (k < 1 || k > TOPK_CAP / 4) {
+        rs_set_error("top-k supports 1 <= k <= %d (got %d)", TOPK_CAP / 4, k);
+        return RS_ERR_UNSUPPORTED;
+    }
+    const int32_t n = h->n_left;
+    topk_merge_kernel<<<(unsigned)m, TOPK_THREADS, 0, h->stream>>>(h->sims, h->ld_s, g0, n, m, 0, k, h->topk_idx,
+                                                                 h->topk_sim);
+    const int64_t rest = (int64_t)n - g0;                     // rows g0 .. n-1 receive transposed contributions
+    if (rest > 1) {
+        dim3 grid((unsigned)((rest + 31) / 32), (unsigned)((m + 31) / 32)), block(32, 8);
+        transpose_slab_kernel<<<grid, block, 0, h->stream>>>(h->sims, h->ld_s, m, g0, n, tbuf, ld_t);
+        topk_merge_kernel<<<(unsigned)rest, TOPK_THREADS, 0, h->stream>>>(tbuf, ld_t, g0, n, m, 1, k, h->topk_idx,
+                                                                        h->topk_sim);
+        h->prof.total_launches += 2;
+    }
+    h->prof.total_launches += 1;
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
+extern "C" int32_t rs_knn_topk_union_device(int32_t n_lists, int64_t n_rows, int32_t k, const int32_t *d_idx_all,
+                                            const double *d_sim_all, int32_t *d_idx, double *d_sim,
+                                            void *cuda_stream) {
+    if (n_lists < 1 || n_rows < 1 || k < 1 || !d_idx_all || !d_sim_all || !d_idx || !d_sim) {
+        rs_set_error("rs_knn_topk_union: bad argument");
+        return RS_ERR_INVALID;
+    }
+    if ((int64_t)n_lists * k > TOPK_CAP) {
+        rs_set_error("rs_knn_topk_union: n_lists * k = %lld exceeds %d", (long long)n_lists * k, TOPK_CAP);
+        return RS_ERR_UNSUPPORTED;
+    }
+    topk_union_kernel<<<(unsigned)n_rows, TOPK_THREADS, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+        d_idx_all, d_sim_all, n_lists, n_rows, k, d_idx, d_sim);
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+

@@ -245,7 +245,7 @@ int32_t rs_sim_stream_launch(rs_knn *h) {
     a.global_bias = h->global_bias; a.shrinkage = h->p.shrinkage;
     a.sims = h->sims; a.ld_s = h->ld_s; a.n_left = h->n_left;
     a.row_begin = h->row_begin; a.row_end = h->row_end;
-    a.symmetric = (h->row_begin == 0 && h->row_end == h->n_left) ? 1 : 0;
+    a.symmetric = ((h->row_begin == 0 && h->row_end == h->n_left) || h->force_sym) ? 1 : 0;
     if (h->row_end <= h->row_begin) return RS_OK;
     a.counter = reinterpret_cast<unsigned long long *>(h->d_flags + 2);
     RS_CUDA(cudaMemsetAsync(a.counter, 0, 8, h->stream));

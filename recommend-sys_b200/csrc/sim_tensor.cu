@@ -948,15 +948,18 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
     // tile list in units of cluster tiles (ci x cj plain tiles each)
     const int nbj = (int)((h->n_left + BN - 1) / BN);
     const int bi0 = (int)(rb / BM), bi1 = (int)((re + BM - 1) / BM);
-    const int64_t key[4] = {h->n_left, rb, re,
-                            (mirror ? 1 : 0) + 2 * (ci * 16 + cj) + 1024 * (int64_t)(sup_i * 4096 + sup_j) + ((int64_t)BN << 40)};
+    const int64_t key[5] = {h->n_left, rb, re,
+                            (mirror ? 1 : 0) + 2 * (ci * 16 + cj) + 1024 * (int64_t)(sup_i * 4096 + sup_j) + ((int64_t)BN << 40),
+                            cosums ? 0 : h->col_begin};
     if (memcmp(key, h->tile_key, sizeof(key)) != 0) {
         // Rasterised in supertiles so concurrently running clusters touch few distinct row blocks.
         const int SUP_I = sup_i / ci > 0 ? sup_i / ci : 1, SUP_J = sup_j / cj > 0 ? sup_j / cj : 1;
         const int cbi0 = bi0 / ci, cbi1 = (bi1 + ci - 1) / ci, ncbj = (nbj + cj - 1) / cj;
         std::vector<int2> tiles;
         auto needed = [&](int cbi, int cbj) {
-            // mirror mode keeps a cluster tile iff it holds a pair (i, j) with j >= i
+            // mirror mode keeps a cluster tile iff it holds a pair (i, j) with j >= i; a symmetric slab
+            // (col_begin > 0) needs nothing left of its first row
+            if (!cosums && (int64_t)(cbj * cj + cj) * BN <= h->col_begin) return false;
             return !mirror || (int64_t)(cbj * cj + cj) * BN > (int64_t)(cbi * ci) * BM;
         };
         for (int sbi = cbi0; sbi < cbi1; sbi += SUP_I)

@@ -38,6 +38,37 @@ def allgather_topk(idx_local, sim_local, n: int, k: int, group=None, align: int 
     return out_i, out_s
 
 
+def allgather_partial_topk(idx_part, sim_part, group=None):
+    """Symmetric-slab sharding (rs_knn_params.shard_count >= 1): every rank holds PARTIAL neighbour
+    lists for all n rows, (n, k).  Returns the stacked (world, n, k) tensors on every rank — the one
+    exchange step of the sharded Fit, an all-gather over NCCL/NVLink (gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    all_i = torch.empty((world,) + tuple(idx_part.shape), dtype=idx_part.dtype, device=idx_part.device)
+    all_s = torch.empty((world,) + tuple(sim_part.shape), dtype=sim_part.dtype, device=sim_part.device)
+    dist.all_gather_into_tensor(all_i, idx_part.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_s, sim_part.contiguous(), group=group)
+    return all_i, all_s
+
+
+def union_topk_device(all_i, all_s):
+    """Unites stacked partial lists (n_lists, n, k) into the final (n, k) lists on the device
+    (rs_knn_topk_union_device; CUDA tensors, the current torch stream)."""
+    import torch
+
+    from . import core
+
+    n_lists, n, k = all_i.shape
+    out_i = torch.empty((n, k), dtype=torch.int32, device=all_i.device)
+    out_s = torch.empty((n, k), dtype=torch.float64, device=all_s.device)
+    core._check(core.knn_lib().rs_knn_topk_union_device(
+        n_lists, n, k, all_i.data_ptr(), all_s.data_ptr(), out_i.data_ptr(), out_s.data_ptr(),
+        torch.cuda.current_stream(all_i.device).cuda_stream))
+    return out_i, out_s
+
+
 def allgather_predictions(pred_local, counts, group=None):
     """All-gather per-rank prediction vectors of (known) lengths `counts` into one vector."""
     import torch

@@ -34,8 +34,8 @@ def test_params_default_matches_reference_defaults():
 
 
 def test_struct_sizes_match_header():
-    # 10 int32 + 2 int64 + 1 double
-    assert C.sizeof(rs.core.RsKnnParams) == 10 * 4 + 2 * 8 + 8
+    # 10 int32 + 2 int64 + 1 double + 2 int32
+    assert C.sizeof(rs.core.RsKnnParams) == 10 * 4 + 2 * 8 + 8 + 2 * 4
     assert C.sizeof(rs.core.RsKnnProfile) == 3 * 8 + 3 * 8 + 2 * 4 + 8
 
 

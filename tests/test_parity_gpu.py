@@ -172,6 +172,41 @@ def test_topk_only_store_matches_matrix_store(ml100k):
         only.PredictBatch(u[:4], i[:4])
 
 
+@pytest.mark.parametrize("sim,path", [("msd", "tensor"), ("cosine", "tensor"), ("msd", "stream"),
+                                      ("pearson", "stream")])
+def test_symmetric_slab_topk(ml100k, sim, path, monkeypatch):
+    """RS_STORE_TOPK with shard_count >= 1: every pair is computed once (right of the diagonal) and
+    feeds both rows' lists.  One shard = the complete lists; three shards on one GPU, united with
+    rs_knn_topk_union_device, = the same lists (multi-GPU without a cluster)."""
+    import torch
+
+    from recommend_sys_b200.shard import union_topk_device
+
+    monkeypatch.setenv("RS_KNN_SLAB_ROWS", "256")     # 943 rows -> 4 slabs
+    u, i, r = split(ml100k["u2_base"])
+    ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
+    k = 50
+    base = {"sim": SIMS[sim], "userBased": True, "simPath": path}
+    full = rs.NewKNN(rs.Parameters(base))
+    full.Fit(ts)
+    want_i, want_s = full.TopK(k)
+    one = rs.NewKNN(rs.Parameters(dict(base, store="topk", topk=k, shardCount=1)))
+    one.Fit(ts)
+    got_i, got_s = one.TopK(k)
+    assert np.array_equal(got_i, want_i) and bits_equal(got_s, want_s)
+    parts = []
+    for rank in range(3):
+        p = rs.NewKNN(rs.Parameters(dict(base, store="topk", topk=k, shardCount=3, shardIndex=rank)))
+        p.Fit(ts)
+        parts.append(p.TopK(k))
+        p.Close()
+    all_i = torch.from_numpy(np.stack([a for a, _ in parts])).cuda()
+    all_s = torch.from_numpy(np.stack([b for _, b in parts])).cuda()
+    uni_i, uni_s = union_topk_device(all_i, all_s)
+    torch.cuda.synchronize()
+    assert np.array_equal(uni_i.cpu().numpy(), want_i) and bits_equal(uni_s.cpu().numpy(), want_s)
+
+
 def test_row_shards_equal_full(ml100k):
     """Multi-GPU without a cluster: the S-shard partition on one GPU equals
     the 1-shard result."""
