@@ -46,11 +46,12 @@ def allgather_partial_topk(idx_part, sim_part, group=None):
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    all_i = torch.empty((world,) + tuple(idx_part.shape), dtype=idx_part.dtype, device=idx_part.device)
-    all_s = torch.empty((world,) + tuple(sim_part.shape), dtype=sim_part.dtype, device=sim_part.device)
+    n, k = idx_part.shape
+    all_i = torch.empty((world * n, k), dtype=idx_part.dtype, device=idx_part.device)
+    all_s = torch.empty((world * n, k), dtype=sim_part.dtype, device=sim_part.device)
     dist.all_gather_into_tensor(all_i, idx_part.contiguous(), group=group)
     dist.all_gather_into_tensor(all_s, sim_part.contiguous(), group=group)
-    return all_i, all_s
+    return all_i.view(world, n, k), all_s.view(world, n, k)
 
 
 def union_topk_device(all_i, all_s):

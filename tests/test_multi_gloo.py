@@ -76,3 +76,69 @@ def test_two_rank_shard_allgather(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok").read_text() == "ok"
+
+
+def _topk_canonical(ids, sims, k):
+    """Top k of (id, sim) candidates, similarity desc then id asc; NaN excluded; padded with -1 / NaN."""
+    ok = ~np.isnan(sims)
+    ids, sims = ids[ok], sims[ok]
+    order = np.lexsort((ids, -(sims + 0.0)))[:k]
+    oi = np.full(k, -1, dtype=np.int32)
+    os_ = np.full(k, np.nan)
+    oi[:len(order)] = ids[order]
+    os_[:len(order)] = sims[order]
+    return oi, os_
+
+
+def _worker_symmetric(rank, world, port, out_dir):
+    """Symmetric-slab sharding (rs_knn_params.shard_count): rank r owns the slabs r, r+world, ... and of
+    each only the pairs right of the diagonal; every pair feeds both rows' PARTIAL lists; one
+    all-gather + union gives the final lists.  The oracle stands in for the device."""
+    sys.path.insert(0, str(ROOT))
+    import torch
+    import torch.distributed as dist
+
+    from oracle import binding as ob
+    from recommend_sys_b200.shard import allgather_partial_topk
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = np.load(ROOT / "tests" / "golden" / "ml100k.npz")
+    tr = g["u1_base"].astype(np.int64)[:20000]
+    ts = ob.TrainSet(tr[:, 0], tr[:, 1], tr[:, 2].astype(float))
+    full = ob.KNN(sim="msd", k=10, user_based=True).fit(ts)
+    S = full.sims()
+    n, k, m = S.shape[0], 10, 64
+    cand = [([], []) for _ in range(n)]
+    for slab in range(rank, (n + m - 1) // m, world):
+        for i in range(slab * m, min(n, slab * m + m)):
+            for j in range(i + 1, n):
+                cand[i][0].append(j); cand[i][1].append(S[i, j])
+                cand[j][0].append(i); cand[j][1].append(S[i, j])
+    part_i = np.full((n, k), -1, dtype=np.int32)
+    part_s = np.full((n, k), np.nan)
+    for r in range(n):
+        part_i[r], part_s[r] = _topk_canonical(np.array(cand[r][0], dtype=np.int32), np.array(cand[r][1]), k)
+    all_i, all_s = allgather_partial_topk(torch.from_numpy(part_i), torch.from_numpy(part_s))
+    assert tuple(all_i.shape) == (world, n, k)
+    if rank == 0:
+        wi, ws = full.topk(k)
+        ai, as_ = all_i.numpy(), all_s.numpy()
+        for r in range(n):
+            ids = ai[:, r, :].reshape(-1)
+            keep = ids >= 0
+            assert len(np.unique(ids[keep])) == keep.sum()          # every pair in exactly one partial list
+            gi, gs = _topk_canonical(ids[keep], as_[:, r, :].reshape(-1)[keep], k)
+            assert np.array_equal(gi, wi[r]) and np.array_equal(np.nan_to_num(gs), np.nan_to_num(ws[r]))
+        (Path(out_dir) / "ok_sym").write_text("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_symmetric_slabs(tmp_path):
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mp.spawn(_worker_symmetric, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok_sym").read_text() == "ok"
