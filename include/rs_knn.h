@@ -82,8 +82,8 @@ typedef struct rs_knn_params {
     double shrinkage;     /* PearsonBaseline extension: (n-1)/(n-1+shrinkage), 0 = off    */
     int32_t shard_count;  /* RS_STORE_TOPK only.  0 (default): the handle computes the full rows of */
     int32_t shard_index;  /*   [row_begin,row_end) and keeps their lists.  >= 1: SYMMETRIC SLABS — the */
-                          /*   left rows are cut into slabs, the handle computes the slabs           */
-                          /*   shard_index, shard_index + shard_count, ... and of each only the part  */
+                          /*   left rows are cut into slabs dealt to the shards in snake order          */
+                          /*   (0..c-1, c-1..0, ...); the handle computes its slabs, of each only the part */
                           /*   right of the diagonal; every pair {i,j} it computes feeds the list of  */
                           /*   row i AND of row j, so no pair is computed twice (half the work) and  */
                           /*   the handle holds PARTIAL lists for ALL n_left rows: complete when      */

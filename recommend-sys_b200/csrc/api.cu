@@ -289,6 +289,13 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
         const int32_t k = h->p.topk > 0 ? h->p.topk : h->p.k;
         const int64_t n = n_left;
         int64_t m = (int64_t)(6ll << 30) / (h->ld_s * 8);        // ~6 GiB slab + the same for its transpose
+        if (h->p.shard_count > 1) {
+            // enough slabs for an even deal: at least 4 per shard (down to 1024 rows each)
+            int64_t want = (n + 4ll * h->p.shard_count - 1) / (4ll * h->p.shard_count);
+            want = (want + 255) / 256 * 256;
+            if (want < 1024) want = 1024;
+            if (want < m) m = want;
+        }
         if (const char *e = getenv("RS_KNN_SLAB_ROWS")) m = atoll(e);   // tests: many slabs on a small matrix
         if (m < 256) m = 256;
         m = m / 256 * 256;
@@ -305,7 +312,12 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
         RS_CUDA(cudaEventRecord(h->ev_b, h->stream));
         const int64_t n_slabs = (n + m - 1) / m;
         h->force_sym = true;
-        for (int64_t sl = h->p.shard_index; sl < n_slabs; sl += h->p.shard_count) {
+        for (int64_t sl = 0; sl < n_slabs; sl++) {
+            // snake deal: slab sl costs ~ (n_slabs - sl); rounds alternate direction so that every
+            // shard gets the same share of the triangle (8 GPUs, 25 slabs dealt plainly: max/mean 1.28)
+            const int64_t round = sl / h->p.shard_count, posn = sl % h->p.shard_count;
+            const int64_t owner = (round & 1) ? h->p.shard_count - 1 - posn : posn;
+            if (owner != h->p.shard_index) continue;
             const int64_t r0 = sl * m, r1 = r0 + m < n ? r0 + m : n;
             h->row_begin = r0;
             h->row_end = r1;

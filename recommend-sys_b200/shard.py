@@ -38,6 +38,13 @@ def allgather_topk(idx_local, sim_local, n: int, k: int, group=None, align: int 
     return out_i, out_s
 
 
+def slab_owner(slab: int, world: int) -> int:
+    """Which shard computes slab `slab` under symmetric-slab sharding: slabs are dealt in snake order
+    (0..world-1, world-1..0, ...) because slab s costs ~ (n_slabs - s) — the same rule as csrc/api.cu."""
+    rnd, pos = divmod(slab, world)
+    return world - 1 - pos if rnd & 1 else pos
+
+
 def allgather_partial_topk(idx_part, sim_part, group=None):
     """Symmetric-slab sharding (rs_knn_params.shard_count >= 1): every rank holds PARTIAL neighbour
     lists for all n rows, (n, k).  Returns the stacked (world, n, k) tensors on every rank — the one

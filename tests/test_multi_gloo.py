@@ -99,7 +99,7 @@ def _worker_symmetric(rank, world, port, out_dir):
     import torch.distributed as dist
 
     from oracle import binding as ob
-    from recommend_sys_b200.shard import allgather_partial_topk
+    from recommend_sys_b200.shard import allgather_partial_topk, slab_owner
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -111,7 +111,9 @@ def _worker_symmetric(rank, world, port, out_dir):
     S = full.sims()
     n, k, m = S.shape[0], 10, 64
     cand = [([], []) for _ in range(n)]
-    for slab in range(rank, (n + m - 1) // m, world):
+    for slab in range((n + m - 1) // m):
+        if slab_owner(slab, world) != rank:
+            continue
         for i in range(slab * m, min(n, slab * m + m)):
             for j in range(i + 1, n):
                 cand[i][0].append(j); cand[i][1].append(S[i, j])
