@@ -428,12 +428,27 @@ def run_ours(args, rank, world, local_rank):
                 "note": ("exact-order FP64 replay: bound by shared-memory read-modify-write and issue slots "
                          "(profiles/r01_stream_notes.md), reported against the HBM roofline of its algorithmic "
                          "bytes (left CSR + emitted similarities) as the contract asks")}
+    # second object for the gather-reduce (the north star asks for "achieved HBM GB/s for predict"):
+    # algorithmic bytes per prediction = C * (4 B id + 8 B similarity + 8 B rating [+ 8 B mean/bias]) + 8 B
+    roof_pred = None
+    if n_pred:
+        deg_right = np.bincount(right, minlength=n_right)
+        cand = float(deg_right[t_right[t_right >= 0]].sum())
+        per_cand = 20 + (8 if knn_type != "basic" else 0)
+        pbytes = cand * per_cand + n_pred * 8.0
+        pms = pred_ms / args.steps
+        roof_pred = {"bound": "hbm", "achieved": pbytes / (pms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": pbytes / (pms / 1e3) / 1e9 / hbm_peak, "traffic": None,
+                     "kernel": "predict_select_kernel", "ms_per_launch": pms,
+                     "candidates_per_prediction": cand / max(1, n_pred)}
     prof_file = ROOT / "profiles" / "traffic.json"
     if prof_file.exists():
         try:
             # DRAM bytes per launch of this kernel ON THIS WORKLOAD from the committed ncu capture
-            roof["traffic"] = json.loads(prof_file.read_text()).get(
-                roof["kernel"].split("<")[0] + "|" + args.workload)
+            tj = json.loads(prof_file.read_text())
+            roof["traffic"] = tj.get(roof["kernel"].split("<")[0] + "|" + args.workload)
+            if roof_pred:
+                roof_pred["traffic"] = tj.get("predict_select_kernel|" + args.workload)
         except (ValueError, OSError):
             pass
 
@@ -461,6 +476,7 @@ def run_ours(args, rank, world, local_rank):
         "kernel_ms": {"sim": sim_ms / args.steps, "predict": pred_ms / args.steps, "prep": prof["prep_ms"] / args.steps},
         "corated_triples": prof["corated_triples"],
         "roofline": roof,
+        "roofline_predict": roof_pred,
     }
     if world == 1 and not args.no_cpu_baseline:
         from oracle import binding as ob
