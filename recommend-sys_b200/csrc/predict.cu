@@ -273,9 +273,30 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
                     thr = b_lo + 1ull;
                     break;
                 }
+                // shrink the window to the keys actually present in the boundary bucket: similarity
+                // data is full of exact ties (27 % of the item-item Pearson values are +-1.0), and a
+                // bucket holding one repeated value is recognised here in ONE pass instead of being
+                // narrowed 8 key bits at a time
                 const uint64_t b_hi = b_lo + ((1ull << sh) - 1ull);
-                klo = b_lo;
-                khi = b_hi < khi ? b_hi : khi;
+                uint64_t nlo = ~0ull, nhi = 0ull;
+                for (int e = lane; e < cnt; e += 32) {
+                    const uint64_t key = e < scap ? sbuf[e] : sim_key_or_zero(row[ids[e]]);
+                    if (key >= b_lo && key <= b_hi && key <= khi) { nlo = key < nlo ? key : nlo; nhi = key > nhi ? key : nhi; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const uint64_t ol = __shfl_xor_sync(0xffffffffu, nlo, o), oh = __shfl_xor_sync(0xffffffffu, nhi, o);
+                    nlo = ol < nlo ? ol : nlo;
+                    nhi = oh > nhi ? oh : nhi;
+                }
+                klo = nlo;
+                khi = nhi;
+                if (nlo == nhi) {          // one key value fills the bucket: genuine ties
+                    tie_key = nlo;
+                    tie_take = num - sure;
+                    thr = nlo + 1ull;
+                    break;
+                }
             }
         }
 
