@@ -938,9 +938,6 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
         else if (!strcmp(e, "1x1")) { ci = 1; cj = 1; }
         else if (!strcmp(e, "1x2")) { ci = 1; cj = 2; }
         else if (!strcmp(e, "2x2")) { ci = 2; cj = 2; }
-        else if (!strcmp(e, "2x4")) { ci = 2; cj = 4; }
-        else if (!strcmp(e, "1x4")) { ci = 1; cj = 4; }
-        else if (!strcmp(e, "1x8")) { ci = 1; cj = 8; }
         else if (!strcmp(e, "2x1")) { ci = 2; cj = 1; }
     }
     int sup_i = 8, sup_j = 1024 / BN;   // supertile (1024 x 1024 similarities), in plain tiles
@@ -1012,11 +1009,8 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
     if (use_pair) rc = mode == TC_COSINE ? launch_pair<TC_COSINE>(h, a) : launch_pair<TC_MSD>(h, a);
     else if (ci == 1 && cj == 1) rc = launch_shape<1, 1>(h, a, cosums);
     else if (ci == 1 && cj == 2) rc = launch_shape<1, 2>(h, a, cosums);
-    else if (ci == 1 && cj == 4) rc = launch_shape<1, 4>(h, a, cosums);
-    else if (ci == 1 && cj == 8) rc = launch_shape<1, 8>(h, a, cosums);
     else if (ci == 2 && cj == 1) rc = launch_shape<2, 1>(h, a, cosums);
-    else if (ci == 2 && cj == 2) rc = launch_shape<2, 2>(h, a, cosums);
-    else rc = launch_shape<2, 4>(h, a, cosums);
+    else rc = launch_shape<2, 2>(h, a, cosums);
     RS_TRY(rc);
     if (!cosums) h->prof.sim_launches++;
     h->prof.total_launches++;
