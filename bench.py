@@ -367,14 +367,19 @@ def run_ours(args, rank, world, local_rank):
         est.Close()
         return out
 
-    e2e_steps = max(1, min(args.steps, 5))
+    # every e2e step is timed on its own (wall clock around the public API call, which ends with the
+    # device->host read of the result); the MEDIAN step is reported: the host part (Python, id maps,
+    # pinned copies) is exposed to noisy neighbours on these shared boxes, the device part is not
+    e2e_steps = max(1, min(args.steps, 10))
     step_e2e()
     barrier()
-    t0 = time.perf_counter()
+    e2e_times = []
     for _ in range(e2e_steps):
+        t0 = time.perf_counter()
         step_e2e()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+        torch.cuda.synchronize()
+        e2e_times.append(time.perf_counter() - t0)
+    e2e_s = statistics.median(e2e_times)
 
     # ---- reduce over ranks: max time, summed units ----
     pairs_rank = n_left * (n_left - 1) / 2 if not shard else (re - rb) * (n_left - 1) / 2.0
@@ -471,7 +476,8 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": pairs_all / e2e_s, "unit": "pairs/s", "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": int(len(left) * 16 + n_pred * 8),
                 "d2h_bytes_per_step": int(n_pred * 8 + (n_left * k * 12 if sym else 0)),
-                "predictions_per_sec": preds_all / e2e_s, "steps": e2e_steps},
+                "predictions_per_sec": preds_all / e2e_s, "steps": e2e_steps, "statistic": "median step",
+                "ms_min": min(e2e_times) * 1e3, "ms_max": max(e2e_times) * 1e3},
         "gpu_launches": int(prof["total_launches"]),
         "kernel_ms": {"sim": sim_ms / args.steps, "predict": pred_ms / args.steps, "prep": prof["prep_ms"] / args.steps},
         "corated_triples": prof["corated_triples"],
