@@ -50,6 +50,9 @@ WORKLOADS = {
     "ml20m_item_pearson_k40": (138_493, 26_744, 20_000_000, 4_000_000, "pearson", "centered", False, 40),
     "ml20m_item_pearson_baseline_k40": (138_493, 26_744, 20_000_000, 4_000_000, "pearson_baseline", "baseline", False, 40),
     "ml20m_user_msd_k100": (138_493, 26_744, 20_000_000, 0, "msd", "basic", True, 100),
+    # Slope One (core/slope_one.go) — item x item deviation matrix + full test-set Predict
+    "ml1m_slope_one": (6040, 3706, 1_000_000, 200_000, "slope_one", "basic", False, 0),
+    "ml20m_slope_one": (138_493, 26_744, 20_000_000, 4_000_000, "slope_one", "basic", False, 0),
     "netflix_item_cosine_k50": (480_189, 17_770, 100_000_000, 20_000_000, "cosine", "basic", False, 50),
 }
 DEFAULT_WORKLOAD = "ml1m_item_pearson_k40"
@@ -129,6 +132,21 @@ def load_peaks():
 def cpu_reference_step(ob, ots, test, sim, knn_type, user_based, k, cores, rows=None, n_pred=None):
     """One step of the reference's CPU algorithm (restated in oracle/): returns (seconds_fit,
     seconds_predict, rows_fitted, n_predicted)."""
+    if sim == "slope_one":      # core/slope_one.go: Fit on all cores, serial Predict loop (core/data.go:98-105)
+        n_items = ots.item_count
+        # a slab is taken at the END of the matrix: row i meets its i predecessors (core/slope_one.go:72),
+        # so the last m rows do ~m*n pair merges — the same scaling rule as the KNN slabs
+        srows = None if rows is None else (n_items - (rows[1] - rows[0]), n_items)
+        t0 = time.perf_counter()
+        so = ob.SlopeOne().fit(ots, n_jobs=cores, rows=srows)
+        t1 = time.perf_counter()
+        u, i = test.Users, test.Items
+        if n_pred is not None:
+            u, i = u[:n_pred], i[:n_pred]
+        t2 = time.perf_counter()
+        so.predict_batch(u, i)
+        t3 = time.perf_counter()
+        return t1 - t0, t3 - t2, (n_items if rows is None else rows[1] - rows[0]), len(u)
     # config 3 (PearsonBaseline + KNNBaseline) uses ALS baselines on both arms (BASELINE.json configs[2])
     knn = ob.KNN(sim=sim, knn_type=knn_type, user_based=user_based, k=k, n_jobs=cores, tie_policy="go",
                  baseline="als" if sim == "pearson_baseline" else "sgd")
@@ -343,7 +361,10 @@ def run_ours(args, rank, world, local_rank):
     train.Ratings = pinned_like(train.Ratings)
     ctor = {"basic": rs.NewKNN, "centered": rs.NewKNNWithMean, "zscore": rs.NewKNNWithZScore,
             "baseline": rs.NewKNNBaseLine}[knn_type]
-    sim_obj = {"cosine": rs.Cosine, "msd": rs.MSD, "pearson": rs.Pearson, "pearson_baseline": rs.PearsonBaseline}[sim]
+    if sim == "slope_one":
+        ctor = rs.NewSlopeOne
+    sim_obj = {"cosine": rs.Cosine, "msd": rs.MSD, "pearson": rs.Pearson, "pearson_baseline": rs.PearsonBaseline,
+               "slope_one": None}[sim]
     params = {"sim": sim_obj, "userBased": user_based, "k": k, "device": local_rank,
               "pearsonMode": args.pearson_mode, "simPath": args.sim_path}
     if sim == "pearson_baseline":
@@ -408,7 +429,7 @@ def run_ours(args, rank, world, local_rank):
     launches_per_step = max(1, prof["sim_launches"]) / args.steps
     sim_step_ms = sim_ms / args.steps            # all similarity launches of one Fit (slabs in top-k mode)
     if prof["sim_path_used"] == rs.core.RS_SIM_PATH["tensor"]:
-        g = {"cosine": 3, "msd": 4, "pearson": 6}[sim]
+        g = {"cosine": 3, "msd": 4, "pearson": 6, "slope_one": 3}[sim]   # slope one: count, sum r_i, sum r_j
         ops = pairs_rank * 2 * g * n_right
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
         tpeak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))

@@ -38,7 +38,13 @@ extern "C" {
 
 /* core/sim.go: Cosine :10, MSD :28, Pearson :47.  PEARSON_BASELINE is an extension
  * (named by the north star, absent from the reference). */
-enum rs_sim { RS_SIM_COSINE = 0, RS_SIM_MSD = 1, RS_SIM_PEARSON = 2, RS_SIM_PEARSON_BASELINE = 3 };
+enum rs_sim { RS_SIM_COSINE = 0, RS_SIM_MSD = 1, RS_SIM_PEARSON = 2, RS_SIM_PEARSON_BASELINE = 3,
+              /* SURVEY.md §8 f-2, the step next to the KNN path: the Slope One deviation matrix
+               * (core/slope_one.go:47-93) instead of a similarity.  Fit with left = items, right =
+               * users; rs_knn_sims_rows returns dev rows (0 = unset, antisymmetric);
+               * rs_knn_predict_batch(left = item, right = user) is SlopeOne.Predict
+               * (core/slope_one.go:22-45).  Integer ratings only (tensor path). */
+              RS_SIM_SLOPE_ONE = 4 };
 /* core/knn.go:10-15 and the four constructors core/knn.go:50-73 */
 enum rs_knn_type { RS_KNN_BASIC = 0, RS_KNN_CENTERED = 1, RS_KNN_ZSCORE = 2, RS_KNN_BASELINE = 3 };
 /* How Pearson is evaluated.

@@ -93,6 +93,20 @@ def lib():
     L.or_knn_topk.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, p32, pd]
     L.or_knn_pair_sums.argtypes = [C.c_void_p, C.c_int64, C.c_int64, p64]
     L.or_baseline_fit.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, pd, pd, pd]
+    L.or_slope_fit.restype = C.c_void_p
+    L.or_slope_fit.argtypes = [C.c_void_p, C.c_int]
+    L.or_slope_fit_rows.restype = C.c_void_p
+    L.or_slope_fit_rows.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64]
+    L.or_slope_free.argtypes = [C.c_void_p]
+    L.or_slope_n.restype = C.c_int64
+    L.or_slope_n.argtypes = [C.c_void_p]
+    L.or_slope_dev.restype = C.POINTER(C.c_double)
+    L.or_slope_dev.argtypes = [C.c_void_p]
+    L.or_slope_user_means.restype = C.POINTER(C.c_double)
+    L.or_slope_user_means.argtypes = [C.c_void_p]
+    L.or_slope_predict.restype = C.c_double
+    L.or_slope_predict.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    L.or_slope_predict_batch.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64, pd]
     L.or_baseline_als.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, pd, pd]
     L.or_baseline_als.restype = None
     L.or_rmse.restype = C.c_double
@@ -262,3 +276,41 @@ def mae(pred, truth):
     pred = np.ascontiguousarray(pred, dtype=np.float64)
     truth = np.ascontiguousarray(truth, dtype=np.float64)
     return lib().or_mae(_p(pred, C.c_double), _p(truth, C.c_double), len(pred))
+
+
+class SlopeOne:
+    """core/slope_one.go restated."""
+
+    def __init__(self):
+        self.h = None
+        self.train = None
+
+    def fit(self, train: TrainSet, n_jobs=8, rows=None):
+        self.train = train
+        self.h = (lib().or_slope_fit(train.h, n_jobs) if rows is None
+                  else lib().or_slope_fit_rows(train.h, n_jobs, rows[0], rows[1]))
+        return self
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().or_slope_free(self.h)
+            self.h = None
+
+    def dev(self):
+        n = lib().or_slope_n(self.h)
+        return np.ctypeslib.as_array(lib().or_slope_dev(self.h), shape=(n, n)).copy()
+
+    def user_means(self):
+        return np.ctypeslib.as_array(lib().or_slope_user_means(self.h), shape=(self.train.user_count,)).copy()
+
+    def predict(self, u, i):
+        return lib().or_slope_predict(self.h, int(u), int(i))
+
+    def predict_batch(self, users, items):
+        users = np.ascontiguousarray(users, dtype=np.int64)
+        items = np.ascontiguousarray(items, dtype=np.int64)
+        out = np.empty(len(users), dtype=np.float64)
+        lib().or_slope_predict_batch(self.h, _p(users, C.c_int64), _p(items, C.c_int64), len(users),
+                                     _p(out, C.c_double))
+        return out
+

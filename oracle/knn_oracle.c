@@ -835,3 +835,118 @@ double or_mae(const double *pred, const double *truth, int64_t n) {
     for (int64_t j = 0; j < n; j++) sum += fabs(pred[j] - truth[j]);
     return sum / (double)n;
 }
+
+/* =====================================================================================
+ * Slope One — core/slope_one.go (the step next to the KNN path; same co-rated
+ * contraction, same Predict-style gather).  Restated op for op.
+ * ===================================================================================== */
+struct or_slope {
+    or_trainset *data;
+    double global_mean;
+    int64_t n_items, n_users;
+    or_idrating **user_ratings;      /* dataset order (core/slope_one.go:51) */
+    int64_t *user_len;
+    or_idrating *user_store;
+    double *user_means;
+    double *dev;                     /* n_items x n_items, zero-initialised (core/slope_one.go:53) */
+};
+
+typedef struct { double *dev; or_idrating **ir; int64_t *ilen; int64_t n, begin, end; } slope_job;
+static void *slope_worker(void *arg) {
+    slope_job *jb = (slope_job *)arg;
+    double *dev = jb->dev;
+    or_idrating **ir = jb->ir;
+    int64_t *ilen = jb->ilen;
+    const int64_t n = jb->n;
+    for (int64_t i = jb->begin; i < jb->end; i++) {                    /* core/slope_one.go:71-90 */
+        for (int64_t j = 0; j < i; j++) {
+            double count = 0.0, sum = 0.0;
+            int64_t ptr = 0;
+            for (int64_t k = 0; k < ilen[i] && ptr < ilen[j]; k++) {
+                or_idrating ur = ir[i][k];
+                while (ptr < ilen[j] && ir[j][ptr].id < ur.id) ptr++;
+                if (ptr < ilen[j] && ir[j][ptr].id == ur.id) {
+                    count++;
+                    sum += ur.rating - ir[j][ptr].rating;
+                }
+            }
+            if (count > 0) {
+                dev[i * n + j] = sum / count;
+                dev[j * n + i] = -dev[i * n + j];
+            }
+        }
+    }
+    return NULL;
+}
+
+or_slope *or_slope_fit_rows(or_trainset *t, int n_jobs, int64_t row0, int64_t row1) {
+    or_slope *s = (or_slope *)calloc(1, sizeof(*s));
+    s->data = t;
+    s->global_mean = t->global_mean;                                   /* core/slope_one.go:50 */
+    s->n_items = t->item_count;
+    s->n_users = t->user_count;
+    /* private copies: the caller may already have fitted a KNN on this trainset, which sorts the
+     * shared lists in place; Slope One reads userRatings in dataset order and sorts its own item lists */
+    build_adjacency(t->n, t->user_count, t->iu, t->ii, t->ratings, &s->user_ratings, &s->user_len, &s->user_store);
+    or_idrating **ir, *istore;
+    int64_t *ilen;
+    build_adjacency(t->n, t->item_count, t->ii, t->iu, t->ratings, &ir, &ilen, &istore);
+    s->user_means = (double *)malloc((size_t)(s->n_users + 1) * sizeof(double));
+    for (int64_t u = 0; u < s->n_users; u++) {                         /* core/data.go:222-235 means() */
+        double sum = 0.0, count = 0.0;
+        for (int64_t x = 0; x < s->user_len[u]; x++) { sum += s->user_ratings[u][x].rating; count++; }
+        s->user_means[u] = sum / count;
+    }
+    const int64_t n = s->n_items;
+    s->dev = (double *)calloc((size_t)n * (size_t)n + 1, sizeof(double));
+    for (int64_t i = 0; i < n; i++) or_sort_by_id(ir[i], ilen[i]);     /* core/slope_one.go:55 sorts(itemRatings) */
+    /* core/slope_one.go:59-92: nJobs goroutines over a static split of the rows */
+    if (n_jobs < 1) n_jobs = 1;
+    pthread_t *th = (pthread_t *)malloc((size_t)n_jobs * sizeof(pthread_t));
+    slope_job *jobs = (slope_job *)malloc((size_t)n_jobs * sizeof(slope_job));
+    for (int jb = 0; jb < n_jobs; jb++) {
+        /* row0 < 0: all rows (the reference); otherwise only rows [row0,row1) x columns j < i (bench slabs) */
+        const int64_t lo = row0 < 0 ? 0 : row0, len = (row0 < 0 ? n : row1) - lo;
+        jobs[jb] = (slope_job){ s->dev, ir, ilen, n, lo + len * jb / n_jobs, lo + len * (jb + 1) / n_jobs };
+        if (n_jobs == 1) slope_worker(&jobs[jb]);
+        else pthread_create(&th[jb], NULL, slope_worker, &jobs[jb]);
+    }
+    if (n_jobs > 1) for (int jb = 0; jb < n_jobs; jb++) pthread_join(th[jb], NULL);
+    free(th); free(jobs);
+    free(ir); free(ilen); free(istore);
+    return s;
+}
+
+or_slope *or_slope_fit(or_trainset *t, int n_jobs) { return or_slope_fit_rows(t, n_jobs, -1, -1); }
+
+void or_slope_free(or_slope *s) {
+    if (!s) return;
+    free(s->user_ratings); free(s->user_len); free(s->user_store); free(s->user_means); free(s->dev);
+    free(s);
+}
+
+int64_t or_slope_n(const or_slope *s) { return s->n_items; }
+const double *or_slope_dev(const or_slope *s) { return s->dev; }
+const double *or_slope_user_means(const or_slope *s) { return s->user_means; }
+
+double or_slope_predict(const or_slope *s, int64_t raw_user, int64_t raw_item) {   /* core/slope_one.go:22-45 */
+    int64_t iu = or_trainset_convert_user(s->data, raw_user);
+    int64_t ii = or_trainset_convert_item(s->data, raw_item);
+    double prediction = 0.0;
+    if (iu >= 0) prediction = s->user_means[iu];                       /* newID = -1, core/data.go:129 */
+    else prediction = s->global_mean;
+    if (ii >= 0 && iu >= 0) {
+        double sum = 0.0, count = 0.0;
+        for (int64_t x = 0; x < s->user_len[iu]; x++) {
+            sum += s->dev[ii * s->n_items + s->user_ratings[iu][x].id];
+            count++;
+        }
+        if (count > 0) prediction += sum / count;
+    }
+    return prediction;
+}
+
+void or_slope_predict_batch(const or_slope *s, const int64_t *users, const int64_t *items, int64_t n, double *out) {
+    for (int64_t x = 0; x < n; x++) out[x] = or_slope_predict(s, users[x], items[x]);
+}
+

@@ -142,6 +142,17 @@ typedef struct {
 } or_sort_iface;
 void or_go_sort(or_sort_iface *s, int64_t n);
 
+/* ---- Slope One (core/slope_one.go) ---- */
+typedef struct or_slope or_slope;
+or_slope *or_slope_fit(or_trainset *t, int n_jobs);
+or_slope *or_slope_fit_rows(or_trainset *t, int n_jobs, int64_t row0, int64_t row1);   /* bench slabs only */     /* nJobs = runtime.NumCPU() in the reference */
+void or_slope_free(or_slope *s);
+int64_t or_slope_n(const or_slope *s);
+const double *or_slope_dev(const or_slope *s);          /* n x n, row-major */
+const double *or_slope_user_means(const or_slope *s);
+double or_slope_predict(const or_slope *s, int64_t raw_user, int64_t raw_item);
+void or_slope_predict_batch(const or_slope *s, const int64_t *users, const int64_t *items, int64_t n, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,7 +37,7 @@ RS_OK = 0
 newID = -1  # core/data.go:129
 
 # enum values of include/rs_knn.h
-RS_SIM = {"cosine": 0, "msd": 1, "pearson": 2, "pearson_baseline": 3}
+RS_SIM = {"cosine": 0, "msd": 1, "pearson": 2, "pearson_baseline": 3, "slope_one": 4}
 RS_KNN_TYPE = {"basic": 0, "centered": 1, "zscore": 2, "baseline": 3}
 RS_PEARSON_MODE = {"exact": 0, "sums": 1}
 RS_SIM_PATH = {"auto": 0, "tensor": 1, "stream": 2}
@@ -695,6 +695,59 @@ def NewKNNWithZScore(params=None):
 
 def NewKNNBaseLine(params=None):
     return KNN(baseline, params)
+
+
+# --------------------------------------------------------------------------------------------
+# core/slope_one.go — Slope One (the step next to the KNN path)
+# --------------------------------------------------------------------------------------------
+class SlopeOne(Base):
+    """core/slope_one.go:8-14.  Fit builds the item x item deviation matrix on the device (the same
+    co-rated integer contractions as the KNN similarities: count, sum r_i, sum r_j on the tensor
+    cores); Predict is a gather over the user's ratings.  `dev` and `userMeans` stay available."""
+
+    def __init__(self, params=None):
+        super().__init__(params)
+        self.globalMean = math.nan
+        self.userMeans = None
+        self._h = None
+
+    def Close(self):
+        if self._h is not None:
+            self._h.close()
+            self._h = None
+
+    def __del__(self):
+        self.Close()
+
+    def Fit(self, trainSet: TrainSet):
+        """core/slope_one.go:47-93"""
+        self.Data = trainSet
+        self.globalMean = trainSet.GlobalMean
+        self.Close()
+        self._h = _Handle(sim="slope_one", knn_type="basic", device=self.Params.GetInt("device", -1),
+                          row_begin=self.Params.GetInt("rowBegin", 0), row_end=self.Params.GetInt("rowEnd", 0))
+        self._h.fit(trainSet.innerItems, trainSet.innerUsers, trainSet.Ratings, trainSet.ItemCount,
+                    trainSet.UserCount, trainSet.GlobalMean)
+
+    @property
+    def dev(self):
+        """core/slope_one.go:13 — the item x item deviation matrix (copied from HBM on demand)."""
+        r0, r1 = self._h.rows
+        return self._h.sims_rows(r0, r1 - r0)
+
+    def PredictBatch(self, userIDs, itemIDs):
+        iu = self.Data.convert_users(userIDs)
+        ii = self.Data.convert_items(itemIDs)
+        return self._h.predict_batch(ii, iu)
+
+    def Predict(self, userID, itemID):
+        """core/slope_one.go:22-45 (a one-element batch)."""
+        return float(self.PredictBatch(np.array([userID], dtype=np.int64), np.array([itemID], dtype=np.int64))[0])
+
+
+def NewSlopeOne(params=None):
+    """core/slope_one.go:16-20 (the reference drops `params`; nothing in Slope One reads any)."""
+    return SlopeOne(params)
 
 
 # --------------------------------------------------------------------------------------------

@@ -38,6 +38,8 @@ void free_fit_state(rs_knn *h) {
     h->l_code = nullptr;
     h->lut = h->means = h->stddevs = h->pmeans = h->left_bias = h->right_bias = nullptr;
     h->r_dev = nullptr;
+    h->rd_col = nullptr;
+    h->right_means = nullptr;
     h->cp = nullptr;
     h->l2r = nullptr;
     h->row_order = nullptr;
@@ -72,7 +74,7 @@ int32_t fold_profile(rs_knn *h) {
 
 bool tensor_eligible(const rs_knn *h) {
     if (h->rating_class != RS_CLASS_INT8) return false;
-    if (h->p.sim == RS_SIM_COSINE || h->p.sim == RS_SIM_MSD) return true;
+    if (h->p.sim == RS_SIM_COSINE || h->p.sim == RS_SIM_MSD || h->p.sim == RS_SIM_SLOPE_ONE) return true;
     if (h->p.sim == RS_SIM_PEARSON && h->p.pearson_mode == RS_PEARSON_SUMS) return true;
     return false;
 }
@@ -130,7 +132,7 @@ int32_t rs_knn_create(const rs_knn_params *p, rs_knn **out) {
         rs_set_error("rs_knn_create: null argument");
         return RS_ERR_INVALID;
     }
-    if (p->sim < RS_SIM_COSINE || p->sim > RS_SIM_PEARSON_BASELINE || p->knn_type < RS_KNN_BASIC ||
+    if (p->sim < RS_SIM_COSINE || p->sim > RS_SIM_SLOPE_ONE || p->knn_type < RS_KNN_BASIC ||
         p->knn_type > RS_KNN_BASELINE || p->k < 1 || p->min_k < 0) {
         rs_set_error("rs_knn_create: invalid sim/knn_type/k/min_k");
         return RS_ERR_INVALID;
@@ -256,6 +258,15 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
     if (const char *force = getenv("RS_KNN_FORCE_PATH")) {  // debugging aid: "stream" | "tensor"
         if (!strcmp(force, "stream")) path = RS_PATH_STREAM;
         else if (!strcmp(force, "tensor")) path = RS_PATH_TENSOR;
+    }
+    if (h->p.sim == RS_SIM_SLOPE_ONE) {
+        // the deviation sums are integer contractions: tensor path only (integer ratings)
+        if (!tensor_eligible(h) || path == RS_PATH_STREAM) {
+            rs_set_error("RS_SIM_SLOPE_ONE needs integer ratings in [-11,11] (tensor path)");
+            free_fit_state(h);
+            return RS_ERR_UNSUPPORTED;
+        }
+        path = RS_PATH_TENSOR;
     }
     if (path == RS_PATH_AUTO) path = tensor_eligible(h) && tensor_faster(h) ? RS_PATH_TENSOR : RS_PATH_STREAM;
     if (path == RS_PATH_TENSOR && !tensor_eligible(h)) {
@@ -454,7 +465,8 @@ int32_t rs_knn_predict_batch_device(rs_knn *h, const int32_t *d_left, const int3
     }
     if (h->pred_pending) RS_TRY(fold_profile(h));
     RS_CUDA(cudaEventRecord(h->ev_d, h->stream));
-    RS_TRY(rs_predict_launch(h, d_left, d_right, n, d_out, nullptr, nullptr, nullptr, 0));
+    if (h->p.sim == RS_SIM_SLOPE_ONE) RS_TRY(rs_slope_predict_launch(h, d_left, d_right, n, d_out));
+    else RS_TRY(rs_predict_launch(h, d_left, d_right, n, d_out, nullptr, nullptr, nullptr, 0));
     RS_CUDA(cudaEventRecord(h->ev_e, h->stream));
     h->pred_pending = true;
     return RS_OK;

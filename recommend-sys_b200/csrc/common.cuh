@@ -101,6 +101,9 @@ struct rs_knn {
     int64_t max_row_cnt = 0;
     double triples = 0.0;         // co-rated triples of the full matrix: sum over right rows of cnt*(cnt-1)/2
     double *right_bias = nullptr;
+    // Slope One: the right rows (users) in DATASET order — left ids only — and their means
+    int32_t *rd_col = nullptr;
+    double *right_means = nullptr;
 
     // stream path: b-side term of every rating in right-CSR order (value, value - row mean, ...),
     // chunk pointers cp[right][Q+1] into each right row, and l2r: left-CSR entry -> right-CSR index
@@ -161,6 +164,7 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
 int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_right, int64_t n, double *d_out,
                           int32_t *d_nb_ids, double *d_nb_sims, int32_t *d_nb_count, int32_t nb_cap);
 int32_t rs_topk_launch(rs_knn *h, int32_t k, int32_t *d_idx, double *d_sim);
+int32_t rs_slope_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_right, int64_t n, double *d_out);
 int32_t rs_topk_slab_launch(rs_knn *h, int64_t g0, int32_t m, double *tbuf, int64_t ld_t, int32_t k);
 
 // order-preserving map double -> uint64 (larger similarity = larger key); -0.0 folded to +0.0

@@ -589,6 +589,61 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_union_kernel(const int32_t 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// SlopeOne.Predict (core/slope_one.go:22-45).  One warp per (item, user) pair:
+//   prediction = userMeans[u] (GlobalMean for an unknown user); for a known item,
+//   += ( sum over the user's ratings, in DATASET order, of dev[item][rated item] ) / (number of ratings).
+// The lanes gather 32 deviations at a time into shared memory and every lane then adds them in
+// order (the reference's sequential float64 sum), so the result is bit-identical.
+constexpr int SLOPE_WARPS = 8;
+__global__ void __launch_bounds__(SLOPE_WARPS * 32) slope_predict_kernel(
+    const int32_t *__restrict__ left, const int32_t *__restrict__ right, int64_t n, double *__restrict__ out,
+    const int64_t *__restrict__ r_ptr, const int32_t *__restrict__ rd_col, const double *__restrict__ right_means,
+    const double *__restrict__ dev, int64_t ld, int64_t row_begin, int64_t row_end, int32_t n_left, int32_t n_right,
+    double global_mean, unsigned long long *work) {
+    __shared__ double s_d[SLOPE_WARPS][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(work, (unsigned long long)PRED_GRAB);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((int64_t)base >= n) break;
+        const int64_t w_end = (int64_t)base + PRED_GRAB < n ? (int64_t)base + PRED_GRAB : n;
+        for (int64_t p = (int64_t)base; p < w_end; p++) {
+            const int32_t item = left[p], user = right[p];
+            if (user < 0 || user >= n_right) {                       // unknown user: core/slope_one.go:30-32
+                if (lane == 0) out[p] = global_mean;
+                continue;
+            }
+            double prediction = right_means[user];
+            if (item < 0 || item >= n_left) {                        // unknown item: the user's mean
+                if (lane == 0) out[p] = prediction;
+                continue;
+            }
+            if (item < row_begin || item >= row_end) {               // not in this shard
+                if (lane == 0) out[p] = nan_v;
+                continue;
+            }
+            const double *row = dev + (item - row_begin) * ld;
+            const int64_t b = r_ptr[user], e = r_ptr[user + 1];
+            double sum = 0.0;
+            for (int64_t x0 = b; x0 < e; x0 += 32) {
+                const int64_t x = x0 + lane;
+                s_d[warp][lane] = x < e ? row[rd_col[x]] : 0.0;
+                __syncwarp();
+                const int lim = (e - x0) < 32 ? (int)(e - x0) : 32;
+                for (int t = 0; t < lim; t++) sum += s_d[warp][t];   // core/slope_one.go:36, in order
+                __syncwarp();
+            }
+            const double count = (double)(e - b);
+            if (count > 0) prediction += sum / count;                // core/slope_one.go:39-41
+            if (lane == 0) out[p] = prediction;
+        }
+    }
+}
+
 }  // namespace
 
 __global__ void iota_kernel(int32_t *out, int32_t n) {
@@ -726,6 +781,28 @@ extern "C" int32_t rs_knn_topk_union_device(int32_t n_lists, int64_t n_rows, int
     }
     topk_union_kernel<<<(unsigned)n_rows, TOPK_THREADS, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
         d_idx_all, d_sim_all, n_lists, n_rows, k, d_idx, d_sim);
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
+int32_t rs_slope_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_right, int64_t n, double *d_out) {
+    if (n <= 0) return RS_OK;
+    if (!h->rd_col || !h->right_means) {
+        rs_set_error("rs_knn_predict_batch: the handle was not fitted with RS_SIM_SLOPE_ONE");
+        return RS_ERR_INVALID;
+    }
+    void *work;
+    RS_TRY(rs_scratch_get(h, 16, 8, &work));
+    RS_CUDA(cudaMemsetAsync(work, 0, 8, h->stream));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    int64_t blocks = (n + SLOPE_WARPS * PRED_GRAB - 1) / (SLOPE_WARPS * PRED_GRAB);
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    slope_predict_kernel<<<(unsigned)blocks, SLOPE_WARPS * 32, 0, h->stream>>>(
+        d_left, d_right, n, d_out, h->r_ptr, h->rd_col, h->right_means, h->sims, h->ld_s, h->row_begin, h->row_end,
+        h->n_left, h->n_right, h->global_mean, reinterpret_cast<unsigned long long *>(work));
+    h->prof.predict_launches++;
+    h->prof.total_launches += 1;
     RS_CUDA(cudaGetLastError());
     return RS_OK;
 }

@@ -311,6 +311,20 @@ __global__ void triples_kernel(const int32_t *__restrict__ rcount, int32_t nr, u
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
+// Slope One: mean of every right row (user).  Integer ratings: the sum is exact in any order, so
+// one correctly rounded division reproduces core/data.go:222-235 whatever the order.
+__global__ void right_means_kernel(const int64_t *__restrict__ r_ptr, const double *__restrict__ r_val, int32_t nr,
+                                   double *__restrict__ out) {
+    const int32_t c = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= nr) return;
+    double s = 0.0;
+    for (int64_t x = r_ptr[c] + lane; x < r_ptr[c + 1]; x += 32) s += r_val[x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[c] = s / (double)(r_ptr[c + 1] - r_ptr[c]);
+}
+
 int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, const double *d_rating,
                       const double *d_left_bias, const double *d_right_bias) {
     cudaStream_t st = h->stream;
@@ -370,6 +384,13 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     gather_keys_kernel<<<blocks_for(nnz), T, 0, st>>>(d_right, perm_lr, nnz, keys_a);
     RS_SORT_PAIRS(keys_a, keys_b, perm_lr, perm_rl, nnz, rb);
     h->prof.total_launches += 2;  // own kernels only; CUB's sort/scan kernels are not counted
+    if (h->p.sim == RS_SIM_SLOPE_ONE) {
+        // SlopeOne.Predict sums dev[item][.] over the user's ratings in DATASET order
+        // (core/slope_one.go:35-38): perm_r is the stable sort by right id of the input rows
+        RS_TRY(rs_alloc(h, &h->rd_col, nnz));
+        gather_keys_kernel<<<blocks_for(nnz), T, 0, st>>>(d_left, perm_r, nnz, h->rd_col);
+        h->prof.total_launches++;
+    }
     h->perm_lr = perm_lr;         // kept for the stream tables (rs_prep_rt); keys_b is free from here on
     h->perm_rl = perm_rl;
     h->perm_tmp = keys_b;
@@ -457,6 +478,11 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
         h->prof.total_launches++;
     }
 
+    if (h->p.sim == RS_SIM_SLOPE_ONE) {
+        RS_TRY(rs_alloc(h, &h->right_means, (size_t)nr + 1));
+        right_means_kernel<<<blocks_for((int64_t)nr * 32), T, 0, st>>>(h->r_ptr, h->r_val, nr, h->right_means);
+        h->prof.total_launches++;
+    }
     if (d_left_bias) {
         RS_TRY(rs_alloc(h, &h->left_bias, (size_t)nl + 1));
         RS_CUDA(cudaMemcpyAsync(h->left_bias, d_left_bias, (size_t)nl * 8, cudaMemcpyDeviceToDevice, st));

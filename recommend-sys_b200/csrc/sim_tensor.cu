@@ -48,7 +48,7 @@ constexpr int TMEM_COLS = 512;
 // plane order in global and shared memory
 constexpr int PL_X2 = 0, PL_M = 1, PL_X = 2;
 
-enum { TC_COSINE = 0, TC_MSD = 1, TC_PEARSON = 2, TC_COSUMS = 3 };
+enum { TC_COSINE = 0, TC_MSD = 1, TC_PEARSON = 2, TC_COSUMS = 3, TC_SLOPE = 4 };
 
 // Per-mode tile shape.  Every tcgen05.mma reads its A slab (128 x 32 B) and B slab (N x 32 B) from
 // shared memory, so narrow instructions are shared-memory bound: 3 x N=64 (the first Cosine
@@ -74,6 +74,12 @@ template <> struct Cfg<TC_PEARSON> {
     static constexpr int C_SYY = 0, C_CNT = 64, C_SY = 128, C_SX = 192, C_SXY = 256, C_SXX = 320;
 };
 template <> struct Cfg<TC_COSUMS> : Cfg<TC_PEARSON> {};
+template <> struct Cfg<TC_SLOPE> {
+    // Slope One deviations (core/slope_one.go:71-90): count, Sy = M_I x [M|X]_J (N = 256), Sx = X_I x M_J
+    static constexpr int BN = 128, BK = 64, STAGES = 4;
+    static constexpr int ACC_COLS = 384, ACC_STAGES = 1;
+    static constexpr int C_CNT = 0, C_SY = 128, C_SX = 256, C_SYY = -1, C_SXY = -1, C_SXX = -1;
+};
 
 template <int MODE> struct Geo {
     using C = Cfg<MODE>;
@@ -400,6 +406,9 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             umma_i8(d0 + C::C_SYY, a_m, b_x2, make_idesc(BN), accum);
                             umma_i8(d0 + C::C_SXY, a_x, b_x, make_idesc(BN), accum);
                             umma_i8(d0 + C::C_SXX, a_x2, b_m, make_idesc(BN), accum);
+                        } else if constexpr (MODE == TC_SLOPE) {
+                            umma_i8(d0 + C::C_CNT, a_m, b_m, make_idesc(2 * BN), accum);    // [count | Sy]
+                            umma_i8(d0 + C::C_SX, a_x, b_m, make_idesc(BN), accum);         // Sx
                         } else if constexpr (MODE == TC_MSD) {
                             umma_i8(d0 + C::C_SYY, a_m, b_x2, make_idesc(2 * BN), accum);   // [Syy | count]
                             umma_i8(d0 + C::C_SYY, a_x2, b_m, make_idesc(BN), 1u);          // Syy += Sxx
@@ -439,8 +448,8 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 8) {
                 int32_t v_syy[8], v_sxy[8], v_sxx[8], v_cnt[8], v_sx[8], v_sy[8];
-                tmem_ld8(tbase + C::C_SYY + c0, v_syy);
-                tmem_ld8(tbase + C::C_SXY + c0, v_sxy);
+                if (C::C_SYY >= 0) tmem_ld8(tbase + (C::C_SYY >= 0 ? C::C_SYY : 0) + c0, v_syy);
+                if (C::C_SXY >= 0) tmem_ld8(tbase + (C::C_SXY >= 0 ? C::C_SXY : 0) + c0, v_sxy);
                 if (C::C_SXX >= 0) tmem_ld8(tbase + (C::C_SXX >= 0 ? C::C_SXX : 0) + c0, v_sxx);
                 if (C::C_CNT >= 0) tmem_ld8(tbase + (C::C_CNT >= 0 ? C::C_CNT : 0) + c0, v_cnt);
                 if (C::C_SX >= 0) {
@@ -466,7 +475,13 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     const int64_t j = j0 + c0 + c;
-                    if constexpr (MODE == TC_COSINE) {
+                    if constexpr (MODE == TC_SLOPE) {
+                        // core/slope_one.go:74-88: for i > j  dev[i][j] = sum(r_i - r_j) / count and
+                        // dev[j][i] = -dev[i][j]; untouched cells (no co-rating, the diagonal) stay +0
+                        const int32_t dbig = i > j ? v_sx[c] - v_sy[c] : v_sy[c] - v_sx[c];   // larger index minus smaller
+                        const double q = (double)dbig / (double)v_cnt[c];
+                        s[c] = (v_cnt[c] == 0 || i == j) ? 0.0 : (i > j ? q : -q);
+                    } else if constexpr (MODE == TC_COSINE) {
                         // core/sim.go:24  l / (sqrt(m) * sqrt(n)),  m = Sxx, n = Syy, l = Sxy
                         s[c] = (double)v_sxy[c] / (sqrt((double)v_sxx[c]) * sqrt((double)v_syy[c]));
                     } else if constexpr (MODE == TC_MSD) {
@@ -479,7 +494,7 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         s[c] = pearson_from_sums(v_cnt[c], v_sx[c], v_sy[c], v_sxx[c], v_syy[c], v_sxy[c], ca, sa,
                                                  cb, sb);
                     }
-                    if (j == i) s[c] = nan_v;   // diagonal stays unset (core/knn.go:202)
+                    if (MODE != TC_SLOPE && j == i) s[c] = nan_v;   // diagonal stays unset (core/knn.go:202)
                 }
                 // S[i][j0+c0 .. +8): 64 contiguous bytes per thread
                 if (row_ok) {
@@ -497,7 +512,11 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
                         const int64_t j = j0 + c0 + c;
-                        if (j < a.n_left) a.sims[j * a.ld_s + i] = s[c];
+                        // Slope One is antisymmetric: dev[j][i] = -dev[i][j], signed zeros included, but cells
+                        // that were never assigned (no co-rating) stay +0 on both sides
+                        double sm = s[c];
+                        if constexpr (MODE == TC_SLOPE) { if (v_cnt[c] != 0 && i != j) sm = -s[c]; }
+                        if (j < a.n_left) a.sims[j * a.ld_s + i] = sm;
                     }
                 }
                 }  // !COSUMS
@@ -897,6 +916,7 @@ int32_t launch_pair(rs_knn *h, const TcArgs &a) {
 template <int CI, int CJ>
 int32_t launch_shape(rs_knn *h, const TcArgs &a, bool cosums) {
     if (cosums) return launch_mode<TC_COSUMS, CI, CJ>(h, a);
+    if (h->p.sim == RS_SIM_SLOPE_ONE) return launch_mode<TC_SLOPE, CI, CJ>(h, a);
     if (h->p.sim == RS_SIM_COSINE) return launch_mode<TC_COSINE, CI, CJ>(h, a);
     if (h->p.sim == RS_SIM_MSD) return launch_mode<TC_MSD, CI, CJ>(h, a);
     if (h->p.sim == RS_SIM_PEARSON) return launch_mode<TC_PEARSON, CI, CJ>(h, a);
@@ -921,12 +941,16 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
     // L2 already serves the sharing, 2x1 (B tile multicast) is worth ~6 % for Cosine / MSD, larger
     // clusters lose to their own lockstep coupling, and Pearson is fastest unclustered.  Small
     // problems run unclustered so every SM gets a tile.  RS_KNN_TC_CLUSTER=1x1|1x2|2x1|... overrides.
-    const int mode = cosums ? TC_COSUMS : (h->p.sim == RS_SIM_COSINE ? TC_COSINE : h->p.sim == RS_SIM_MSD ? TC_MSD : TC_PEARSON);
-    const int BN = (mode == TC_COSINE || mode == TC_MSD) ? Cfg<TC_COSINE>::BN : Cfg<TC_PEARSON>::BN;
-    const int BK = (mode == TC_COSINE || mode == TC_MSD) ? Cfg<TC_COSINE>::BK : Cfg<TC_PEARSON>::BK;
-    static_assert(Cfg<TC_COSINE>::BN == Cfg<TC_MSD>::BN && Cfg<TC_COSINE>::BK == Cfg<TC_MSD>::BK, "host tile geometry");
+    const int mode = cosums ? TC_COSUMS
+                            : (h->p.sim == RS_SIM_COSINE ? TC_COSINE
+                               : h->p.sim == RS_SIM_MSD ? TC_MSD : h->p.sim == RS_SIM_SLOPE_ONE ? TC_SLOPE : TC_PEARSON);
+    const bool wide = mode == TC_COSINE || mode == TC_MSD || mode == TC_SLOPE;       // 128 x 128 tiles, 64-byte K blocks
+    const int BN = wide ? Cfg<TC_COSINE>::BN : Cfg<TC_PEARSON>::BN;
+    const int BK = wide ? Cfg<TC_COSINE>::BK : Cfg<TC_PEARSON>::BK;
+    static_assert(Cfg<TC_COSINE>::BN == Cfg<TC_MSD>::BN && Cfg<TC_COSINE>::BK == Cfg<TC_MSD>::BK &&
+                  Cfg<TC_COSINE>::BN == Cfg<TC_SLOPE>::BN && Cfg<TC_COSINE>::BK == Cfg<TC_SLOPE>::BK, "host tile geometry");
     const int64_t plain_tiles = ((re - rb + BM - 1) / BM) * ((h->n_left + BN - 1) / BN) / (mirror ? 2 : 1);
-    int ci = (mode == TC_COSINE || mode == TC_MSD) ? 2 : 1, cj = 1;
+    int ci = wide ? 2 : 1, cj = 1;
     if (plain_tiles < 4 * 148) { ci = 1; cj = 1; }
     // Cosine / MSD on large problems: the cta_group::2 pair kernel (256 x 128 tiles = the 2x1 cluster
     // tile of the list below).  RS_KNN_TC_PAIR=0|1 overrides.

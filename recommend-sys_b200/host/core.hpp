@@ -261,6 +261,47 @@ inline std::unique_ptr<KNN> NewKNNWithMean(const Parameters &p = {}) { return st
 inline std::unique_ptr<KNN> NewKNNWithZScore(const Parameters &p = {}) { return std::make_unique<KNN>("zscore", p); }
 inline std::unique_ptr<KNN> NewKNNBaseLine(const Parameters &p = {}) { return std::make_unique<KNN>("baseline", p); }
 
+// core/slope_one.go: deviation matrix on the device (RS_SIM_SLOPE_ONE), Predict as a
+// batch gather.  Fit with left = items, right = users.
+struct SlopeOne : Estimator {
+    const TrainSet *Data = nullptr;
+    explicit SlopeOne(const Parameters &p = {}) { Params = p; }
+    ~SlopeOne() override { Close(); }
+    void Close() { if (h_) { rs_knn_destroy(h_); h_ = nullptr; } }
+    void Fit(const TrainSet &t) override {  // core/slope_one.go:47-93
+        Data = &t;
+        Close();
+        rs_knn_params p;
+        rs_check(rs_knn_params_default(&p));
+        p.sim = RS_SIM_SLOPE_ONE;
+        p.device = Params.GetInt("device", -1);
+        rs_check(rs_knn_create(&p, &h_));
+        rs_check(rs_knn_fit(h_, t.innerItems.data(), t.innerUsers.data(), t.Ratings.data(), (int64_t)t.Length(),
+                            t.ItemCount, t.UserCount, t.GlobalMean, nullptr, nullptr, 0.0));
+    }
+    std::vector<double> PredictBatch(const std::vector<int64_t> &users, const std::vector<int64_t> &items) override {
+        std::vector<int32_t> l(users.size()), r(users.size());
+        for (size_t j = 0; j < users.size(); j++) {
+            l[j] = Data->ConvertItemID(items[j]);
+            r[j] = Data->ConvertUserID(users[j]);
+        }
+        std::vector<double> out(users.size());
+        rs_check(rs_knn_predict_batch(h_, l.data(), r.data(), (int64_t)l.size(), out.data()));
+        return out;
+    }
+    double Predict(int64_t u, int64_t i) override { return PredictBatch({u}, {i})[0]; }  // core/slope_one.go:22-45
+    std::vector<double> DevRows(int64_t row0, int64_t nrows) {  // backs SlopeOne.dev (core/slope_one.go:13)
+        std::vector<double> out((size_t)nrows * Data->ItemCount);
+        rs_check(rs_knn_sims_rows(h_, row0, nrows, out.data()));
+        return out;
+    }
+    std::unique_ptr<Estimator> Clone() const override { return std::make_unique<SlopeOne>(Params); }
+
+  private:
+    rs_knn *h_ = nullptr;
+};
+inline std::unique_ptr<SlopeOne> NewSlopeOne(const Parameters &p = {}) { return std::make_unique<SlopeOne>(p); }
+
 // core/utils.go:160-180 with the intended ([]float64, []float64) signature
 using Evaluator = std::function<double(const std::vector<double> &, const std::vector<double> &)>;
 inline double RMSE(const std::vector<double> &p, const std::vector<double> &t) {

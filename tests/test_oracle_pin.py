@@ -131,3 +131,26 @@ def test_als_baselines_extension_matches_numpy():
         bi = np.bincount(ii, weights=r - mu - bu[iu], minlength=ts.item_count) / (10.0 + ci)
         bu = np.bincount(iu, weights=r - mu - bi[ii], minlength=ts.user_count) / (15.0 + cu)
     assert np.abs(ub - bu).max() < 1e-12 and np.abs(ib - bi).max() < 1e-12
+
+
+def test_slope_one_bounds_ml100k(ml100k):
+    """core/base_test.go:46-48 — TestSlopeOne: 5-fold CV on ml-100k, RMSE <= 0.946 + 0.008 and
+    MAE <= 0.743 + 0.008 (the reference's own acceptance test pins the restatement of
+    core/slope_one.go)."""
+    rm, ma = [], []
+    for tr, te in _kfold(ml100k["u_data"], 5, 0):
+        so = ob.SlopeOne().fit(ob.TrainSet(*split(tr)))
+        u, i, r = split(te)
+        p = so.predict_batch(u, i)
+        rm.append(ob.rmse(p, r))
+        ma.append(ob.mae(p, r))
+    assert np.mean(rm) <= 0.946 + 0.008, np.mean(rm)
+    assert np.mean(ma) <= 0.743 + 0.008, np.mean(ma)
+    assert np.mean(rm) >= 0.946 - 0.03
+
+
+def test_slope_one_deviation_matrix_properties(ml100k):
+    so = ob.SlopeOne().fit(ob.TrainSet(*split(ml100k["u1_base"][:30000])))
+    d = so.dev()
+    assert np.array_equal(d, -d.T + 0.0) or np.array_equal(np.abs(d), np.abs(d.T))      # dev[j][i] = -dev[i][j]
+    assert (np.diag(d) == 0).all()                                                      # never assigned

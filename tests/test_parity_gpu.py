@@ -297,6 +297,37 @@ def test_als_baselines_extension(ml100k):
         rs.core._check(rs.core.knn_lib().rs_baseline_als(-1, None, None, None, 0, 1, 1, 0.0, 1.0, 1.0, 1, None, None))
 
 
+@pytest.mark.parametrize("fold", ["u1", "u5"])
+def test_slope_one_bit_exact(ml100k, fold):
+    """SURVEY.md §8 f-2 — core/slope_one.go on the device: the deviation matrix (integer co-rating
+    sums on the tensor cores) and SlopeOne.Predict, bit-identical to the restated reference, signed
+    zeros included; the reference's own acceptance bound (core/base_test.go:46-48) on the fold."""
+    u, i, r = split(ml100k[fold + "_base"])
+    ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
+    est = rs.NewSlopeOne(None)
+    est.Fit(ts)
+    ref = ob.SlopeOne().fit(ob.TrainSet(u, i, r))
+    got, want = est.dev, ref.dev()
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))       # bit for bit, -0.0 vs +0.0 too
+    tu, ti, tr_ = split(ml100k[fold + "_test"])
+    tu = np.concatenate([tu, [10 ** 9, tu[0], 10 ** 9]])                     # unknown user / item / both
+    ti = np.concatenate([ti, [ti[0], 10 ** 9, 10 ** 9]])
+    pg = rs.NewRawSet(tu, ti, np.zeros(len(tu))).Predict(est)
+    pw = ref.predict_batch(tu, ti)
+    assert bits_equal(pg, pw)
+    assert est.Predict(int(tu[5]), int(ti[5])) == pw[5]
+    assert rs.RMSE(pg[:len(tr_)], tr_) <= 0.946 + 0.03
+    # a row shard equals the full matrix's rows
+    n = got.shape[0]
+    part = rs.NewSlopeOne(rs.Parameters({"rowBegin": 256, "rowEnd": 640}))
+    part.Fit(ts)
+    assert np.array_equal(part.dev.view(np.uint64), want[256:640].view(np.uint64))
+    # non-integer ratings are refused loudly (tensor path only)
+    with pytest.raises(rs.core.RsError):
+        rs.NewSlopeOne(None).Fit(rs.NewTrainSet(rs.NewRawSet(u[:1000], i[:1000], r[:1000] + 0.5)))
+
+
 def test_errors_are_loud():
     left = np.array([0, 0, 1], dtype=np.int32)
     right = np.array([0, 0, 1], dtype=np.int32)
