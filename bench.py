@@ -51,8 +51,8 @@ WORKLOADS = {
     "ml20m_item_pearson_baseline_k40": (138_493, 26_744, 20_000_000, 4_000_000, "pearson_baseline", "baseline", False, 40),
     "ml20m_user_msd_k100": (138_493, 26_744, 20_000_000, 0, "msd", "basic", True, 100),
     # Slope One (core/slope_one.go) — item x item deviation matrix + full test-set Predict
-    "ml1m_slope_one": (6040, 3706, 1_000_000, 200_000, "slope_one", "basic", False, 0),
-    "ml20m_slope_one": (138_493, 26_744, 20_000_000, 4_000_000, "slope_one", "basic", False, 0),
+    "ml1m_slope_one": (6040, 3706, 1_000_000, 200_000, "slope_one", "basic", False, 40),   # k unused
+    "ml20m_slope_one": (138_493, 26_744, 20_000_000, 4_000_000, "slope_one", "basic", False, 40),
     "netflix_item_cosine_k50": (480_189, 17_770, 100_000_000, 20_000_000, "cosine", "basic", False, 50),
 }
 DEFAULT_WORKLOAD = "ml1m_item_pearson_k40"

@@ -606,8 +606,8 @@ __host__ __device__ constexpr uint32_t make_idesc_2sm(int n) {
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sim_tensor_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
-    static_assert(MODE == TC_COSINE || MODE == TC_MSD, "pair kernel: Cosine / MSD");
-    constexpr int C_SYY = 0, C_B = 128, C_C = 256;   // Cosine: Syy, Sxy, Sxx   MSD: Syy+Sxx, count, Sxy
+    static_assert(MODE == TC_COSINE || MODE == TC_MSD || MODE == TC_SLOPE, "pair kernel: Cosine / MSD / Slope One");
+    constexpr int C_SYY = 0, C_B = 128, C_C = 256;   // Cosine: Syy, Sxy, Sxx   MSD: Syy+Sxx, count, Sxy   Slope: count, Sy, Sx
     const int rank = (int)cluster_ctarank();         // 0 = even CTA = MMA issuer
     const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     extern __shared__ uint8_t smem_raw[];
@@ -706,7 +706,11 @@ sim_tensor_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                         const uint64_t b_x2 = make_desc<P_BK>(sb + PL_X2 * P_B_PLANE + ko);
                         const uint64_t b_m = make_desc<P_BK>(sb + PL_M * P_B_PLANE + ko);
                         const uint64_t b_x = make_desc<P_BK>(sb + PL_X * P_B_PLANE + ko);
-                        if constexpr (MODE == TC_COSINE) {
+                        if constexpr (MODE == TC_SLOPE) {
+                            umma_i8_2sm(d0 + C_SYY, a_m, b_m, make_idesc_2sm(P_BN), accum);    // count
+                            umma_i8_2sm(d0 + C_B, a_m, b_x, make_idesc_2sm(P_BN), accum);      // Sy
+                            umma_i8_2sm(d0 + C_C, a_x, b_m, make_idesc_2sm(P_BN), accum);      // Sx
+                        } else if constexpr (MODE == TC_COSINE) {
                             umma_i8_2sm(d0 + C_SYY, a_m, b_x2, make_idesc_2sm(P_BN), accum);   // Syy
                             umma_i8_2sm(d0 + C_B, a_x, b_x, make_idesc_2sm(P_BN), accum);      // Sxy
                             umma_i8_2sm(d0 + C_C, a_x2, b_m, make_idesc_2sm(P_BN), accum);     // Sxx
@@ -750,7 +754,12 @@ sim_tensor_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     const int64_t j = j0 + c0 + c;
-                    if constexpr (MODE == TC_COSINE) {
+                    if constexpr (MODE == TC_SLOPE) {
+                        // core/slope_one.go:74-88 (see the single-CTA epilogue): v_a = count, v_b = Sy, v_c = Sx
+                        const int32_t dbig = i > j ? v_c[c] - v_b[c] : v_b[c] - v_c[c];
+                        const double q = (double)dbig / (double)v_a[c];
+                        s[c] = (v_a[c] == 0 || i == j) ? 0.0 : (i > j ? q : -q);
+                    } else if constexpr (MODE == TC_COSINE) {
                         // core/sim.go:24  l / (sqrt(m) * sqrt(n)),  m = Sxx, n = Syy, l = Sxy
                         s[c] = (double)v_b[c] / (sqrt((double)v_c[c]) * sqrt((double)v_a[c]));
                     } else {
@@ -758,7 +767,7 @@ sim_tensor_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                         const int32_t sum = v_a[c] - 2 * v_c[c];
                         s[c] = 1.0 / ((double)sum / (double)v_b[c] + 1.0);
                     }
-                    if (j == i) s[c] = nan_v;   // diagonal stays unset (core/knn.go:202)
+                    if (MODE != TC_SLOPE && j == i) s[c] = nan_v;   // diagonal stays unset (core/knn.go:202)
                 }
                 if (row_ok) {
                     double *o = a.sims + (i - a.row_begin) * a.ld_s + j0 + c0;
@@ -774,7 +783,9 @@ sim_tensor_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
                         const int64_t j = j0 + c0 + c;
-                        if (j < a.n_left) a.sims[j * a.ld_s + i] = s[c];
+                        double sm = s[c];
+                        if constexpr (MODE == TC_SLOPE) { if (v_a[c] != 0 && i != j) sm = -s[c]; }   // antisymmetric
+                        if (j < a.n_left) a.sims[j * a.ld_s + i] = sm;
                     }
                 }
             }
@@ -954,8 +965,8 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
     if (plain_tiles < 4 * 148) { ci = 1; cj = 1; }
     // Cosine / MSD on large problems: the cta_group::2 pair kernel (256 x 128 tiles = the 2x1 cluster
     // tile of the list below).  RS_KNN_TC_PAIR=0|1 overrides.
-    bool use_pair = (mode == TC_COSINE || mode == TC_MSD) && ci == 2 && cj == 1;
-    if (const char *e = getenv("RS_KNN_TC_PAIR")) use_pair = (mode == TC_COSINE || mode == TC_MSD) && atoi(e) != 0;
+    bool use_pair = wide && ci == 2 && cj == 1;
+    if (const char *e = getenv("RS_KNN_TC_PAIR")) use_pair = wide && atoi(e) != 0;
     if (use_pair) { ci = 2; cj = 1; }
     if (const char *e = getenv("RS_KNN_TC_CLUSTER")) {
         if (use_pair) {}
@@ -1030,7 +1041,8 @@ int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int
     if (const char *e = getenv("RS_KNN_TC_SYNC")) sscanf(e, "%d,%d,%d", &a.sync_chunk, &a.sync_slack, &a.sync_timeout);
     if (a.sync_chunk > 0) RS_CUDA(cudaMemsetAsync(a.progress, 0, 8, h->stream));
     int32_t rc;
-    if (use_pair) rc = mode == TC_COSINE ? launch_pair<TC_COSINE>(h, a) : launch_pair<TC_MSD>(h, a);
+    if (use_pair) rc = mode == TC_COSINE ? launch_pair<TC_COSINE>(h, a)
+                       : mode == TC_MSD ? launch_pair<TC_MSD>(h, a) : launch_pair<TC_SLOPE>(h, a);
     else if (ci == 1 && cj == 1) rc = launch_shape<1, 1>(h, a, cosums);
     else if (ci == 1 && cj == 2) rc = launch_shape<1, 2>(h, a, cosums);
     else if (ci == 2 && cj == 1) rc = launch_shape<2, 1>(h, a, cosums);

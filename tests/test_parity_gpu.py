@@ -297,11 +297,13 @@ def test_als_baselines_extension(ml100k):
         rs.core._check(rs.core.knn_lib().rs_baseline_als(-1, None, None, None, 0, 1, 1, 0.0, 1.0, 1.0, 1, None, None))
 
 
+@pytest.mark.parametrize("pair", ["0", "1"])
 @pytest.mark.parametrize("fold", ["u1", "u5"])
-def test_slope_one_bit_exact(ml100k, fold):
+def test_slope_one_bit_exact(ml100k, fold, pair, monkeypatch):
     """SURVEY.md §8 f-2 — core/slope_one.go on the device: the deviation matrix (integer co-rating
     sums on the tensor cores) and SlopeOne.Predict, bit-identical to the restated reference, signed
     zeros included; the reference's own acceptance bound (core/base_test.go:46-48) on the fold."""
+    monkeypatch.setenv("RS_KNN_TC_PAIR", pair)      # single-CTA / cta_group::2 pair kernel
     u, i, r = split(ml100k[fold + "_base"])
     ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
     est = rs.NewSlopeOne(None)
