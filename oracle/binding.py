@@ -107,6 +107,8 @@ def lib():
     L.or_slope_predict.restype = C.c_double
     L.or_slope_predict.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     L.or_slope_predict_batch.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64, pd]
+    L.or_rows_sims.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_int64, pd]
+    L.or_rows_sims.restype = None
     L.or_baseline_als.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, pd, pd]
     L.or_baseline_als.restype = None
     L.or_rmse.restype = C.c_double
@@ -313,4 +315,14 @@ class SlopeOne:
         lib().or_slope_predict_batch(self.h, _p(users, C.c_int64), _p(items, C.c_int64), len(users),
                                      _p(out, C.c_double))
         return out
+
+
+def rows_sims(train: TrainSet, sim: str, user_based: bool, rows):
+    """Similarities of the given left rows against all N (n_rows x N), for shapes too large for the
+    N x N matrix."""
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    n = train.user_count if user_based else train.item_count
+    out = np.empty((len(rows), n), dtype=np.float64)
+    lib().or_rows_sims(train.h, SIM[sim], int(user_based), _p(rows, C.c_int64), len(rows), _p(out, C.c_double))
+    return out
 

@@ -950,3 +950,24 @@ void or_slope_predict_batch(const or_slope *s, const int64_t *users, const int64
     for (int64_t x = 0; x < n; x++) out[x] = or_slope_predict(s, users[x], items[x]);
 }
 
+/* =====================================================================================
+ * Test helper for shapes whose N x N matrix does not fit in host memory (BASELINE config 4:
+ * 138,493 users): the similarities of a handful of left rows against all N, straight from
+ * core/sim.go on lists sorted by id (core/knn.go:190), with the diagonal and "no co-rating"
+ * cells NaN as KNN.Fit leaves them.  Cosine / MSD / Pearson only.
+ * ===================================================================================== */
+void or_rows_sims(or_trainset *t, int sim, int user_based, const int64_t *rows, int64_t n_rows, double *out) {
+    or_idrating **lr, *store;
+    int64_t *len;
+    const int64_t n = user_based ? t->user_count : t->item_count;
+    if (user_based) build_adjacency(t->n, t->user_count, t->iu, t->ii, t->ratings, &lr, &len, &store);
+    else build_adjacency(t->n, t->item_count, t->ii, t->iu, t->ratings, &lr, &len, &store);
+    for (int64_t i = 0; i < n; i++) or_sort_by_id(lr[i], len[i]);
+    for (int64_t r = 0; r < n_rows; r++) {
+        const int64_t i = rows[r];
+        for (int64_t j = 0; j < n; j++)
+            out[r * n + j] = (i == j) ? NAN : or_sim_lists(sim, lr[i], len[i], lr[j], len[j]);
+    }
+    free(lr); free(len); free(store);
+}
+

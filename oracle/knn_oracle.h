@@ -153,6 +153,10 @@ const double *or_slope_user_means(const or_slope *s);
 double or_slope_predict(const or_slope *s, int64_t raw_user, int64_t raw_item);
 void or_slope_predict_batch(const or_slope *s, const int64_t *users, const int64_t *items, int64_t n, double *out);
 
+/* Similarities of a few left rows against all N (test helper for shapes whose N x N matrix does not
+ * fit in host memory); out is n_rows x N, NaN on the diagonal and where there is no co-rating. */
+void or_rows_sims(or_trainset *t, int sim, int user_based, const int64_t *rows, int64_t n_rows, double *out);
+
 #ifdef __cplusplus
 }
 #endif

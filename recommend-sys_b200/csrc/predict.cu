@@ -428,8 +428,12 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_rows_kernel(const double *_
             pos[slot] = (uint32_t)j;
         }
         __syncthreads();
-        if (s_have > TOPK_CAP - TOPK_THREADS) {
-            const int have = s_have;
+        // every thread must see the SAME count: read it, then a second barrier before anybody's next
+        // atomicAdd can change it (otherwise a slow thread may take the branch below alone)
+        const int have_now = s_have;
+        __syncthreads();
+        if (have_now > TOPK_CAP - TOPK_THREADS) {
+            const int have = have_now;
             for (int t = have + threadIdx.x; t < TOPK_CAP; t += blockDim.x) { keys[t] = 0; pos[t] = 0xffffffffu; }
             block_bitonic(keys, pos, TOPK_CAP);
             if (threadIdx.x == 0) {
@@ -514,8 +518,12 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_merge_kernel(const double *
             pos[slot] = (uint32_t)j + id_off;
         }
         __syncthreads();
-        if (s_have > TOPK_CAP - TOPK_THREADS) {
-            const int have = s_have;
+        // every thread must see the SAME count: read it, then a second barrier before anybody's next
+        // atomicAdd can change it (otherwise a slow thread may take the branch below alone)
+        const int have_now = s_have;
+        __syncthreads();
+        if (have_now > TOPK_CAP - TOPK_THREADS) {
+            const int have = have_now;
             for (int t = have + threadIdx.x; t < TOPK_CAP; t += blockDim.x) { keys[t] = 0; pos[t] = 0xffffffffu; }
             block_bitonic(keys, pos, TOPK_CAP);
             if (threadIdx.x == 0) {

@@ -460,3 +460,43 @@ def test_ml20m_shape_properties():
     cos_s = rs.NewKNN(rs.Parameters({"sim": rs.Cosine, "userBased": False, "simPath": "stream"}))
     cos_s.Fit(train)
     assert bits_equal(T1, cos_s._h.sims_rows(a0, 256))
+
+
+def test_config4_shape_symmetric_slab_topk():
+    """BASELINE.json config 4 at FULL size: user-based MSD, k = 100, MovieLens-20M shape (138,493 users,
+    9.6e9 pairs; the 153 GB matrix never exists).  Neighbour lists from the symmetric-slab Fit — one
+    shard, and two shards on one GPU united with rs_knn_topk_union_device — against rows computed by
+    the oracle straight from core/sim.go: indices and similarities bit for bit."""
+    import torch
+
+    from recommend_sys_b200.shard import union_topk_device
+
+    d = rs.core.synth_ratings(138_493, 26_744, 20_000_000, 0x5EED0004)
+    train = rs.NewTrainSet(d)
+    n, k = train.UserCount, 100
+    base = {"sim": rs.MSD, "userBased": True, "store": "topk", "topk": k}
+    one = rs.NewKNN(rs.Parameters(dict(base, shardCount=1)))
+    one.Fit(train)
+    gi, gs = one.TopK(k)
+    one.Close()
+    assert gi.shape == (n, k)
+    rows = np.array([0, 1, 777, 5000, 65535, 65536, 100_000, n - 2, n - 1], dtype=np.int64)
+    S = ob.rows_sims(ob.TrainSet(train.Users, train.Items, train.Ratings), "msd", True, rows)
+    for x, row in enumerate(rows):
+        s = S[x]
+        ok = np.where(~np.isnan(s))[0]
+        order = ok[np.lexsort((ok, -s[ok]))][:k]                      # similarity desc, inner id asc
+        assert np.array_equal(gi[row][:len(order)], order), row
+        assert bits_equal(gs[row][:len(order)], s[order]), row
+        assert (gi[row][len(order):] == -1).all()
+    parts = []
+    for rank in range(2):
+        p = rs.NewKNN(rs.Parameters(dict(base, shardCount=2, shardIndex=rank)))
+        p.Fit(train)
+        parts.append(p.TopK(k))
+        p.Close()
+    ui, us = union_topk_device(torch.from_numpy(np.stack([a for a, _ in parts])).cuda(),
+                               torch.from_numpy(np.stack([b for _, b in parts])).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(ui.cpu().numpy(), gi) and bits_equal(us.cpu().numpy(), gs)
+
