@@ -500,3 +500,27 @@ def test_config4_shape_symmetric_slab_topk():
     torch.cuda.synchronize()
     assert np.array_equal(ui.cpu().numpy(), gi) and bits_equal(us.cpu().numpy(), gs)
 
+
+
+def test_netflix_shape_tensor_stream_oracle():
+    """BASELINE.json config 5 at FULL size (item-based Cosine on the Netflix-Prize shape: 480,189 users x
+    17,770 items, 100 M ratings; K = 480 k is the longest contraction of any config): the CTA-pair tensor
+    kernel and the exact sparse replay agree bit for bit on a slab, and both agree with oracle rows
+    straight from core/sim.go."""
+    d = rs.core.synth_ratings(480_189, 17_770, 100_000_000, 0x5EED0005)
+    train = rs.NewTrainSet(d)
+    n = train.ItemCount
+    a = rs.NewKNN(rs.Parameters({"sim": rs.Cosine, "userBased": False, "simPath": "tensor"}))
+    a.Fit(train)
+    assert a.Profile()["sim_path_used"] == rs.core.RS_SIM_PATH["tensor"]
+    T = a._h.sims_rows(3000, 256)
+    T2 = a._h.sims_rows(n - 200, 200)
+    a.Close()
+    b = rs.NewKNN(rs.Parameters({"sim": rs.Cosine, "userBased": False, "simPath": "stream"}))
+    b.Fit(train)
+    assert bits_equal(T, b._h.sims_rows(3000, 256))
+    assert bits_equal(T2, b._h.sims_rows(n - 200, 200))
+    b.Close()
+    rows = np.array([3000, 3100, n - 1], dtype=np.int64)
+    S = ob.rows_sims(ob.TrainSet(train.Users, train.Items, train.Ratings), "cosine", False, rows)
+    assert bits_equal(T[[0, 100]], S[:2]) and bits_equal(T2[-1:], S[2:])
