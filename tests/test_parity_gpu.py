@@ -460,6 +460,64 @@ def test_ml20m_shape_properties():
     cos_s = rs.NewKNN(rs.Parameters({"sim": rs.Cosine, "userBased": False, "simPath": "stream"}))
     cos_s.Fit(train)
     assert bits_equal(T1, cos_s._h.sims_rows(a0, 256))
+    cos_s.Close()
+    est.Close()
+    # Pearson from the six integer sums on the tensor cores (K = 138 k) against the exact replay
+    ps = rs.NewKNN(rs.Parameters({"sim": rs.Pearson, "userBased": False, "pearsonMode": "sums", "simPath": "tensor"}))
+    ps.Fit(train)
+    assert ps.Profile()["sim_path_used"] == rs.core.RS_SIM_PATH["tensor"]
+    P = ps._h.sims_rows(a0, m)
+    ps.Close()
+    assert np.array_equal(np.isnan(P), np.isnan(A))
+    okp = ~np.isnan(A)
+    assert (np.abs(P[okp] - A[okp]) <= 1e-9 * np.maximum(1.0, np.abs(A[okp]))).all()
+    # ALS baselines (extension) at full size: device == oracle bit for bit
+    bl = rs.NewBaseLine(rs.Parameters({"baseline": "als"}))
+    bl.Fit(train)
+    oub, oib, _ = ob.TrainSet(train.Users, train.Items, train.Ratings).baseline_als()
+    assert bits_equal(bl.userBias, oub) and bits_equal(bl.itemBias, oib)
+    # Slope One at full size: cells against a direct evaluation of core/slope_one.go:74-88
+    so = rs.NewSlopeOne(None)
+    so.Fit(train)
+    D = so._h.sims_rows(a0, 64)
+    by_item = {}
+    iu, ii, rr = train.innerUsers, train.innerItems, train.Ratings
+    rng = np.random.RandomState(3)
+    pairs = [(a0 + int(x), int(y)) for x, y in zip(rng.randint(0, 64, 40), rng.randint(0, n, 40))] + [(a0 + 3, a0 + 3)]
+    for i_, j_ in pairs:
+        for t_ in (i_, j_):
+            if t_ not in by_item:
+                sel = np.where(ii == t_)[0]
+                by_item[t_] = dict(zip(iu[sel].tolist(), rr[sel].tolist()))
+        common = sorted(set(by_item[i_]) & set(by_item[j_]))
+        if i_ == j_ or not common:
+            want = 0.0
+        else:
+            big, small = max(i_, j_), min(i_, j_)
+            ssum = 0.0
+            for u_ in common:                       # ascending user id, as the merge walks them
+                ssum += by_item[big][u_] - by_item[small][u_]
+            want = ssum / float(len(common))
+            if i_ < j_:
+                want = -want
+        assert D[i_ - a0, j_] == want and np.signbit(D[i_ - a0, j_]) == np.signbit(want), (i_, j_)
+    E_ = so._h.sims_rows(b0, 64)
+    assert np.array_equal(D[:, b0:b0 + 64], -E_[:, a0:a0 + 64].T + 0.0) or \
+        np.array_equal(np.abs(D[:, b0:b0 + 64]), np.abs(E_[:, a0:a0 + 64].T))       # antisymmetric
+    # SlopeOne.Predict for pairs whose item row is in the slab: sequential sum in dataset order
+    tu = train.convert_users(test.Users)
+    ti = train.convert_items(test.Items)
+    sel = np.where((ti >= a0) & (ti < a0 + 64) & (tu >= 0))[0][:40]
+    got = so.PredictBatch(test.Users[sel], test.Items[sel])
+    cnt = np.bincount(iu, minlength=train.UserCount)
+    for x, q in enumerate(sel):
+        rows_u = np.where(iu == tu[q])[0]                               # dataset order
+        ssum = 0.0
+        for it_ in ii[rows_u]:
+            ssum += D[ti[q] - a0, it_]
+        want = float(np.add.reduce(rr[rows_u]) / len(rows_u)) + ssum / float(len(rows_u))
+        assert got[x] == want, (q, got[x], want)
+    so.Close()
 
 
 def test_config4_shape_symmetric_slab_topk():
