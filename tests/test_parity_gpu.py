@@ -568,11 +568,34 @@ def test_netflix_shape_tensor_stream_oracle():
     d = rs.core.synth_ratings(480_189, 17_770, 100_000_000, 0x5EED0005)
     train = rs.NewTrainSet(d)
     n = train.ItemCount
-    a = rs.NewKNN(rs.Parameters({"sim": rs.Cosine, "userBased": False, "simPath": "tensor"}))
+    a = rs.NewKNN(rs.Parameters({"sim": rs.Cosine, "userBased": False, "simPath": "tensor", "k": 50}))
     a.Fit(train)
     assert a.Profile()["sim_path_used"] == rs.core.RS_SIM_PATH["tensor"]
     T = a._h.sims_rows(3000, 256)
     T2 = a._h.sims_rows(n - 200, 200)
+    # KNN.Predict (k = 50) for item 3000 and users of very different activity, restated here from
+    # core/knn.go:75-141 on the device's own similarity row (canonical tie rule)
+    iu, ii, rr = train.innerUsers, train.innerItems, train.Ratings
+    deg = np.bincount(iu, minlength=train.UserCount)
+    users = [int(np.argmax(deg)), int(np.argsort(deg)[len(deg) // 2]), int(np.argmin(deg)), 12345, 400_000]
+    raw_item = int(train.Items[np.where(ii == 3000)[0][0]])
+    raw_users = [int(train.Users[np.where(iu == u_)[0][0]]) for u_ in users]
+    got = a.PredictBatch(np.array(raw_users), np.array([raw_item] * len(users)))
+    for x, u_ in enumerate(users):
+        sel = np.where(iu == u_)[0]
+        ids, rat = ii[sel], rr[sel]
+        sv = T[0][ids]
+        ok = ~np.isnan(sv)
+        if ok.sum() <= 1:
+            want = train.GlobalMean
+        else:
+            order = np.lexsort((ids[ok], -(sv[ok] + 0.0)))[:50]
+            ws = wr = 0.0
+            for t_ in order:
+                ws += sv[ok][t_]
+                wr += sv[ok][t_] * rat[ok][t_]
+            want = wr / ws
+        assert got[x] == want, (u_, got[x], want)
     a.Close()
     b = rs.NewKNN(rs.Parameters({"sim": rs.Cosine, "userBased": False, "simPath": "stream"}))
     b.Fit(train)
