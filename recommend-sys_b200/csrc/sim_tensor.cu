@@ -18,7 +18,7 @@
 //               TMA 4-D boxes (BK bytes of K x rows, one plane per instruction) land one pipeline stage with SWIZZLE_128B (BK = 128,
 //               Pearson: 3 stages x 72 KB) or SWIZZLE_64B (BK = 64, Cosine / MSD: 4 stages x 48 KB)
 //   pipeline  = mbarrier full/empty ring; warp 0 lane 0 issues TMA, warp 1 lane 0 issues
-//               tcgen05.mma, warps 2-5 run the epilogue (tcgen05.ld -> FP64 -> HBM)
+//               tcgen05.mma, warps 2-9 run the epilogue (tcgen05.ld -> FP64 -> HBM)
 //   MMAs      = the B planes of a stage are adjacent in shared memory in the order (X2, M, X), so
 //               products that share an A plane are ONE instruction with a wider N:
 //                 Pearson: M_I x [X2|M|X]_J (N=192), X_I x [M|X]_J (N=128), X2_I x M_J (N=64)
@@ -42,7 +42,12 @@
 namespace {
 
 constexpr int BM = RS_TC_BM;   // 128 left rows per tile (MMA M, TMEM lanes)
-constexpr int NUM_THREADS = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+// warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..9 epilogue.  Eight epilogue warps: a warp can only read the
+// TMEM lane quarter (warp % 4), so two warps share each quarter and take half of the tile's columns each —
+// with single-buffered accumulators the epilogue is exposed, and on short contractions (K of a few
+// thousand) its FP64 divisions and square roots cost more than the MMAs of the tile.
+constexpr int NUM_THREADS = 320;
+constexpr int EPI_THREADS = 256;
 constexpr int TMEM_COLS = 512;
 
 // plane order in global and shared memory
@@ -312,7 +317,7 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(tfull_bar + 8 * s, 1);
-            mbar_init(tempty_bar + 8 * s, 128);
+            mbar_init(tempty_bar + 8 * s, EPI_THREADS);
         }
         fence_barrier_init();
     }
@@ -429,8 +434,9 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
         }
     } else {
-        // ======================= epilogue (4 warps, TMEM lane quarter = warp % 4) =======================
+        // ======================= epilogue (8 warps: TMEM lane quarter = warp % 4, column half = (warp-2)/4) =======================
         const int q = warp & 3;
+        const int chalf = (warp - 2) >> 2;          // which half of the tile's columns this warp converts
         const int r_in_tile = q * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -446,7 +452,7 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (MODE == TC_PEARSON && i < a.n_left) { ca = a.row_cnt[i]; sa = a.row_sum[i]; }
             const bool row_ok = (i < a.n_left) && (i >= a.row_begin) && (i < a.row_end);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 8) {
+            for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 8) {
                 int32_t v_syy[8], v_sxy[8], v_sxx[8], v_cnt[8], v_sx[8], v_sy[8];
                 if (C::C_SYY >= 0) tmem_ld8(tbase + (C::C_SYY >= 0 ? C::C_SYY : 0) + c0, v_syy);
                 if (C::C_SXY >= 0) tmem_ld8(tbase + (C::C_SXY >= 0 ? C::C_SXY : 0) + c0, v_sxy);
@@ -522,7 +528,7 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }  // !COSUMS
             }
             tc_fence_before();
-            mbar_arrive(tempty_bar + 8 * acc);     // 128 arrivals release the accumulator buffer
+            mbar_arrive(tempty_bar + 8 * acc);     // 256 arrivals release the accumulator buffer
             if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         }
     }
@@ -550,7 +556,7 @@ sim_tensor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 //                        CTA's producer posts the expected bytes of both
 //             empty[s] : one per CTA; tcgen05.commit.cta_group::2 multicast to both
 //             tfull    : one per CTA (commit multicast) -> each CTA's epilogue reads ITS 128 TMEM lanes
-//             tempty   : even CTA only, 256 arrivals (both epilogues; the odd one arrives remotely)
+//             tempty   : even CTA only, 512 arrivals (both epilogues; the odd one arrives remotely)
 // Accumulator columns: Cosine [Syy | Sxy | Sxx], MSD [Syy+Sxx | count | Sxy] (N = 128 each; the wide
 // N = 256 combination of the single-CTA kernel is not available because the pair splits B by rows).
 namespace pair {
@@ -631,7 +637,7 @@ sim_tensor_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             mbar_init(empty_bar + 8 * s, 1);
         }
         mbar_init(tfull_bar, 1);
-        mbar_init(tempty_bar, 256);
+        mbar_init(tempty_bar, 2 * EPI_THREADS);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
@@ -731,6 +737,7 @@ sim_tensor_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     } else {
         // ======================= epilogue (both CTAs: own 128 TMEM lanes) =======================
         const int q = warp & 3;
+        const int chalf = (warp - 2) >> 2;          // which half of the tile's columns this warp converts
         const int r_in_tile = q * 32 + lane;
         uint32_t acc_phase = 0;
         const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
@@ -744,7 +751,7 @@ sim_tensor_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
             const bool row_ok = (i < a.n_left) && (i >= a.row_begin) && (i < a.row_end);
 #pragma unroll 1
-            for (int c0 = 0; c0 < P_BN; c0 += 8) {
+            for (int c0 = chalf * (P_BN / 2); c0 < (chalf + 1) * (P_BN / 2); c0 += 8) {
                 int32_t v_a[8], v_b[8], v_c[8];
                 tmem_ld8(tbase + C_SYY + c0, v_a);
                 tmem_ld8(tbase + C_B + c0, v_b);
@@ -790,7 +797,7 @@ sim_tensor_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 }
             }
             tc_fence_before();
-            mbar_arrive_cluster(tempty_leader);    // 2 x 128 arrivals release the accumulators of the pair
+            mbar_arrive_cluster(tempty_leader);    // 2 x 256 arrivals release the accumulators of the pair
             acc_phase ^= 1u;
         }
     }
