@@ -30,6 +30,7 @@ func main() {
 		algo core.Estimator
 	}
 	estimators := []entry{
+		{"Slope One", core.NewSlopeOne(nil)},
 		{"KNN", core.NewKNN(nil)},
 		{"Centered K-NN", core.NewKNNWithMean(nil)},
 		{"K-NN Baseline", core.NewKNNBaseLine(nil)},

@@ -1,5 +1,5 @@
 // benchmark.cc — the compiled counterpart of the reference's benchmark.go (benchmark.go:12-52)
-// for the path in scope: the four KNN estimators through 5-fold cross-validation with
+// for the path in scope: Slope One and the four KNN estimators through 5-fold cross-validation with
 // params = nil (user-based MSD, k = 40, core/knn.go:79-81,145-148), one table row each:
 // Name / RMSE / MAE / Time — plus the hot-path device times the library measured.
 //
@@ -45,8 +45,9 @@ int main(int argc, char **argv) {
         std::fprintf(stderr, "usage: %s <ratings.tsv> | --synthetic USERS ITEMS NNZ\n", argv[0]);
         return 2;
     }
-    struct Row { const char *name; std::unique_ptr<core::KNN> algo; };
-    Row rows[4] = {{"KNN", core::NewKNN()}, {"Centered K-NN", core::NewKNNWithMean()},
+    struct Row { const char *name; std::unique_ptr<core::Estimator> algo; };
+    Row rows[5] = {{"Slope One", core::NewSlopeOne()},      // benchmark.go:26
+                   {"KNN", core::NewKNN()}, {"Centered K-NN", core::NewKNNWithMean()},
                    {"K-NN Baseline", core::NewKNNBaseLine()}, {"K-NN Z-Score", core::NewKNNWithZScore()}};
     std::printf("%-16s %10s %10s %12s\n", "Name", "RMSE", "MAE", "Time");
     for (auto &r : rows) {
