@@ -77,6 +77,30 @@ def test_metrics_match_oracle():
     assert abs(rs.MAE(p, t) - ob.mae(p, t)) < 1e-12
 
 
+def test_metric_known_answers():
+    """core/eval_test.go:32-46 — TestRMSE / TestMAE, the reference's own vectors (tolerance 1e-5), on the
+    host mirror and on the oracle."""
+    a, b = [-2.0, 0.0, 2.0], [0.0, 0.0, 0.0]
+    for rmse, mae in ((rs.RMSE, rs.MAE), (ob.rmse, ob.mae)):
+        assert abs(rmse(np.array(a), np.array(b)) - 1.63299) < 1e-5
+        assert abs(mae(np.array(a), np.array(b)) - 1.33333) < 1e-5
+
+
+def test_slab_owner_deals_every_slab_once_and_evenly():
+    from recommend_sys_b200.shard import slab_owner
+
+    for world in (1, 2, 3, 8):
+        for n_slabs in (1, 5, 25, 64):
+            owners = [slab_owner(s, world) for s in range(n_slabs)]
+            assert all(0 <= o < world for o in owners)
+            # slab s costs ~ (n_slabs - s): the snake deal keeps the shares within one round of each other
+            cost = np.zeros(world)
+            for s_, o in enumerate(owners):
+                cost[o] += n_slabs - s_
+            if n_slabs >= 4 * world:
+                assert cost.max() / cost.mean() < 1.12, (world, n_slabs, cost)
+
+
 def test_shard_rows_cover_everything():
     from recommend_sys_b200.shard import shard_rows
 
