@@ -383,6 +383,7 @@ def run_ours(args, rank, world, local_rank):
         out = e2e_test.Predict(est) if n_test else None
         if sym:     # the result of a top-k-only Fit is the neighbour lists: united across ranks, read to the host
             est._h.topk_device(k, d_tk_i.data_ptr(), d_tk_s.data_ptr())
+            est._h.synchronize()     # the estimator works on its own stream; the union below on torch's
             li, ls = (union_topk_device(*allgather_partial_topk(d_tk_i, d_tk_s)) if world > 1 else (d_tk_i, d_tk_s))
             out = (li.cpu(), ls.cpu())
         est.Close()

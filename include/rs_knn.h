@@ -139,7 +139,10 @@ int32_t rs_knn_set_stream(rs_knn *h, void *cuda_stream, int32_t use_own);
  *   global_mean       TrainSet.GlobalMean (core/data.go:134)
  *   left_bias         Bias of the left side for RS_KNN_BASELINE (core/knn.go:179-187), else NULL
  *   right_bias,global_bias  only for RS_SIM_PEARSON_BASELINE (both bias vectors), else NULL/0
- * Host pointers; copied to the device inside the call. */
+ * Host pointers; copied to the device inside the call, and free to reuse when it returns.  The call
+ * returns once the inputs are consumed and validated (errors in the data are reported here); the
+ * similarity kernel may still be running — every call that needs its result is ordered behind it on
+ * the handle's stream, and rs_knn_synchronize waits for it explicitly. */
 int32_t rs_knn_fit(rs_knn *h, const int32_t *left, const int32_t *right, const double *rating,
                    int64_t nnz, int32_t n_left, int32_t n_right, double global_mean,
                    const double *left_bias, const double *right_bias, double global_bias);

@@ -165,6 +165,8 @@ int32_t rs_knn_create(const rs_knn_params *p, rs_knn **out) {
     h->device = dev;
     RS_CUDA(cudaSetDevice(dev));
     RS_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    RS_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    RS_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
     h->stream = h->own_stream;
     RS_CUDA(cudaEventCreate(&h->ev_a));
     RS_CUDA(cudaEventCreate(&h->ev_b));
@@ -191,6 +193,8 @@ int32_t rs_knn_destroy(rs_knn *h) {
     cudaEventDestroy(h->ev_d);
     cudaEventDestroy(h->ev_e);
     cudaStreamDestroy(h->own_stream);
+    cudaStreamDestroy(h->aux_stream);
+    cudaEventDestroy(h->ev_in);
     delete h;
     return RS_OK;
 }
@@ -429,11 +433,16 @@ int32_t rs_knn_fit(rs_knn *h, const int32_t *left, const int32_t *right, const d
         RS_TRY(rs_scratch_get(h, 11, (size_t)n_right * 8, &d_rb));
         RS_CUDA(cudaMemcpyAsync(d_rb, right_bias, (size_t)n_right * 8, cudaMemcpyHostToDevice, h->stream));
     }
+    RS_CUDA(cudaEventRecord(h->ev_in, h->stream));
     RS_TRY(rs_knn_fit_device(h, (const int32_t *)d_left, (const int32_t *)d_right, (const double *)d_rating, nnz,
                              n_left, n_right, global_mean, (const double *)d_lb, (const double *)d_rb,
                              global_bias));
-    // the inputs are borrowed for the duration of the call only
-    cudaError_t e = cudaStreamSynchronize(h->stream);
+    // The inputs are borrowed for the duration of the call only: wait until the host->device copies
+    // are done (they are — the validation read-backs of the build synchronised after them), NOT for
+    // the similarity kernel.  Fit returns while it runs; everything that needs its result
+    // (predict, sims_rows, topk, profile) is ordered behind it on the handle's stream, so the
+    // caller's next host work (converting the test set's ids, core/data.go:98-105) overlaps it.
+    cudaError_t e = cudaEventSynchronize(h->ev_in);
     if (e != cudaSuccess) {
         rs_set_error("rs_knn_fit: %s", cudaGetErrorString(e));
         h->fitted = false;
@@ -603,8 +612,10 @@ static int32_t copy_vec(rs_knn *h, const double *d, double *out, const char *who
         rs_set_error("%s: not fitted or null argument", who);
         return RS_ERR_INVALID;
     }
-    RS_CUDA(cudaMemcpyAsync(out, d, (size_t)h->n_left * 8, cudaMemcpyDeviceToHost, h->stream));
-    RS_CUDA(cudaStreamSynchronize(h->stream));
+    // row statistics are final when Fit returns (the build ends with a synchronisation): read them on
+    // the auxiliary stream so that the read-back does not queue behind the similarity kernel
+    RS_CUDA(cudaMemcpyAsync(out, d, (size_t)h->n_left * 8, cudaMemcpyDeviceToHost, h->aux_stream));
+    RS_CUDA(cudaStreamSynchronize(h->aux_stream));
     return RS_OK;
 }
 

@@ -53,6 +53,8 @@ struct rs_knn {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr;   // read-backs of Fit statistics that must not wait for the similarity kernel
+    cudaEvent_t ev_in = nullptr;         // the host inputs of rs_knn_fit have been consumed
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr;
     rs_knn_profile prof{};
     // pending event pairs whose elapsed time has not been folded into prof yet
