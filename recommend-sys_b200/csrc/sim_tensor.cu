@@ -15,8 +15,9 @@
 //   tile      = 128 left rows (MMA M, TMEM lanes) x BN left rows (MMA N) x all K;
 //               BN = 128 for Cosine / MSD, 64 for Pearson (six accumulators), see Cfg<>
 //   operands  = planes laid out K-blocked, [plane][K / 256][row][256] int8 (see tma_load_box);
-//               TMA 4-D boxes (BK bytes of K x rows, one plane per instruction) land one pipeline stage with SWIZZLE_128B (BK = 128,
-//               Pearson: 3 stages x 72 KB) or SWIZZLE_64B (BK = 64, Cosine / MSD: 4 stages x 48 KB)
+//               TMA 4-D boxes (BK bytes of K x rows, one plane per instruction) land one pipeline
+//               stage with SWIZZLE_128B (BK = 128, Pearson: 3 stages x 72 KB) or SWIZZLE_64B
+//               (BK = 64, Cosine / MSD / Slope One: 4 stages x 48 KB)
 //   pipeline  = mbarrier full/empty ring; warp 0 lane 0 issues TMA, warp 1 lane 0 issues
 //               tcgen05.mma, warps 2-9 run the epilogue (tcgen05.ld -> FP64 -> HBM)
 //   MMAs      = the B planes of a stage are adjacent in shared memory in the order (X2, M, X), so
@@ -25,7 +26,10 @@
 //                 MSD    : M_I x [X2|M]_J (N=256), then X2_I x M_J accumulated INTO the Syy columns
 //                          (only Sxx+Syy is needed), X_I x X_J (N=128)
 //                 Cosine : M_I x X2_J, X_I x X_J, X2_I x M_J (N=128 each)
+//                 Slope  : M_I x [M|X]_J (N=256: count, Sy), X_I x M_J (Sx)   (core/slope_one.go)
 //   TMEM      = 384 accumulator columns in every mode
+//   large Cosine / MSD / Slope One problems run the CTA-pair variant below (namespace pair:
+//   tcgen05 cta_group::2, 256 x 128 tiles, each SM stages its 128 A rows and half of the B rows)
 //   schedule  = block-triangular: a tile runs iff it holds a pair (i, j) with j >= i and writes both
 //               S[i][j] and S[j][i] (the similarities are bit-symmetric, core/knn.go:205-208); a
 //               row-sharded handle runs every bj for its own row blocks and writes S[i][j] only.
