@@ -55,7 +55,7 @@ WORKLOADS = {
     "ml20m_slope_one": (138_493, 26_744, 20_000_000, 4_000_000, "slope_one", "basic", False, 40),
     "netflix_item_cosine_k50": (480_189, 17_770, 100_000_000, 20_000_000, "cosine", "basic", False, 50),
 }
-DEFAULT_WORKLOAD = "ml1m_item_pearson_k40"
+DEFAULT_WORKLOAD = "ml20m_item_pearson_k40"
 SEED = 0x5EED0000 + 1  # config index 1
 
 

@@ -129,6 +129,8 @@ def host_lib():
     L.rs_host_synth_ratings.restype = C.c_int64
     L.rs_host_synth_ratings.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p,
                                         C.c_void_p]
+    L.rs_host_mean_seq.restype = C.c_double
+    L.rs_host_mean_seq.argtypes = [C.c_void_p, C.c_int64]
     L.rs_host_convert_dense.restype = None
     L.rs_host_convert_dense.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     _host_lib = L
@@ -304,13 +306,25 @@ def _inner_ids(raw):
     return inner, int(count)
 
 
+def _global_mean(ratings):
+    """core/data.go:134.  Integer ratings: the sum is exact in any order (vectorised); otherwise the
+    sequential sum of the restatement (gonum's own order is pinned by no reference test)."""
+    n = len(ratings)
+    if n == 0:
+        return math.nan
+    r = np.ascontiguousarray(ratings, dtype=np.float64)
+    if np.array_equal(r, np.rint(r)) and float(np.abs(r).max()) * n < 2.0 ** 53:
+        return float(np.add.reduce(r) / n)
+    return float(host_lib().rs_host_mean_seq(_ptr(r), n))
+
+
 class TrainSet(DataSet):
     """core/data.go:109-216"""
 
     def __init__(self, rowSet: DataSet):
         super().__init__(rowSet.Users, rowSet.Items, rowSet.Ratings)
         # core/data.go:134 — stat.Mean(Ratings, nil)
-        self.GlobalMean = float(np.add.reduce(self.Ratings) / len(self.Ratings)) if len(self.Ratings) else math.nan
+        self.GlobalMean = _global_mean(self.Ratings)
         # core/data.go:137-151 — inner id = order of first appearance
         self.innerUsers, self.UserCount = _inner_ids(self.Users)
         self.innerItems, self.ItemCount = _inner_ids(self.Items)

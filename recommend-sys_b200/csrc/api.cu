@@ -36,7 +36,7 @@ void free_fit_state(rs_knn *h) {
     h->l_col = h->r_col = nullptr;
     h->l_val = h->r_val = h->ld_val = nullptr;
     h->l_code = nullptr;
-    h->lut = h->means = h->stddevs = h->pmeans = h->left_bias = h->right_bias = nullptr;
+    h->means = h->stddevs = h->pmeans = h->left_bias = h->right_bias = nullptr;
     h->r_dev = nullptr;
     h->rd_col = nullptr;
     h->right_means = nullptr;

@@ -29,7 +29,7 @@ void rs_set_error(const char *fmt, ...);
 
 // Rating classes (how a rating is represented as one byte; 0 = missing).
 //   RS_CLASS_INT8 : every rating is an integer in [-11,11]; code = rating + 12.
-//   RS_CLASS_TABLE: <= 255 distinct values; code = 1 + rank in the sorted value table.
+//   RS_CLASS_TABLE: any other float64 ratings; no byte code (stream path only, reads the values).
 enum { RS_CLASS_INT8 = 0, RS_CLASS_TABLE = 1 };
 constexpr int RS_INT8_BIAS = 12;
 
@@ -69,7 +69,6 @@ struct rs_knn {
     int64_t topk_rows = 0;               // rows covered by topk_idx / topk_sim
     double global_mean = 0.0, global_bias = 0.0;
     int rating_class = RS_CLASS_INT8;
-    int n_codes = 0;
 
     // Grow-only device arena: Fit bump-allocates from it and the next Fit reuses the same
     // chunks, so a refit of the same shape performs no cudaMalloc / cudaFree at all.
@@ -93,7 +92,6 @@ struct rs_knn {
     int32_t *r_col = nullptr;
     double *r_val = nullptr;
 
-    double *lut = nullptr;        // [256] code -> rating value
     double *means = nullptr;      // KNN.Means    (dataset order sum / count)
     double *stddevs = nullptr;    // KNN.StdDevs
     double *pmeans = nullptr;     // Pearson's own row means (sorted-order sum, core/sim.go:49-62)
@@ -113,6 +111,8 @@ struct rs_knn {
     int32_t *cp = nullptr;
     int32_t n_chunks = 0;
     int32_t stream_jc = 256;
+    bool stream_lower = false;     // full-matrix stream Fit computes j < i (else j > i); chosen per Fit from the lookup counts
+    double inc_upper = 0.0, inc_lower = 0.0;   // (entry, chunk) lookups of the two triangles
     int64_t *l2r = nullptr;
     int32_t *perm_lr = nullptr, *perm_rl = nullptr, *perm_tmp = nullptr;  // CSR position -> input row (arena, valid until the next Fit)
     int32_t *row_order = nullptr;  // left rows sorted by descending length

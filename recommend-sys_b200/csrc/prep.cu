@@ -105,29 +105,6 @@ __global__ void code_int8_kernel(const double *__restrict__ val, int64_t nnz, ui
     if (i < nnz) code[i] = (uint8_t)((int)val[i] + RS_INT8_BIAS);
 }
 
-__global__ void lut_int8_kernel(double *__restrict__ lut) {
-    int c = threadIdx.x;
-    lut[c] = (c >= 1 && c <= 2 * RS_INT8_BIAS - 1) ? (double)(c - RS_INT8_BIAS) : 0.0;
-}
-
-__global__ void lut_table_kernel(const double *__restrict__ uniq, int n, double *__restrict__ lut) {
-    int c = threadIdx.x;
-    lut[c] = (c >= 1 && c <= n) ? uniq[c - 1] : 0.0;
-}
-
-__global__ void code_table_kernel(const double *__restrict__ val, int64_t nnz, const double *__restrict__ uniq,
-                                  int n, uint8_t *__restrict__ code) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nnz) return;
-    double v = val[i] + 0.0;
-    int lo = 0, hi = n - 1;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (uniq[mid] < v) lo = mid + 1; else hi = mid;
-    }
-    code[i] = (uint8_t)(lo + 1);
-}
-
 __global__ void row_isum_kernel(const int64_t *__restrict__ l_ptr, const uint8_t *__restrict__ l_code,
                                 int32_t n_left, int32_t *__restrict__ row_cnt, int32_t *__restrict__ row_sum) {
     int32_t row = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -311,6 +288,26 @@ __global__ void triples_kernel(const int32_t *__restrict__ rcount, int32_t nr, u
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
+// (entry, chunk) lookups the stream kernel performs when it computes the upper (j > i) or the lower
+// (j < i) triangle: row i pays one lookup per entry and per column chunk it visits.
+__global__ void incidence_kernel(const int32_t *__restrict__ lcount, int32_t nl, int32_t jc,
+                                 unsigned long long *out) {
+    unsigned long long up = 0, lo = 0;
+    const long long q_all = (nl + jc - 1) / jc;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nl; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long d = (unsigned long long)lcount[i];
+        const long long q = i / jc;
+        up += d * (unsigned long long)(q_all - q);
+        lo += d * (unsigned long long)(q + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        up += __shfl_xor_sync(0xffffffffu, up, o);
+        lo += __shfl_xor_sync(0xffffffffu, lo, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, up); atomicAdd(out + 1, lo); }
+}
+
 // Slope One: mean of every right row (user).  Integer ratings: the sum is exact in any order, so
 // one correctly rounded division reproduces core/data.go:222-235 whatever the order.
 __global__ void right_means_kernel(const int64_t *__restrict__ r_ptr, const double *__restrict__ r_val, int32_t nr,
@@ -323,6 +320,12 @@ __global__ void right_means_kernel(const int64_t *__restrict__ r_ptr, const doub
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) out[c] = s / (double)(r_ptr[c + 1] - r_ptr[c]);
+}
+
+static int32_t rs_stream_jc(int32_t n_left) {
+    int32_t jc = n_left < 8192 ? 128 : 256;
+    if (const char *e = getenv("RS_KNN_STREAM_JC")) jc = atoi(e) == 128 ? 128 : 256;
+    return jc;
 }
 
 int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, const double *d_rating,
@@ -345,21 +348,26 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     RS_TRY(rs_alloc(h, &perm_rl, nnz));
     RS_TRY(rs_alloc(h, &lcount, (size_t)nl + 1));
     RS_TRY(rs_alloc(h, &rcount, (size_t)nr + 1));
-    RS_TRY(rs_alloc(h, &h->d_flags, 8));
+    RS_TRY(rs_alloc(h, &h->d_flags, 16));
     RS_CUDA(cudaMemsetAsync(lcount, 0, ((size_t)nl + 1) * 4, st));
     RS_CUDA(cudaMemsetAsync(rcount, 0, ((size_t)nr + 1) * 4, st));
-    RS_CUDA(cudaMemsetAsync(h->d_flags, 0, 32, st));
+    RS_CUDA(cudaMemsetAsync(h->d_flags, 0, 64, st));
 
     iota_validate_kernel<<<blocks_for(nnz), T, 0, st>>>(d_left, d_right, d_rating, nnz, nl, nr, idx, lcount,
                                                        rcount, h->d_flags);
     triples_kernel<<<148, T, 0, st>>>(rcount, nr, reinterpret_cast<unsigned long long *>(h->d_flags + 6));
-    h->prof.total_launches += 2;
+    h->stream_jc = rs_stream_jc(nl);
+    incidence_kernel<<<148, T, 0, st>>>(lcount, nl, h->stream_jc, reinterpret_cast<unsigned long long *>(h->d_flags + 8));
+    h->prof.total_launches += 3;
     int32_t flags = 0;
-    int32_t fl8[8] = {0};
-    RS_CUDA(cudaMemcpyAsync(fl8, h->d_flags, 32, cudaMemcpyDeviceToHost, st));
+    int32_t fl8[16] = {0};
+    RS_CUDA(cudaMemcpyAsync(fl8, h->d_flags, 64, cudaMemcpyDeviceToHost, st));
     RS_CUDA(cudaStreamSynchronize(st));
     flags = fl8[0];
     { unsigned long long t; memcpy(&t, fl8 + 6, 8); h->triples = (double)t; }
+    { unsigned long long t[2]; memcpy(t, fl8 + 8, 16); h->inc_upper = (double)t[0]; h->inc_lower = (double)t[1]; }
+    h->stream_lower = h->inc_lower < h->inc_upper;
+    if (const char *e = getenv("RS_KNN_STREAM_TRI")) h->stream_lower = !strcmp(e, "lower");   // tests: force a triangle
     if (flags & FLAG_BAD_ID) {
         rs_set_error("rating rows contain inner ids outside [0,n_left) x [0,n_right)");
         return RS_ERR_INVALID;
@@ -417,7 +425,6 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     RS_TRY(rs_alloc(h, &h->ld_val, nnz));
     RS_TRY(rs_alloc(h, &h->r_col, nnz));
     RS_TRY(rs_alloc(h, &h->r_val, nnz));
-    RS_TRY(rs_alloc(h, &h->l_code, nnz));
     gather_csr_kernel<<<blocks_for(nnz), T, 0, st>>>(perm_lr, d_left, d_right, d_rating, nnz, h->l_col, h->l_val,
                                                     h->d_flags);
     gather_csr_kernel<<<blocks_for(nnz), T, 0, st>>>(perm_rl, d_right, d_left, d_rating, nnz, h->r_col, h->r_val,
@@ -425,38 +432,13 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     if (need_dataset_order) gather_val_kernel<<<blocks_for(nnz), T, 0, st>>>(perm_l, d_rating, nnz, h->ld_val);
     h->prof.total_launches += need_dataset_order ? 3 : 2;
 
-    // rating codes + value table
-    RS_TRY(rs_alloc(h, &h->lut, 256));
+    // byte codes (rating + 12) of the integer class: operands of the tensor path and of the exact
+    // integer row sums.  Any other float64 rating set runs on the stream path, which reads the
+    // values themselves (l_val / r_dev) — no code table, no limit on the number of distinct values.
     if (h->rating_class == RS_CLASS_INT8) {
+        RS_TRY(rs_alloc(h, &h->l_code, nnz));
         code_int8_kernel<<<blocks_for(nnz), T, 0, st>>>(h->l_val, nnz, h->l_code);
-        lut_int8_kernel<<<1, 256, 0, st>>>(h->lut);
-        h->n_codes = 2 * RS_INT8_BIAS - 1;
-        h->prof.total_launches += 2;
-    } else {
-        double *sorted, *uniq;
-        int *d_num;
-        RS_TRY(rs_alloc(h, &sorted, nnz));
-        RS_TRY(rs_alloc(h, &uniq, nnz));
-        RS_TRY(rs_alloc(h, &d_num, 4));
-        size_t need = 0;
-        RS_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, need, h->l_val, sorted, (int)nnz, 0, 64, st));
-        if (need > tmp.bytes) { RS_TRY(rs_dev_alloc(h, &tmp.p, need)); tmp.bytes = need; }
-        RS_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp.bytes, h->l_val, sorted, (int)nnz, 0, 64, st));
-        need = 0;
-        RS_CUDA(cub::DeviceSelect::Unique(nullptr, need, sorted, uniq, d_num, (int)nnz, st));
-        if (need > tmp.bytes) { RS_TRY(rs_dev_alloc(h, &tmp.p, need)); tmp.bytes = need; }
-        RS_CUDA(cub::DeviceSelect::Unique(tmp.p, tmp.bytes, sorted, uniq, d_num, (int)nnz, st));
-        int num = 0;
-        RS_CUDA(cudaMemcpyAsync(&num, d_num, 4, cudaMemcpyDeviceToHost, st));
-        RS_CUDA(cudaStreamSynchronize(st));
-        if (num > 255) {
-            rs_set_error("%d distinct rating values; the device path supports at most 255", num);
-            return RS_ERR_UNSUPPORTED;
-        }
-        h->n_codes = num;
-        lut_table_kernel<<<1, 256, 0, st>>>(uniq, num, h->lut);
-        code_table_kernel<<<blocks_for(nnz), T, 0, st>>>(h->l_val, nnz, uniq, num, h->l_code);
-        h->prof.total_launches += 2;
+        h->prof.total_launches += 1;
     }
 
     // row statistics
@@ -505,8 +487,6 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
 
 int32_t rs_prep_rt(rs_knn *h) {
     cudaStream_t st = h->stream;
-    h->stream_jc = h->n_left < 8192 ? 128 : 256;
-    if (const char *e = getenv("RS_KNN_STREAM_JC")) h->stream_jc = atoi(e) == 128 ? 128 : 256;
     h->n_chunks = (int32_t)(((int64_t)h->n_left + h->stream_jc - 1) / h->stream_jc);
     RS_TRY(rs_alloc(h, &h->r_dev, (size_t)h->nnz));
     RS_TRY(rs_alloc(h, &h->l2r, (size_t)h->nnz));

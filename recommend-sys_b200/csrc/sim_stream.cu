@@ -43,7 +43,7 @@ struct StreamArgs {
     int64_t ld_s;
     int32_t n_left;
     int64_t row_begin, row_end;
-    int symmetric;            // 1: only columns j > i are computed (the mirror pass fills j < i)
+    int symmetric;            // 0: full rows; 1: only columns j > i are computed; 2: only j < i (the mirror pass fills the rest)
     unsigned long long *counter;
 };
 
@@ -63,13 +63,17 @@ __device__ __forceinline__ void stream_update(double *acc, int j, double ra, dou
     }
 }
 
-// SYM: the full matrix is being computed, only columns j > i are visited (the run starts right
-// after i's own position in c's list) and the mirror pass fills j < i; otherwise (row shard) the
-// whole run is visited and the diagonal pair (i,i) is skipped by index.
+// SYM = 1: the full matrix is being computed, only columns j > i are visited (the run starts right
+// after i's own position in c's list) and the mirror pass fills j < i.  SYM = 2: only columns j < i
+// (the run ends at i's own position).  Which triangle is cheaper depends on how the row lengths
+// correlate with the ids: a row pays one lookup per (entry, chunk) it visits, so long rows should
+// visit few chunks — with first-appearance ids the popular rows have the LOW ids and the lower
+// triangle costs 3.5x fewer lookups on the MovieLens-20M shape (rs_prep_rt picks per Fit).
+// SYM = 0 (row shard): the whole run is visited and the diagonal pair (i,i) is skipped by index.
 // Indices into the right CSR are kept in 32 bits inside the loop (nnz < 2^32 is checked at launch)
 // and the per-entry a-side terms are staged in shared memory, which halves the instructions per
 // column against the first version of this kernel (profiles/r01_stream_notes.md).
-template <int SIM, bool SHRINK, bool SYM, int JC>
+template <int SIM, bool SHRINK, int SYM, int JC>
 __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
     constexpr int NACC = SHRINK ? 4 : 3;
     extern __shared__ double s_acc_all[];                    // [SW][NACC][JC] accumulators, then [SW][32] a-side terms
@@ -91,7 +95,8 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
         const int64_t q = (int64_t)item % Q;
         const int32_t i = a.row_order[(int64_t)item / Q];
         const int j0 = (int)(q * JC);
-        if (SYM && j0 + JC <= i) continue;  // every column of the chunk is < i
+        if (SYM == 1 && j0 + JC <= i) continue;  // every column of the chunk is < i
+        if (SYM == 2 && j0 > i) continue;        // every column of the chunk is > i
 
         for (int x = lane; x < NACC * JC; x += 32) acc[x] = 0.0;
 
@@ -115,9 +120,10 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
                 const int64_t rp = a.r_ptr[c];
                 const int32_t *cpc = a.cp + (int64_t)c * (Q + 1) + q;
                 int64_t lo64 = rp + cpc[0];
-                const int64_t hi = rp + cpc[1];
+                int64_t hi = rp + cpc[1];
                 const int64_t self64 = a.l2r[e];
-                if (SYM) { if (self64 + 1 > lo64) lo64 = self64 + 1; }            // only j > i
+                if (SYM == 1) { if (self64 + 1 > lo64) lo64 = self64 + 1; }       // only j > i
+                else if (SYM == 2) { if (self64 < hi) hi = self64; }              // only j < i
                 else self = (uint32_t)self64;
                 n = hi > lo64 ? (int)(hi - lo64) : 0;
                 lo = (uint32_t)lo64;
@@ -176,7 +182,8 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
         for (int j = lane; j < JC; j += 32) {
             const int64_t col = (int64_t)j0 + j;
             if (col >= a.n_left) break;
-            if (SYM && col < i) continue;                                         // mirror pass writes it
+            if (SYM == 1 && col < i) continue;                                    // mirror pass writes it
+            if (SYM == 2 && col > i) break;
             double s;
             if (SIM == RS_SIM_MSD) s = 1.0 / (acc[j] / acc[JC + j] + 1.0);        // core/sim.go:43
             else s = acc[2 * JC + j] / (sqrt(acc[j]) * sqrt(acc[JC + j]));        // core/sim.go:24 / :80
@@ -195,12 +202,13 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
 // bit-symmetric (sums and products commute), which is why the reference can write
 // Sims[j][i] = Sims[i][j] (core/knn.go:205-208).  32x32 tiles through shared memory,
 // coalesced on both sides.  `chunk` is the column-chunk width the producer skipped by.
-__global__ void symmetrize_kernel(double *__restrict__ s, int64_t ld, int32_t n, int chunk) {
+// lower = 1: the producer computed j < i, the destinations are the cells right of the diagonal.
+__global__ void symmetrize_kernel(double *__restrict__ s, int64_t ld, int32_t n, int lower) {
     __shared__ double tile[32][33];
-    const int64_t bi = blockIdx.y, bj = blockIdx.x;          // destination tile (rows bi, cols bj)
+    int64_t bi = blockIdx.y, bj = blockIdx.x;                // destination tile (rows bi, cols bj)
+    if (bj > bi) return;                                     // one block per unordered tile pair
+    if (lower) { const int64_t t = bi; bi = bj; bj = t; }
     const int64_t r0 = bi * 32, c0 = bj * 32;
-    // destination (r, c) was skipped by the producer iff chunk(c) < chunk(r)
-    if ((c0 / chunk) >= ((r0 + 31) / chunk)) return;  // every destination in this tile was computed
     for (int y = threadIdx.y; y < 32; y += blockDim.y) {
         int64_t sr = c0 + y, sc = r0 + threadIdx.x;          // source = transposed position
         tile[y][threadIdx.x] = (sr < n && sc < n) ? s[sr * ld + sc] : 0.0;
@@ -208,13 +216,13 @@ __global__ void symmetrize_kernel(double *__restrict__ s, int64_t ld, int32_t n,
     __syncthreads();
     for (int y = threadIdx.y; y < 32; y += blockDim.y) {
         int64_t r = r0 + y, c = c0 + threadIdx.x;
-        if (r < n && c < n && (c / chunk) < (r / chunk)) s[r * ld + c] = tile[threadIdx.x][y];
+        if (r < n && c < n && (lower ? c > r : c < r)) s[r * ld + c] = tile[threadIdx.x][y];
     }
 }
 
 }  // namespace
 
-template <int SIM, bool SHRINK, bool SYM, int JC>
+template <int SIM, bool SHRINK, int SYM, int JC>
 static int32_t launch_stream_jc(rs_knn *h, const StreamArgs &s, int grid) {
     const int smem = SW * ((SHRINK ? 4 : 3) * JC + 32) * (int)sizeof(double);
     auto kern = sim_stream_kernel<SIM, SHRINK, SYM, JC>;
@@ -222,7 +230,7 @@ static int32_t launch_stream_jc(rs_knn *h, const StreamArgs &s, int grid) {
     kern<<<grid, SW * 32, smem, h->stream>>>(s);
     return RS_OK;
 }
-template <int SIM, bool SHRINK, bool SYM>
+template <int SIM, bool SHRINK, int SYM>
 static int32_t launch_stream_sym(rs_knn *h, const StreamArgs &s, int grid) {
     if (h->stream_jc == 128) return launch_stream_jc<SIM, SHRINK, SYM, 128>(h, s, grid);
     return launch_stream_jc<SIM, SHRINK, SYM, 256>(h, s, grid);
@@ -233,7 +241,8 @@ static int32_t launch_stream(rs_knn *h, const StreamArgs &s, int grid) {
         rs_set_error("stream path indexes the ratings with 32 bits (nnz=%lld)", (long long)h->nnz);
         return RS_ERR_UNSUPPORTED;
     }
-    return s.symmetric ? launch_stream_sym<SIM, SHRINK, true>(h, s, grid) : launch_stream_sym<SIM, SHRINK, false>(h, s, grid);
+    if (s.symmetric == 2) return launch_stream_sym<SIM, SHRINK, 2>(h, s, grid);
+    return s.symmetric ? launch_stream_sym<SIM, SHRINK, 1>(h, s, grid) : launch_stream_sym<SIM, SHRINK, 0>(h, s, grid);
 }
 
 int32_t rs_sim_stream_launch(rs_knn *h) {
@@ -245,7 +254,7 @@ int32_t rs_sim_stream_launch(rs_knn *h) {
     a.global_bias = h->global_bias; a.shrinkage = h->p.shrinkage;
     a.sims = h->sims; a.ld_s = h->ld_s; a.n_left = h->n_left;
     a.row_begin = h->row_begin; a.row_end = h->row_end;
-    a.symmetric = ((h->row_begin == 0 && h->row_end == h->n_left) || h->force_sym) ? 1 : 0;
+    a.symmetric = h->force_sym ? 1 : (h->row_begin == 0 && h->row_end == h->n_left) ? (h->stream_lower ? 2 : 1) : 0;
     if (h->row_end <= h->row_begin) return RS_OK;
     a.counter = reinterpret_cast<unsigned long long *>(h->d_flags + 2);
     RS_CUDA(cudaMemsetAsync(a.counter, 0, 8, h->stream));
@@ -274,7 +283,7 @@ int32_t rs_symmetrize_launch(rs_knn *h) {
     if (!(h->row_begin == 0 && h->row_end == h->n_left)) return RS_OK;
     const unsigned t = (unsigned)((h->n_left + 31) / 32);
     dim3 grid(t, t), block(32, 8);
-    symmetrize_kernel<<<grid, block, 0, h->stream>>>(h->sims, h->ld_s, h->n_left, 1);
+    symmetrize_kernel<<<grid, block, 0, h->stream>>>(h->sims, h->ld_s, h->n_left, h->stream_lower ? 1 : 0);
     h->prof.total_launches++;
     RS_CUDA(cudaGetLastError());
     return RS_OK;

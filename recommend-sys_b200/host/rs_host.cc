@@ -147,6 +147,15 @@ int64_t rs_host_synth_ratings(int32_t n_users, int32_t n_items, int64_t nnz_targ
     return w;
 }
 
+// core/data.go:134 `stat.Mean(rowSet.Ratings, nil)`: sum / n.  The restatement (oracle/knn_oracle.c) sums
+// sequentially; for integer ratings every order gives the same double, for other ratings gonum's
+// summation order is not pinned by any reference test (DESIGN.md "parity unpinned").
+double rs_host_mean_seq(const double *x, int64_t n) {
+    double sum = 0.0;
+    for (int64_t i = 0; i < n; i++) sum += x[i];
+    return sum / (double)n;
+}
+
 void rs_host_convert_dense(const int32_t *table, int64_t n_table, const int64_t *raw, int64_t n, int32_t *inner_out) {
     for (int64_t x = 0; x < n; x++) {
         const int64_t r = raw[x];

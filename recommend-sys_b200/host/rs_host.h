@@ -25,6 +25,8 @@ void rs_host_baseline_sgd(const int32_t *inner_user, const int32_t *inner_item, 
 
 /* Batch ConvertUserID / ConvertItemID (core/data.go:157-183) through a dense raw -> inner table
  * (table[raw] = inner id or -1; raw ids outside [0, n_table) are new ids = -1). */
+/* TrainSet.GlobalMean (core/data.go:134): sequential sum / n. */
+double rs_host_mean_seq(const double *x, int64_t n);
 void rs_host_convert_dense(const int32_t *table, int64_t n_table, const int64_t *raw, int64_t n, int32_t *inner_out);
 
 /* Deterministic synthetic rating matrices of the BASELINE.json shapes:

@@ -68,6 +68,39 @@ def test_sims_bit_exact_ml100k(ml100k, sim, user_based):
     assert bits_equal(got, got.T)                            # core/knn.go:205-208
 
 
+# ---- both triangles of the full-matrix stream Fit (rs_prep_rt picks the cheaper one per Fit) ----
+@pytest.mark.parametrize("tri", ["upper", "lower"])
+@pytest.mark.parametrize("user_based", [True, False])
+@pytest.mark.parametrize("sim", ["cosine", "msd", "pearson"])
+def test_sims_bit_exact_both_triangles(ml100k, sim, user_based, tri, monkeypatch):
+    monkeypatch.setenv("RS_KNN_STREAM_TRI", tri)
+    est, ref = fit_pair(ml100k["u4_base"], sim, "basic", user_based, extra={"simPath": "stream"})
+    got, want = est.Sims, ref.sims()
+    assert np.isnan(np.diag(got)).all()
+    assert bits_equal(got, want)
+    assert bits_equal(got, got.T)
+
+
+# ---- arbitrary float64 ratings (continuous values, thousands of distinct ones): the stream path
+# reads the values themselves, so anything the reference accepts is fitted (core/sim.go has no
+# notion of a rating scale) ----
+@pytest.mark.parametrize("knn_type", ["basic", "zscore"])
+@pytest.mark.parametrize("sim", ["cosine", "msd", "pearson"])
+def test_continuous_ratings_bit_exact(ml100k, sim, knn_type):
+    arr = ml100k["u5_base"].copy()
+    rng = np.random.RandomState(7)
+    u, i, r = split(arr)
+    r = r + rng.uniform(-0.49, 0.49, len(r))          # 80,000 distinct doubles
+    ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
+    est = CTORS[knn_type](rs.Parameters({"sim": SIMS[sim], "userBased": True, "k": 40}))
+    est.Fit(ts)
+    ref = ob.KNN(sim=sim, knn_type=knn_type, user_based=True, k=40, n_jobs=8,
+                 tie_policy="canonical").fit(ob.TrainSet(u, i, r))
+    assert bits_equal(est.Sims, ref.sims())
+    tu, ti, _ = split(ml100k["u5_test"])
+    assert bits_equal(rs.NewRawSet(tu, ti, np.zeros(len(tu))).Predict(est), ref.predict_batch(tu, ti, n_threads=8))
+
+
 # ---- both chunk widths of the stream kernel (128 for small matrices, 256 for large ones) ----
 @pytest.mark.parametrize("jc", ["128", "256"])
 @pytest.mark.parametrize("sim", ["cosine", "msd", "pearson"])
@@ -342,9 +375,8 @@ def test_errors_are_loud():
     assert e.value.code == -1
     with pytest.raises(rs.core.RsError):           # Predict before Fit
         h.predict_batch(left, right)
-    many = np.arange(600, dtype=np.int32)
-    with pytest.raises(rs.core.RsError) as e:      # > 255 distinct non-integer values
-        h.fit(many, many, many * 0.37 + 0.1, 600, 600, 1.0)
+    with pytest.raises(rs.core.RsError) as e:      # the tensor path needs small integer ratings
+        rs.core._Handle(sim="cosine", sim_path="tensor").fit(left[1:], right[1:], np.array([1.5, 2.25]), 2, 2, 1.9)
     assert e.value.code == -3
     with pytest.raises(rs.core.RsError):           # baseline KNN without bias
         rs.core._Handle(knn_type="baseline").fit(left[1:], right[1:], np.array([1.0, 2.0]), 2, 2, 1.5)
