@@ -4,25 +4,28 @@
     python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU algorithm
 
-One "step" = one pass of the hot path over one synthetic rating matrix of BASELINE.json configs[1]
-(KNNWithMeans, item-based Pearson, k=40, MovieLens-1M shape 6040 x 3706 with 1,000,000 training
-ratings; the test set is a further 200,000 held-out pairs of the same generator):
-    Fit(train)    -> dense N x N float64 similarity matrix resident in HBM (N = 3706 items)
-    Predict(test) -> 200,000 predictions
+One "step" = one pass of the hot path over one synthetic rating matrix.  The default workload is the
+north-star target of BASELINE.json: KNNWithMeans, item-based Pearson (exact mode: bit-identical to the
+reference), k = 40, MovieLens-20M shape (138,493 x 26,744 with 20,000,000 training ratings; the test set
+is a further 4,000,000 held-out pairs of the same generator):
+    Fit(train)    -> dense N x N float64 similarity matrix resident in HBM (N = 26,744 items, 5.7 GB)
+    Predict(test) -> 4,000,000 predictions
 metric = similarity pairs/s = N(N-1)/2 unordered left-row pairs / step time (Fit + Predict);
 predictions/s over the same step is reported beside it.  `value` is timed with CUDA events with
 every input already resident in HBM; `e2e` is the same step through the public API with HOST
-buffers (pinned), host<->device copies inside the timed region.
+buffers (pinned), host<->device copies inside the timed region.  Other BASELINE.json configs are
+selectable with --workload (configs[1] = ml1m_item_pearson_k40).
 
-N > 1 (torchrun, one rank per GPU): the path partitions into independent units, so rank r
-processes its own rating matrix of the named shape (a cross-validation fold per GPU, exactly
-how the reference parallelises, core/eval.go:28-35) — no data-path collective, scaling "weak".
-`--shard-rows` instead row-shards ONE matrix across the ranks and assembles the neighbour lists
-with an NCCL all-gather (scaling "strong"; meant for the ML-20M shapes, see profiles/).
+N > 1 (torchrun, one rank per GPU): STRONG scaling of that ONE matrix.  The exact sparse path runs as
+cyclic row shards — every pair is computed once across the ranks, the other triangle of a rank's rows is
+pulled from the peers' matrices over NVLink, each rank predicts the test pairs whose left row it owns and
+the predictions are all-gathered (NCCL) inside the timed region.  Tensor-path workloads use contiguous
+row shards, top-k-only workloads symmetric slabs.  `--folds` gives a fold per GPU instead (weak).
 
 The reference arm times the CPU restatement of the Go algorithm (oracle/, the reference itself
 is Go and no Go toolchain exists in the image) on the box's host cores: Fit with nJobs = all
 cores exactly as core/knn.go:192-216, Predict as the reference's serial loop (core/data.go:98-105).
+Under torchrun rank 0 alone runs it, on the full workload whatever N is.
 """
 import argparse
 import json
@@ -175,8 +178,30 @@ def ots_inner(ots, user_based):
     return lambda raw: np.array([conv(ots.h, int(x)) for x in raw], dtype=np.int64)
 
 
+def representative_slab(left_inner, n, rows):
+    """A contiguous slab of `rows` left rows whose mean length is closest to the mean over all rows
+    (deterministic).  A CPU merge-join Fit pays about N*len(i) + nnz steps for row i, so a slab of the
+    longest rows (the low ids) would overstate the cost of the whole matrix by an order of magnitude."""
+    deg = np.bincount(left_inner, minlength=n).astype(np.float64)
+    if rows >= n:
+        return 0, n
+    c = np.concatenate([[0.0], np.cumsum(deg)])
+    means = (c[rows:] - c[:-rows]) / rows
+    i0 = int(np.argmin(np.abs(means - deg.mean())))
+    return i0, i0 + rows
+
+
+def cpu_sample_rows(n, nnz, budget_merge_steps):
+    """Rows of a Fit slab that cost about `budget_merge_steps` two-pointer steps (2*nnz per row on average)."""
+    rows = int(budget_merge_steps / (2.0 * nnz))
+    if rows >= n:
+        return n
+    return max(64, rows // 64 * 64)
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path (restated)."""
+    """--impl reference: the reference's own CPU implementation of the path (restated), on rank 0,
+    on the FULL workload whatever N is (the other ranks exit without work)."""
     if rank != 0:
         return
     from oracle import binding as ob
@@ -186,22 +211,22 @@ def run_reference(args, rank, world):
     ots = ob.TrainSet(train.Users, train.Items, train.Ratings)
     cores = os.cpu_count() or 1
     n = train.UserCount if user_based else train.ItemCount
+    left_inner = train.innerUsers if user_based else train.innerItems
     pairs_full = n * (n - 1) / 2
-    budget_s = 200.0
-    # probe: a 64-row slab tells how long a full step would take
-    tf, tp, rows_done, npred = cpu_reference_step(ob, ots, test, sim, knn_type, user_based, k, cores,
-                                                  rows=(0, min(64, n)), n_pred=2000)
-    est_full = tf * (n / max(1, rows_done)) * 0.55 + (tp / max(1, npred)) * test.Length()
     total_steps = args.steps + args.warmup
-    if est_full * total_steps <= budget_s:
+    # a bounded, DETERMINISTIC sample: the slab size follows from the workload and K + W only
+    # (about 150 s of 16-thread merge-join work over the whole run, ~6e8 steps/s), never from a timing probe
+    nrows = cpu_sample_rows(n, train.Length(), 9e10 / max(1, total_steps))
+    if nrows >= n:
         rows, n_pred, sample = None, None, f"full workload: Fit all {n} rows + {test.Length()} serial predictions"
+        if test.Length() > 200_000:
+            n_pred = 200_000 // max(1, total_steps) * 4
+            sample = f"full Fit of all {n} rows + first {n_pred} test pairs predicted serially (scaled)"
     else:
-        frac = budget_s / (est_full * total_steps)
-        nrows = max(64, int(n * frac))
-        rows = (0, min(n, nrows))
-        n_pred = max(1000, int(test.Length() * frac))
-        sample = (f"slab of {rows[1]} of {n} left rows x all {n} (pairs/s from the slab) + first {n_pred} "
-                  f"of the slab's test pairs, serial")
+        rows = representative_slab(left_inner, n, nrows)
+        n_pred = max(1000, 40_000 // max(1, total_steps) * 4)
+        sample = (f"Fit slab of rows [{rows[0]},{rows[1]}) of {n} (mean row length closest to the matrix mean) x all {n} "
+                  f"columns, scaled x{n / nrows:.1f}/2 + first {n_pred} of the slab's test pairs predicted serially, scaled")
     times = []
     for s in range(total_steps):
         tf, tp, rows_done, npred = cpu_reference_step(ob, ots, test, sim, knn_type, user_based, k, cores, rows=rows,
@@ -211,21 +236,19 @@ def run_reference(args, rank, world):
     tf = sum(t[0] for t in times) / len(times)
     tp = sum(t[1] for t in times) / len(times)
     rows_done, npred = times[0][2], times[0][3]
-    if rows is None:
-        pairs = pairs_full
-        step_s = tf + tp
-    else:
-        # the slab computes rows_done x (n-1) ordered pairs; a full Fit computes every unordered
-        # pair once (core/knn.go:203 skips filled cells), i.e. n/rows_done/2 slabs' worth
-        pairs = pairs_full
-        step_s = tf * (n / rows_done) * 0.5 + (tp / max(1, npred)) * test.Length()
-    value = pairs / step_s
+    # the slab computes rows_done x (n-1) ordered pairs; a full Fit computes every unordered
+    # pair once (core/knn.go:203 skips filled cells), i.e. n/rows_done/2 slabs' worth
+    fit_s = tf if rows is None else tf * (n / rows_done) * 0.5
+    pred_s = (tp / max(1, npred)) * test.Length()
+    step_s = fit_s + pred_s
+    value = pairs_full / step_s
     line = {
         "impl": "reference", "metric": "similarity_pairs_per_sec", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 and not args.folds else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "predictions_per_sec": test.Length() / step_s,
-        "fit_ms": tf * 1e3, "predict_ms": tp * 1e3,
+        "fit_ms": fit_s * 1e3, "predict_ms": pred_s * 1e3,
         "config": {"workload": args.workload, "shape": f"{users}x{items}", "train_ratings": train.Length(),
                    "test_pairs": test.Length(), "sim": sim, "knn_type": knn_type, "user_based": user_based, "k": k,
                    "tie_policy": "go (pdqsort port)"},
@@ -253,7 +276,8 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
 
     import recommend_sys_b200 as rs
-    from recommend_sys_b200.shard import allgather_partial_topk, allgather_topk, shard_rows, union_topk_device
+    from recommend_sys_b200.shard import (ShardedKNN, allgather_partial_topk, allgather_predictions, allgather_topk,
+                                          attach_peers_and_mirror, route_pairs, shard_rows, union_topk_device)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback "
@@ -261,12 +285,19 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     users, items, nnz, n_test, sim, knn_type, user_based, k = WORKLOADS[args.workload]
-    # top-k-only workloads (config 4: no test set, the N x N matrix would not fit) run as SYMMETRIC
-    # SLABS: every pair is computed once, the slabs are dealt round-robin over the ranks, and one
-    # all-gather + union assembles the neighbour lists (also the single-GPU form of this workload)
+    # How N > 1 GPUs share ONE matrix (strong scaling; --folds restores a fold per GPU, weak):
+    #   sym    top-k-only workloads (config 4: no test set, the N x N matrix would not fit): SYMMETRIC SLABS,
+    #          every pair once, slabs dealt in snake order, all-gather + union of partial neighbour lists
+    #   cyc    exact sparse path (Pearson exact, PearsonBaseline, --sim-path stream): CYCLIC ROW SHARDS, every
+    #          pair once, the other triangle pulled from the peers over NVLink, test pairs routed to the owner
+    #          of their left row, predictions all-gathered
+    #   shard  tensor path: contiguous 128-aligned row shards (full rows), all-gather of lists and predictions
     sym = n_test == 0
-    shard = (args.shard_rows and world > 1) and not sym
-    train, test = make_data(args.workload, fold=0 if (shard or sym) else rank)
+    multi = world > 1 and not args.folds
+    stream_exact = (sim in ("pearson", "pearson_baseline") and args.pearson_mode == "exact") or args.sim_path == "stream"
+    cyc = multi and not sym and stream_exact and not args.shard_rows
+    shard = multi and not sym and not cyc
+    train, test = make_data(args.workload, fold=rank if (world > 1 and args.folds) else 0)
     n_left = train.UserCount if user_based else train.ItemCount
     n_right = train.ItemCount if user_based else train.UserCount
     left = train.innerUsers if user_based else train.innerItems
@@ -276,8 +307,15 @@ def run_ours(args, rank, world, local_rank):
     t_left = (train.convert_users if user_based else train.convert_items)(t_left_raw)
     t_right = (train.convert_items if user_based else train.convert_users)(t_right_raw)
     rb, re = shard_rows(n_left, world, rank) if shard else (0, 0)
+    counts = None
+    mine = None
     if shard and n_test:
         mine = (t_left >= rb) & (t_left < re)
+    if cyc:
+        owner = route_pairs(t_left, world)
+        counts = np.bincount(owner, minlength=world).tolist()
+        mine = owner == rank
+    if mine is not None:
         t_left, t_right = t_left[mine], t_right[mine]
     n_pred = len(t_left)
 
@@ -285,7 +323,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_stream(stream)
     h = rs.core._Handle(sim=sim, knn_type=knn_type, k=k, device=local_rank, row_begin=rb, row_end=re,
                         store="topk" if sym else "matrix", topk=k,
-                        shard_count=world if sym else 0, shard_index=rank if sym else 0,
+                        shard_count=world if ((sym and not args.folds) or cyc) else (1 if sym else 0),
+                        shard_index=rank if ((sym and not args.folds) or cyc) else 0,
                         pearson_mode=args.pearson_mode, sim_path=args.sim_path)
     h.set_stream(stream.cuda_stream)
 
@@ -318,14 +357,18 @@ def run_ours(args, rank, world, local_rank):
         h.fit_device(d_left.data_ptr(), d_right.data_ptr(), d_rating.data_ptr(), len(left), n_left, n_right,
                      train.GlobalMean, d_lb.data_ptr() if d_lb is not None else 0,
                      d_rb.data_ptr() if d_rb is not None else 0, global_bias)
+        if cyc:
+            attach_peers_and_mirror(h)          # the exchange step: other triangle over NVLink
         if n_pred:
             h.predict_batch_device(d_tl.data_ptr(), d_tr.data_ptr(), n_pred, d_out.data_ptr())
+        if cyc:
+            return allgather_predictions(d_out[:n_pred], counts)
         if shard:
             h.topk_device(k, d_tk_i.data_ptr(), d_tk_s.data_ptr())
             allgather_topk(d_tk_i, d_tk_s, n_left, k)
         if sym:
             h.topk_device(k, d_tk_i.data_ptr(), d_tk_s.data_ptr())
-            if world > 1:
+            if multi:
                 return union_topk_device(*allgather_partial_topk(d_tk_i, d_tk_s))
             return d_tk_i, d_tk_s
 
@@ -372,19 +415,25 @@ def run_ours(args, rank, world, local_rank):
     if shard:
         params.update({"rowBegin": rb, "rowEnd": re})
     if sym:
-        params.update({"store": "topk", "topk": k, "shardCount": world, "shardIndex": rank})
+        params.update({"store": "topk", "topk": k, "shardCount": world if multi else 1, "shardIndex": rank if multi else 0})
     e2e_test = test
     if shard and n_test:
         e2e_test = test.SubSet(np.where(mine)[0])
 
     def step_e2e():
+        if cyc:     # Fit + Predict of the ONE matrix on all ranks through the sharded estimator
+            est = ShardedKNN(ctor(rs.Parameters(params)))
+            est.Fit(train)
+            out = est.PredictBatch(test.Users, test.Items)
+            est.Close()
+            return out
         est = ctor(rs.Parameters(params))
         est.Fit(train)
         out = e2e_test.Predict(est) if n_test else None
         if sym:     # the result of a top-k-only Fit is the neighbour lists: united across ranks, read to the host
             est._h.topk_device(k, d_tk_i.data_ptr(), d_tk_s.data_ptr())
             est._h.synchronize()     # the estimator works on its own stream; the union below on torch's
-            li, ls = (union_topk_device(*allgather_partial_topk(d_tk_i, d_tk_s)) if world > 1 else (d_tk_i, d_tk_s))
+            li, ls = (union_topk_device(*allgather_partial_topk(d_tk_i, d_tk_s)) if multi else (d_tk_i, d_tk_s))
             out = (li.cpu(), ls.cpu())
         est.Close()
         return out
@@ -397,6 +446,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_times = []
     for _ in range(e2e_steps):
+        barrier()
         t0 = time.perf_counter()
         step_e2e()
         torch.cuda.synchronize()
@@ -404,16 +454,20 @@ def run_ours(args, rank, world, local_rank):
     e2e_s = statistics.median(e2e_times)
 
     # ---- reduce over ranks: max time, summed units ----
-    pairs_rank = n_left * (n_left - 1) / 2 if not shard else (re - rb) * (n_left - 1) / 2.0
-    if sym:
-        pairs_rank = n_left * (n_left - 1) / 2.0 / world      # every pair once, slabs dealt round-robin
-    red = torch.tensor([total_ms, e2e_s, prof["sim_kernel_ms"], prof["predict_kernel_ms"]], dtype=torch.float64,
-                       device=dev)
+    pairs_full = n_left * (n_left - 1) / 2.0
+    if world > 1 and args.folds:
+        pairs_rank = pairs_full                                  # a fold per GPU
+    elif shard:
+        pairs_rank = (re - rb) * (n_left - 1) / 2.0
+    else:
+        pairs_rank = pairs_full / (world if multi else 1)        # every pair once across the ranks
+    red = torch.tensor([total_ms, e2e_s, prof["sim_kernel_ms"], prof["predict_kernel_ms"], prof["prep_ms"]],
+                       dtype=torch.float64, device=dev)
     units = torch.tensor([pairs_rank, float(n_pred)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(units, op=dist.ReduceOp.SUM)
-    total_ms, e2e_s, sim_ms, pred_ms = red.tolist()
+    total_ms, e2e_s, sim_ms, pred_ms, prep_ms = red.tolist()
     pairs_all, preds_all = units.tolist()
     if rank != 0:
         h.close()
@@ -422,21 +476,21 @@ def run_ours(args, rank, world, local_rank):
     ms_per_step = total_ms / args.steps
     value = pairs_all / (ms_per_step / 1e3)
     hbm_peak, peak_src = load_peaks()
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    tpeak, tpeak_src = int8_peak(peaks, peak_src)
     # dominant kernel = the similarity kernel.  Algorithmic bytes per launch:
     # one read of the left CSR (4 B id + 8 B rating per entry) + 8 B per similarity the kernel emits
-    # (the computed block-triangle; the mirror pass writes the rest) — stream path; the tensor path
+    # (the computed triangle; the mirror pass writes the rest) — stream path; the tensor path
     # reports int8 ops instead.
     sim_launch_ms = sim_ms / max(1, prof["sim_launches"])
     launches_per_step = max(1, prof["sim_launches"]) / args.steps
     sim_step_ms = sim_ms / args.steps            # all similarity launches of one Fit (slabs in top-k mode)
+    g = {"cosine": 3, "msd": 4, "pearson": 6, "pearson_baseline": 6, "slope_one": 3}[sim]   # slope one: count, sum r_i, sum r_j
+    dense_ops = pairs_rank * 2 * g * n_right
     if prof["sim_path_used"] == rs.core.RS_SIM_PATH["tensor"]:
-        g = {"cosine": 3, "msd": 4, "pearson": 6, "slope_one": 3}[sim]   # slope one: count, sum r_i, sum r_j
-        ops = pairs_rank * 2 * g * n_right
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
-        tpeak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
-        roof = {"bound": "tensor", "achieved": ops / (sim_step_ms / 1e3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
-                "frac": ops / (sim_step_ms / 1e3) / 1e12 / tpeak, "traffic": None,
-                "peak_source": f"2 x {peak_src} bf16 burst (int8 is not in MEASURED_PEAKS.json)",
+        roof = {"bound": "tensor", "achieved": dense_ops / (sim_step_ms / 1e3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                "frac": dense_ops / (sim_step_ms / 1e3) / 1e12 / tpeak, "traffic": None,
+                "peak_source": tpeak_src,
                 "kernel": ("sim_tensor_pair_kernel" if sim in ("cosine", "msd") and
                            (n_left / 128.0) * (n_left / 128.0) / 2 >= 4 * 148 else "sim_tensor_kernel"),
                 "ms_per_launch": sim_launch_ms,
@@ -446,90 +500,128 @@ def run_ours(args, rank, world, local_rank):
                                       "includes the per-slab top-k selection" if shard else
                                       "; includes the per-slab transpose and top-k merges" if sym else ""))}
     else:
-        emitted = pairs_rank + n_left * 512  # block-triangle incl. the diagonal chunks
+        emitted = pairs_rank + (n_left / (world if multi else 1))   # the computed triangle + the diagonal
         alg_bytes = len(left) * 12 + emitted * 8
         roof = {"bound": "hbm", "achieved": alg_bytes / (sim_step_ms / 1e3) / 1e9, "peak": hbm_peak,
                 "unit": "GB/s", "frac": alg_bytes / (sim_step_ms / 1e3) / 1e9 / hbm_peak, "traffic": None,
                 "peak_source": f"{peak_src} copy bandwidth", "kernel": f"sim_stream_kernel<{sim}>",
                 "ms_per_launch": sim_launch_ms, "launches_per_step": launches_per_step,
-                "note": ("exact-order FP64 replay: bound by shared-memory read-modify-write and issue slots "
-                         "(profiles/r01_stream_notes.md), reported against the HBM roofline of its algorithmic "
-                         "bytes (left CSR + emitted similarities) as the contract asks")}
+                "triples_per_sec": prof["corated_triples"] / (world if multi else 1) / (sim_step_ms / 1e3),
+                "dense_equivalent": {"tops": dense_ops / (sim_step_ms / 1e3) / 1e12, "int8_peak_tops": tpeak,
+                                     "frac": dense_ops / (sim_step_ms / 1e3) / 1e12 / tpeak,
+                                     "note": ("int8 ops the dense masked-contraction formulation of the same pairs "
+                                              "needs (SURVEY.md §8d: N(N-1)/2 * 2*G*K) / this kernel's time, against "
+                                              "the int8 tensor roofline: > 1 means the exact sparse replay finishes "
+                                              "before a tensor-core kernel running AT its roofline could")},
+                "note": ("exact-order FP64 sparse replay: work = the co-rated triples; bound by shared-memory "
+                         "read-modify-write wavefronts and issue slots, not by HBM (profiles/r02_stream_notes.md); "
+                         "reported against the HBM roofline of its algorithmic bytes (left CSR + emitted "
+                         "similarities) as the contract asks")}
     # second object for the gather-reduce (the north star asks for "achieved HBM GB/s for predict"):
-    # algorithmic bytes per prediction = C * (4 B id + 8 B similarity + 8 B rating [+ 8 B mean/bias]) + 8 B
+    # algorithmic bytes per prediction = C * (4 B id + 1 B rating + 8 B similarity
+    # [+ 8 B mean/bias for the non-basic types]) + 8 B out
     roof_pred = None
     if n_pred:
         deg_right = np.bincount(right, minlength=n_right)
         cand = float(deg_right[t_right[t_right >= 0]].sum())
-        per_cand = 20 + (8 if knn_type != "basic" else 0)
+        per_cand = 13 + (8 if knn_type != "basic" else 0)
         pbytes = cand * per_cand + n_pred * 8.0
         pms = pred_ms / args.steps
         roof_pred = {"bound": "hbm", "achieved": pbytes / (pms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "frac": pbytes / (pms / 1e3) / 1e9 / hbm_peak, "traffic": None,
                      "kernel": "predict_select_kernel", "ms_per_launch": pms,
+                     "bytes_per_candidate": per_cand,
                      "candidates_per_prediction": cand / max(1, n_pred)}
     prof_file = ROOT / "profiles" / "traffic.json"
     if prof_file.exists():
         try:
             # DRAM bytes per launch of this kernel ON THIS WORKLOAD from the committed ncu capture
             tj = json.loads(prof_file.read_text())
-            roof["traffic"] = tj.get(roof["kernel"].split("<")[0] + "|" + args.workload)
-            if roof_pred:
-                roof_pred["traffic"] = tj.get("predict_select_kernel|" + args.workload)
+            if world == 1:
+                roof["traffic"] = tj.get(roof["kernel"].split("<")[0] + "|" + args.workload)
+                if roof_pred:
+                    roof_pred["traffic"] = tj.get("predict_select_kernel|" + args.workload)
         except (ValueError, OSError):
             pass
 
+    parallelism = ("single GPU" if world == 1 else
+                   "one fold per GPU, no collective" if args.folds else
+                   "symmetric slabs dealt in snake order + NCCL all-gather and union of partial neighbour lists" if sym else
+                   "cyclic row shards: every pair once, other triangle pulled from peer memory over NVLink "
+                   "(CUDA IPC), test pairs routed to the owner of their left row, NCCL all-gather of predictions" if cyc else
+                   "contiguous row shards (full rows) + NCCL all-gather of neighbour lists")
+    limiter = None
+    if multi:
+        fixed = prep_ms / args.steps
+        limiter = (f"replicated per-rank work: CSR build {fixed:.1f} ms of the {ms_per_step:.1f} ms step is not divided "
+                   f"by N (every rank sorts the full rating set); then the exchange step and launch latency")
     line = {
         "metric": "similarity_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong" if (shard or (sym and world > 1)) else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong" if multi else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "predictions_per_sec": preds_all / (ms_per_step / 1e3),
         "config": {"workload": args.workload, "shape": f"{users}x{items}", "train_ratings": train.Length(),
                    "test_pairs": int(preds_all), "sim": sim, "knn_type": knn_type, "user_based": user_based, "k": k,
                    "tie_policy": "canonical", "pearson_mode": args.pearson_mode,
                    "sim_path": {0: "auto", 1: "tensor", 2: "stream"}[prof["sim_path_used"]],
                    "l2": "flushed between timed iterations (256 MiB write)",
-                   "parallelism": ("symmetric slabs dealt round-robin + NCCL all-gather and union of partial "
-                                   "neighbour lists" if (sym and world > 1) else
-                                   "symmetric slabs, single GPU" if sym else
-                                   "row-sharded + NCCL all-gather of neighbour lists" if shard
-                                   else ("one fold per GPU, no collective" if world > 1 else "single GPU"))},
+                   "parallelism": parallelism},
         "clocks": clock_info,
         "e2e": {"value": pairs_all / e2e_s, "unit": "pairs/s", "ms_per_step": e2e_s * 1e3,
-                "h2d_bytes_per_step": int(len(left) * 16 + n_pred * 8),
-                "d2h_bytes_per_step": int(n_pred * 8 + (n_left * k * 12 if sym else 0)),
+                "h2d_bytes_per_step": int(len(left) * 16 / (world if cyc else 1) + (n_pred if cyc else test.Length()) * 8),
+                "d2h_bytes_per_step": int((test.Length() if cyc else n_pred) * 8 + (n_left * k * 12 if sym else 0)),
                 "predictions_per_sec": preds_all / e2e_s, "steps": e2e_steps, "statistic": "median step",
                 "ms_min": min(e2e_times) * 1e3, "ms_max": max(e2e_times) * 1e3},
         "gpu_launches": int(prof["total_launches"]),
-        "kernel_ms": {"sim": sim_ms / args.steps, "predict": pred_ms / args.steps, "prep": prof["prep_ms"] / args.steps},
+        "kernel_ms": {"sim": sim_ms / args.steps, "predict": pred_ms / args.steps, "prep": prep_ms / args.steps},
         "corated_triples": prof["corated_triples"],
         "roofline": roof,
         "roofline_predict": roof_pred,
     }
+    if limiter:
+        line["scaling_limiter"] = limiter
     if world == 1 and not args.no_cpu_baseline:
         from oracle import binding as ob
 
         ots = ob.TrainSet(train.Users, train.Items, train.Ratings)
         cores = os.cpu_count() or 1
         n = n_left
+        slab = representative_slab(left, n, cpu_sample_rows(n, train.Length(), 6e9))
         tf, tp, rows_done, npred = cpu_reference_step(ob, ots, test, sim, knn_type, user_based, k, cores,
-                                                      rows=(0, min(256, n)), n_pred=20000)
+                                                      rows=slab, n_pred=20000)
         # slab: rows_done x (n-1) ordered pairs; the full Fit computes each unordered pair about once
         est_fit = tf * (n / rows_done) * 0.5
-        if est_fit < 25:
+        if rows_done >= n:
+            est_fit = tf
+            sample = f"full Fit ({n} rows, {cores} threads) + first {npred} test pairs predicted serially"
+        elif est_fit < 25:
             tf, tp, rows_done, npred = cpu_reference_step(ob, ots, test, sim, knn_type, user_based, k, cores,
                                                           n_pred=20000)
             est_fit = tf
             sample = f"full Fit ({n} rows, {cores} threads) + first {npred} test pairs predicted serially"
         else:
-            sample = (f"Fit slab of {rows_done} rows x all {n} ({cores} threads, scaled x{n / rows_done:.1f}/2) + "
-                      f"first {npred} of the slab's test pairs predicted serially")
+            sample = (f"Fit slab of rows [{slab[0]},{slab[1]}) (mean row length closest to the matrix mean) x all {n} "
+                      f"({cores} threads, scaled x{n / rows_done:.1f}/2) + first {npred} of the slab's test pairs "
+                      f"predicted serially")
         cpu_step = est_fit + (tp / max(1, npred)) * test.Length()
         line["cpu_baseline"] = {"value": (n * (n - 1) / 2) / cpu_step, "unit": "pairs/s", "cores": cores,
                                 "kind": "port", "sample": sample, "fit_s": est_fit,
                                 "predict_s": (tp / max(1, npred)) * test.Length()}
     print(json.dumps(line), flush=True)
     h.close()
+
+
+def int8_peak(peaks, peak_src):
+    """Denominator of the tensor roofline: the measured plain kind::i8 GEMM peak when profiles/ holds one
+    (tools/i8_peak), else 2 x the measured bf16 burst, labelled."""
+    f = ROOT / "profiles" / "int8_peak.json"
+    if f.exists():
+        try:
+            j = json.loads(f.read_text())
+            return float(j["tops"]), f"measured dense kind::i8 GEMM ({j.get('how', 'tools/i8_peak')})"
+        except (ValueError, KeyError, OSError):
+            pass
+    return 2.0 * float(peaks.get("bf16_tflops", 1590.0)), f"2 x {peak_src} bf16 burst (no measured int8 peak committed)"
 
 
 def main():
@@ -539,7 +631,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--shard-rows", action="store_true")
+    ap.add_argument("--shard-rows", action="store_true", help="N > 1: contiguous row shards even on the exact sparse path")
+    ap.add_argument("--folds", action="store_true", help="N > 1: one cross-validation fold per GPU (weak scaling), "
+                    "the reference's own parallelism (core/eval.go:28-35)")
     ap.add_argument("--pearson-mode", default="exact", choices=["exact", "sums"])
     ap.add_argument("--sim-path", default="auto", choices=["auto", "tensor", "stream"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

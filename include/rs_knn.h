@@ -18,7 +18,13 @@
  *   - "left" is the side similarities are computed over (users if userBased, else items,
  *     core/knn.go:154-162), "right" is the other side;
  *   - there is no CPU fallback: without a CUDA device every compute entry point fails
- *     with RS_ERR_CUDA.
+ *     with RS_ERR_CUDA;
+ *   - threading: distinct handles may be used concurrently from any threads; calls on ONE handle
+ *     are serialised internally (a per-handle mutex held for the whole call), so concurrent
+ *     Predict calls on a fitted estimator are safe, as they are in the reference;
+ *   - Fit is asynchronous: rs_knn_fit returns once the inputs are consumed and validated, the
+ *     similarity kernel may still be running.  A device fault in it surfaces on the next call that
+ *     waits for the stream; callers that want Fit errors eagerly call rs_knn_synchronize.
  */
 #ifndef RS_KNN_H
 #define RS_KNN_H
@@ -54,18 +60,23 @@ enum rs_knn_type { RS_KNN_BASIC = 0, RS_KNN_CENTERED = 1, RS_KNN_ZSCORE = 2, RS_
  *          equal to EXACT within 1e-9*max(1,|s|), not bit-identical (SURVEY.md hazard 2). */
 enum rs_pearson_mode { RS_PEARSON_EXACT = 0, RS_PEARSON_SUMS = 1 };
 /* Which device kernel computes the similarities.
- *   AUTO  : TENSOR for Cosine/MSD (and Pearson in SUMS mode) when every rating is an
- *           integer in [-11, 11]; STREAM otherwise.
+ *   AUTO  : Pearson in EXACT mode and any rating set that is not small integers run STREAM.
+ *           Otherwise (Cosine / MSD / Pearson SUMS on integer ratings in [-11, 11], where both
+ *           kernels are bit-exact or within the stated tolerance) the faster one by a two-term
+ *           cost model: dense int8 work N(N-1)/2 * 2*G*K against the co-rated triples counted
+ *           during Fit (csrc/api.cu tensor_faster; constants measured on B200).
  *   TENSOR: tcgen05.mma.kind::i8 masked contractions (fails with RS_ERR_UNSUPPORTED if
  *           the ratings are not small integers).
- *   STREAM: FP64 CUDA-core kernel streaming the transposed rating bytes, accumulation in
- *           the reference's order (any rating set with <= 255 distinct values). */
+ *   STREAM: FP64 CUDA-core sparse replay: work proportional to the co-rated triples,
+ *           accumulation in the reference's order; accepts ANY float64 ratings (no limit on
+ *           the number of distinct values; NaN ratings are refused). */
 enum rs_sim_path { RS_PATH_AUTO = 0, RS_PATH_TENSOR = 1, RS_PATH_STREAM = 2 };
 /* What Fit leaves resident in HBM.
  *   MATRIX: the dense similarity rows of this handle's shard (what core/knn.go:157,161
  *           keeps; required by Predict).
- *   TOPK  : only the per-row top-`topk` neighbour lists, selected in the kernel epilogue;
- *           the N x N matrix never lands in HBM (BASELINE.json config 4). */
+ *   TOPK  : only the per-row top-`topk` neighbour lists; the N x N matrix is never resident
+ *           (BASELINE.json config 4).  The rows are produced slab by slab into a bounded
+ *           work buffer and reduced to the lists by selection kernels. */
 enum rs_store { RS_STORE_MATRIX = 0, RS_STORE_TOPK = 1 };
 
 typedef struct rs_knn rs_knn; /* opaque handle; one per estimator copy (core/eval.go:29-30) */
@@ -86,7 +97,13 @@ typedef struct rs_knn_params {
     int64_t row_begin;    /* shard of left rows this handle owns: [row_begin,row_end);    */
     int64_t row_end;      /*   0,0 = all rows.  One handle per GPU when row-sharding.     */
     double shrinkage;     /* PearsonBaseline extension: (n-1)/(n-1+shrinkage), 0 = off    */
-    int32_t shard_count;  /* RS_STORE_TOPK only.  0 (default): the handle computes the full rows of */
+                          /* RS_STORE_MATRIX with shard_count >= 2: CYCLIC ROW SHARDS.  The left rows are   */
+                          /*   dealt in blocks of 32 (block b -> shard b % shard_count); the handle        */
+                          /*   computes ONE triangle of the rows it owns (every pair once across the       */
+                          /*   shards, exact sparse path) and the other triangle is pulled from the peers'  */
+                          /*   matrices over NVLink by rs_knn_mirror (after rs_knn_peer_import).  Predict   */
+                          /*   then serves the test pairs whose left row the handle owns.                  */
+    int32_t shard_count;  /* RS_STORE_TOPK.  0 (default): the handle computes the full rows of             */
     int32_t shard_index;  /*   [row_begin,row_end) and keeps their lists.  >= 1: SYMMETRIC SLABS — the */
                           /*   left rows are cut into slabs dealt to the shards in snake order          */
                           /*   (0..c-1, c-1..0, ...); the handle computes its slabs, of each only the part */
@@ -156,7 +173,7 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
  * (core/knn.go:75-141): out[i] = prediction for (left[i], right[i]); -1 on either side
  * returns GlobalMean.  Ties between equal similarities are broken by ascending inner id
  * (the canonical policy; Go's sort.Sort is unstable, SURVEY.md hazard 1).
- * Requires RS_STORE_MATRIX; left ids must lie in the handle's row shard. */
+ * Requires RS_STORE_MATRIX; left ids outside the handle's row shard yield NaN.  k <= 256. */
 int32_t rs_knn_predict_batch(rs_knn *h, const int32_t *left, const int32_t *right, int64_t n,
                              double *out);
 int32_t rs_knn_predict_batch_device(rs_knn *h, const int32_t *d_left, const int32_t *d_right,
@@ -206,6 +223,28 @@ int32_t rs_baseline_als(int32_t device, const int32_t *users, const int32_t *ite
  * which is what symmetric-slab handles (shard_count >= 1) produce.  n_lists * k <= 2048. */
 int32_t rs_knn_topk_union_device(int32_t n_lists, int64_t n_rows, int32_t k, const int32_t *d_idx_all,
                                  const double *d_sim_all, int32_t *d_idx, double *d_sim, void *cuda_stream);
+
+/* Parameters["k"] / ["mink"] are read at Predict time by the reference (core/knn.go:80-81): change
+ * them on a fitted handle without refitting.  The predict kernel supports k <= 256. */
+int32_t rs_knn_set_k(rs_knn *h, int32_t k, int32_t min_k);
+
+/* CYCLIC ROW SHARDS (RS_STORE_MATRIX, shard_count >= 2) — the exchange step of a Fit sharded over the
+ * GPUs of one box; replaces the goroutine row split of core/knn.go:192-216.
+ *   rs_knn_peer_export  : a CUDA IPC handle (64 bytes) + byte offset of this shard's matrix, to be
+ *                         all-gathered by the host (torch.distributed / MPI / a pipe);
+ *   rs_knn_peer_import  : attaches the matrices of all shard_count shards (handles: shard_count x 64
+ *                         bytes, offsets: shard_count); mappings are cached for the life of the handle;
+ *   rs_knn_peer_import_local : the same for shards that live in THIS process (one handle per GPU, or
+ *                         several on one GPU in tests): peers[q] = handle of shard q;
+ *   rs_knn_mirror       : fills the triangle this shard did not compute from the peers' matrices (P2P
+ *                         loads over NVLink, transposed through shared memory).  The caller orders it
+ *                         after every peer's Fit has finished (rs_knn_synchronize + a barrier) and
+ *                         keeps the peers' matrices alive until it has finished.
+ * Until rs_knn_mirror has run, Predict / sims_rows / topk on a cyclic shard fail with RS_ERR_INVALID. */
+int32_t rs_knn_peer_export(rs_knn *h, unsigned char *handle64, int64_t *offset);
+int32_t rs_knn_peer_import(rs_knn *h, int32_t n_peers, const unsigned char *handles, const int64_t *offsets);
+int32_t rs_knn_peer_import_local(rs_knn *h, int32_t n_peers, rs_knn *const *peers);
+int32_t rs_knn_mirror(rs_knn *h);
 
 int32_t rs_knn_profile_get(rs_knn *h, rs_knn_profile *out);
 int32_t rs_knn_profile_reset(rs_knn *h);

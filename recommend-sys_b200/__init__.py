@@ -10,3 +10,4 @@ repository root) loads it.
 """
 from .core import *  # noqa: F401,F403
 from . import core  # noqa: F401
+from . import shard  # noqa: F401

@@ -66,7 +66,8 @@ ABI_SYMBOLS = [
     "rs_knn_predict_batch_device", "rs_knn_predict_neighbors", "rs_knn_sims_rows", "rs_knn_topk",
     "rs_knn_topk_device", "rs_knn_cosums", "rs_knn_means", "rs_knn_stddevs", "rs_knn_profile_get",
     "rs_knn_profile_reset", "rs_knn_synchronize", "rs_knn_trim_cache", "rs_baseline_als",
-    "rs_knn_topk_union_device",
+    "rs_knn_topk_union_device", "rs_knn_set_k", "rs_knn_peer_export", "rs_knn_peer_import",
+    "rs_knn_peer_import_local", "rs_knn_mirror",
 ]
 
 _knn_lib = None
@@ -109,6 +110,11 @@ def knn_lib():
             getattr(L, name).restype = i32
     L.rs_baseline_als.argtypes = [i32, vp, vp, vp, i64, i32, i32, dbl, dbl, dbl, i32, vp, vp]
     L.rs_knn_topk_union_device.argtypes = [i32, i64, i32, vp, vp, vp, vp, vp]
+    L.rs_knn_set_k.argtypes = [vp, i32, i32]
+    L.rs_knn_peer_export.argtypes = [vp, vp, C.POINTER(i64)]
+    L.rs_knn_peer_import.argtypes = [vp, i32, vp, vp]
+    L.rs_knn_peer_import_local.argtypes = [vp, i32, vp]
+    L.rs_knn_mirror.argtypes = [vp]
     _knn_lib = L
     return L
 
@@ -409,6 +415,19 @@ def LoadDataFromFile(fileName, sep="\t"):
     return NewRawSet(users, items, ratings)
 
 
+CYC_B = 32   # RS_CYC_B of csrc/common.cuh: rows are dealt to cyclic shards in blocks of 32
+
+
+def cyclic_rows(n, count, index):
+    """Global ids of the rows shard `index` of `count` owns under cyclic row sharding."""
+    i = np.arange(n)
+    return i[(i // CYC_B) % count == index]
+
+
+def cyclic_owner(ids, count):
+    return (np.asarray(ids) // CYC_B) % count
+
+
 # --------------------------------------------------------------------------------------------
 # device handle
 # --------------------------------------------------------------------------------------------
@@ -525,6 +544,35 @@ class _Handle:
     def synchronize(self):
         _check(knn_lib().rs_knn_synchronize(self.h))
 
+    def set_k(self, k, min_k):
+        _check(knn_lib().rs_knn_set_k(self.h, int(k), int(min_k)))
+
+    # ---- cyclic row shards (RS_STORE_MATRIX, shard_count >= 2): the exchange step ----
+    def peer_export(self):
+        """(64-byte CUDA IPC handle, byte offset) of this shard's matrix."""
+        hb = np.zeros(64, dtype=np.uint8)
+        off = C.c_int64(0)
+        _check(knn_lib().rs_knn_peer_export(self.h, _ptr(hb), C.byref(off)))
+        return hb, int(off.value)
+
+    def peer_import(self, handles, offsets):
+        handles = np.ascontiguousarray(handles, dtype=np.uint8).reshape(-1, 64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        _check(knn_lib().rs_knn_peer_import(self.h, len(offsets), _ptr(handles), _ptr(offsets)))
+
+    def peer_import_local(self, peers):
+        arr = (C.c_void_p * len(peers))(*[p.h for p in peers])
+        _check(knn_lib().rs_knn_peer_import_local(self.h, len(peers), arr))
+
+    def mirror(self):
+        _check(knn_lib().rs_knn_mirror(self.h))
+
+    def owned_rows(self):
+        """Global ids of the left rows this handle stores, in storage order."""
+        if self.params.store == RS_STORE["matrix"] and self.params.shard_count >= 2:
+            return cyclic_rows(self.n_left, self.params.shard_count, self.params.shard_index)
+        return np.arange(self.rows[0], self.rows[1])
+
 
 # --------------------------------------------------------------------------------------------
 # core/base.go:108-163 — BaseLine (host; sequential SGD)
@@ -618,13 +666,11 @@ class KNN(Base):
     def __del__(self):
         self.Close()
 
-    def Fit(self, trainSet: TrainSet):
-        """core/knn.go:143-217"""
+    def _prepare(self, trainSet: TrainSet):
+        """The host half of core/knn.go:143-187: parameters, orientation, baseline biases."""
         sim = self.Params.GetSim("sim", MSD)
         userBased = self.Params.GetBool("userBased", True)
         self.Params.GetInt("nJobs", 0)  # accepted for compatibility; the device needs no job count
-        k = self.Params.GetInt("k", 40)
-        minK = self.Params.GetInt("mink", 1)
         self.Data = trainSet
         self.GlobalMean = trainSet.GlobalMean
         if userBased:
@@ -643,28 +689,48 @@ class KNN(Base):
                 self.Bias = left_bias
             if sim.name != "pearson_baseline":
                 right_bias = None
-        self.Close()
-        self._h = _Handle(sim=sim.name, knn_type=self.KNNType, k=k, min_k=minK,
-                          device=self.Params.GetInt("device", -1),
-                          pearson_mode=self.Params.GetString("pearsonMode", "exact"),
-                          sim_path=self.Params.GetString("simPath", "auto"),
-                          store=self.Params.GetString("store", "matrix"),
-                          topk=self.Params.GetInt("topk", 0),
-                          row_begin=self.Params.GetInt("rowBegin", 0), row_end=self.Params.GetInt("rowEnd", 0),
-                          shrinkage=self.Params.GetFloat64("shrinkage", 0.0),
-                          shard_count=self.Params.GetInt("shardCount", 0),
-                          shard_index=self.Params.GetInt("shardIndex", 0))
-        self._h.fit(left, right, trainSet.Ratings, n_left, n_right, trainSet.GlobalMean, left_bias, right_bias,
-                    global_bias)
         self._userBased = userBased
+        return sim, left, right, n_left, n_right, left_bias, right_bias, global_bias
+
+    def _new_handle(self, sim, **over):
+        k = self.Params.GetInt("k", 40)
+        minK = self.Params.GetInt("mink", 1)
+        self._kk = (k, minK)
+        kw = dict(sim=sim.name, knn_type=self.KNNType, k=k, min_k=minK,
+                  device=self.Params.GetInt("device", -1),
+                  pearson_mode=self.Params.GetString("pearsonMode", "exact"),
+                  sim_path=self.Params.GetString("simPath", "auto"),
+                  store=self.Params.GetString("store", "matrix"),
+                  topk=self.Params.GetInt("topk", 0),
+                  row_begin=self.Params.GetInt("rowBegin", 0), row_end=self.Params.GetInt("rowEnd", 0),
+                  shrinkage=self.Params.GetFloat64("shrinkage", 0.0),
+                  shard_count=self.Params.GetInt("shardCount", 0),
+                  shard_index=self.Params.GetInt("shardIndex", 0))
+        kw.update(over)
+        return _Handle(**kw)
+
+    def _after_fit(self):
         if self.KNNType in (centered, zScore):
             self.Means = self._h.means()
         if self.KNNType == zScore:
             self.StdDevs = self._h.stddevs()
 
+    def Fit(self, trainSet: TrainSet):
+        """core/knn.go:143-217"""
+        sim, left, right, n_left, n_right, left_bias, right_bias, global_bias = self._prepare(trainSet)
+        self.Close()
+        self._h = self._new_handle(sim)
+        self._h.fit(left, right, trainSet.Ratings, n_left, n_right, trainSet.GlobalMean, left_bias, right_bias,
+                    global_bias)
+        self._after_fit()
+
     @property
     def Sims(self):
         """core/knn.go:21 — the dense N x N matrix, NaN = unset (copied from HBM on demand)."""
+        if self._h.params.store == RS_STORE["matrix"] and self._h.params.shard_count >= 2:
+            rows = self._h.owned_rows()          # cyclic shard: block by block, in storage order
+            return np.concatenate([self._h.sims_rows(int(b[0]), len(b))
+                                   for b in np.split(rows, np.flatnonzero(np.diff(rows) != 1) + 1)])
         r0, r1 = self._h.rows
         return self._h.sims_rows(r0, r1 - r0)
 
@@ -673,6 +739,11 @@ class KNN(Base):
         iu = self.Data.convert_users(userIDs)
         ii = self.Data.convert_items(itemIDs)
         left, right = (iu, ii) if self._userBased else (ii, iu)
+        # core/knn.go:80-81 reads k / mink in Predict: SetParams after Fit takes effect here
+        k, mink = self.Params.GetInt("k", 40), self.Params.GetInt("mink", 1)
+        if (k, mink) != self._kk:
+            self._h.set_k(k, mink)
+            self._kk = (k, mink)
         return self._h.predict_batch(left, right)
 
     def Predict(self, userID, itemID):
@@ -746,6 +817,10 @@ class SlopeOne(Base):
     @property
     def dev(self):
         """core/slope_one.go:13 — the item x item deviation matrix (copied from HBM on demand)."""
+        if self._h.params.store == RS_STORE["matrix"] and self._h.params.shard_count >= 2:
+            rows = self._h.owned_rows()          # cyclic shard: block by block, in storage order
+            return np.concatenate([self._h.sims_rows(int(b[0]), len(b))
+                                   for b in np.split(rows, np.flatnonzero(np.diff(rows) != 1) + 1)])
         r0, r1 = self._h.rows
         return self._h.sims_rows(r0, r1 - r0)
 

@@ -2,6 +2,7 @@
 // No CPU fallback anywhere: every compute entry point needs a CUDA device.
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "common.cuh"
@@ -26,6 +27,15 @@ int32_t enter(rs_knn *h) {
     RS_CUDA(cudaSetDevice(h->device));
     return RS_OK;
 }
+
+// Entry points on ONE handle are serialised: they share the handle's stream, staging buffers and
+// event pairs (the reference's Predict is read-only and may be called from several goroutines,
+// core/knn.go:75-141).  Recursive because host-pointer entry points call their _device variants.
+struct Guard {
+    std::unique_lock<std::recursive_mutex> lk;
+    explicit Guard(rs_knn *h) { if (h) lk = std::unique_lock<std::recursive_mutex>(h->mu); }
+};
+#define RS_ENTER(h) Guard guard_(h); RS_TRY(enter(h))
 
 // Forget the fitted state; the arena's chunks are kept for the next Fit.
 void free_fit_state(rs_knn *h) {
@@ -96,6 +106,20 @@ bool tensor_faster(const rs_knn *h) {
     return t_tensor <= t_stream;
 }
 
+int32_t init_handle(rs_knn *h) {
+    RS_CUDA(cudaSetDevice(h->device));
+    RS_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    RS_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    RS_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    h->stream = h->own_stream;
+    RS_CUDA(cudaEventCreate(&h->ev_a));
+    RS_CUDA(cudaEventCreate(&h->ev_b));
+    RS_CUDA(cudaEventCreate(&h->ev_c));
+    RS_CUDA(cudaEventCreate(&h->ev_d));
+    RS_CUDA(cudaEventCreate(&h->ev_e));
+    return RS_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -163,16 +187,11 @@ int32_t rs_knn_create(const rs_knn_params *p, rs_knn **out) {
     if (!h) return RS_ERR_OOM;
     h->p = *p;
     h->device = dev;
-    RS_CUDA(cudaSetDevice(dev));
-    RS_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    RS_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
-    RS_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
-    h->stream = h->own_stream;
-    RS_CUDA(cudaEventCreate(&h->ev_a));
-    RS_CUDA(cudaEventCreate(&h->ev_b));
-    RS_CUDA(cudaEventCreate(&h->ev_c));
-    RS_CUDA(cudaEventCreate(&h->ev_d));
-    RS_CUDA(cudaEventCreate(&h->ev_e));
+    const int32_t rc = init_handle(h);
+    if (rc != RS_OK) {             // a partially built handle is torn down, not leaked
+        rs_knn_destroy(h);
+        return rc;
+    }
     *out = h;
     return RS_OK;
 }
@@ -180,27 +199,28 @@ int32_t rs_knn_create(const rs_knn_params *p, rs_knn **out) {
 int32_t rs_knn_destroy(rs_knn *h) {
     if (!h) return RS_OK;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     free_fit_state(h);
     for (auto &c : h->chunks) rs_cached_free(h->device, c.p, c.bytes);
     h->chunks.clear();
+    for (auto &pm : h->peer_cache) cudaIpcCloseMemHandle(pm.base);
     if (h->tile_buf) cudaFree(h->tile_buf);
     if (h->ovf) rs_cached_free(h->device, h->ovf, h->ovf_bytes);
     for (size_t i = 0; i < h->scratch.size(); i++) rs_cached_free(h->device, h->scratch[i], h->scratch_bytes[i]);
-    cudaEventDestroy(h->ev_a);
-    cudaEventDestroy(h->ev_b);
-    cudaEventDestroy(h->ev_c);
-    cudaEventDestroy(h->ev_d);
-    cudaEventDestroy(h->ev_e);
-    cudaStreamDestroy(h->own_stream);
-    cudaStreamDestroy(h->aux_stream);
-    cudaEventDestroy(h->ev_in);
+    if (h->ev_a) cudaEventDestroy(h->ev_a);
+    if (h->ev_b) cudaEventDestroy(h->ev_b);
+    if (h->ev_c) cudaEventDestroy(h->ev_c);
+    if (h->ev_d) cudaEventDestroy(h->ev_d);
+    if (h->ev_e) cudaEventDestroy(h->ev_e);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
     delete h;
     return RS_OK;
 }
 
 int32_t rs_knn_set_stream(rs_knn *h, void *cuda_stream, int32_t use_own) {
-    RS_TRY(enter(h));
+    RS_ENTER(h);
     RS_CUDA(cudaStreamSynchronize(h->stream));
     // NULL is a real stream (the legacy default stream), so "own" needs its own flag
     h->stream = use_own ? h->own_stream : reinterpret_cast<cudaStream_t>(cuda_stream);
@@ -208,7 +228,7 @@ int32_t rs_knn_set_stream(rs_knn *h, void *cuda_stream, int32_t use_own) {
 }
 
 int32_t rs_knn_synchronize(rs_knn *h) {
-    RS_TRY(enter(h));
+    RS_ENTER(h);
     RS_CUDA(cudaStreamSynchronize(h->stream));
     return RS_OK;
 }
@@ -216,7 +236,7 @@ int32_t rs_knn_synchronize(rs_knn *h) {
 int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_right, const double *d_rating,
                           int64_t nnz, int32_t n_left, int32_t n_right, double global_mean,
                           const double *d_left_bias, const double *d_right_bias, double global_bias) {
-    RS_TRY(enter(h));
+    RS_ENTER(h);
     if (!d_left || !d_right || !d_rating || nnz <= 0 || n_left <= 0 || n_right <= 0) {
         rs_set_error("rs_knn_fit: empty or null input (nnz=%lld n_left=%d n_right=%d)", (long long)nnz, n_left,
                      n_right);
@@ -249,10 +269,23 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
         rs_set_error("shard_index %d outside [0, shard_count=%d)", h->p.shard_index, h->p.shard_count);
         return RS_ERR_INVALID;
     }
-    if (h->p.shard_count >= 1 && (h->p.store != RS_STORE_TOPK || rows != n_left)) {
-        rs_set_error("symmetric slabs (shard_count >= 1) need RS_STORE_TOPK and no row_begin/row_end");
+    if (h->p.shard_count >= 1 && rows != n_left) {
+        rs_set_error("shard_count >= 1 and row_begin/row_end are two different sharding schemes: use one");
         return RS_ERR_INVALID;
     }
+    // RS_STORE_MATRIX with shard_count >= 2: CYCLIC ROW SHARDS (see rs_knn_params::shard_count)
+    h->cyc_R = (h->p.store == RS_STORE_MATRIX && h->p.shard_count >= 2) ? h->p.shard_count : 0;
+    h->cyc_r = h->cyc_R ? h->p.shard_index : 0;
+    h->peers_ready = false;
+    if (h->cyc_R > RS_MAX_PEERS) {
+        rs_set_error("at most %d cyclic row shards", RS_MAX_PEERS);
+        return RS_ERR_UNSUPPORTED;
+    }
+    if (h->cyc_R && h->p.sim == RS_SIM_SLOPE_ONE) {
+        rs_set_error("RS_SIM_SLOPE_ONE does not support cyclic row shards (use row_begin/row_end)");
+        return RS_ERR_UNSUPPORTED;
+    }
+    h->rows_local = h->cyc_R ? rs_cyc_rows(n_left, h->cyc_R, h->cyc_r) : rows;
 
     RS_CUDA(cudaEventRecord(h->ev_a, h->stream));
     int32_t rc = rs_prep_build(h, d_left, d_right, d_rating, d_left_bias, d_right_bias);
@@ -272,6 +305,16 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
         }
         path = RS_PATH_TENSOR;
     }
+    if (h->cyc_R) {
+        // every pair is computed once by the shard that owns the larger (or smaller) row and the other
+        // triangle arrives by rs_knn_mirror: that schedule exists for the exact sparse path only
+        if (path == RS_PATH_TENSOR) {
+            rs_set_error("cyclic row shards run the stream path; shard the tensor path with row_begin/row_end");
+            free_fit_state(h);
+            return RS_ERR_UNSUPPORTED;
+        }
+        path = RS_PATH_STREAM;
+    }
     if (path == RS_PATH_AUTO) path = tensor_eligible(h) && tensor_faster(h) ? RS_PATH_TENSOR : RS_PATH_STREAM;
     if (path == RS_PATH_TENSOR && !tensor_eligible(h)) {
         rs_set_error("tensor path needs integer ratings in [-11,11] and Cosine/MSD (or Pearson in SUMS mode)");
@@ -285,7 +328,7 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
 
     h->ld_s = ((int64_t)n_left + 15) / 16 * 16;
     if (h->p.store == RS_STORE_MATRIX) {
-        rc = rs_alloc(h, &h->sims, (size_t)rows * (size_t)h->ld_s);
+        rc = rs_alloc(h, &h->sims, (size_t)h->rows_local * (size_t)h->ld_s);
         if (rc != RS_OK) { free_fit_state(h); return rc; }
         RS_CUDA(cudaEventRecord(h->ev_b, h->stream));
         rc = (path == RS_PATH_TENSOR) ? rs_sim_tensor_launch(h, nullptr, 0, 0) : rs_sim_stream_launch(h);
@@ -411,7 +454,7 @@ int32_t rs_scratch_get(rs_knn *h, int slot, size_t bytes, void **out) {
 int32_t rs_knn_fit(rs_knn *h, const int32_t *left, const int32_t *right, const double *rating, int64_t nnz,
                    int32_t n_left, int32_t n_right, double global_mean, const double *left_bias,
                    const double *right_bias, double global_bias) {
-    RS_TRY(enter(h));
+    RS_ENTER(h);
     if (!left || !right || !rating || nnz <= 0 || n_left <= 0 || n_right <= 0) {
         rs_set_error("rs_knn_fit: empty or null input (nnz=%lld n_left=%d n_right=%d)", (long long)nnz, n_left,
                      n_right);
@@ -460,12 +503,16 @@ static int32_t require_matrix(rs_knn *h, const char *who) {
         rs_set_error("%s needs RS_STORE_MATRIX (the handle keeps top-k lists only)", who);
         return RS_ERR_INVALID;
     }
+    if (h->cyc_R > 1 && !h->peers_ready) {
+        rs_set_error("%s: cyclic row shards hold one triangle of their rows until rs_knn_mirror has run", who);
+        return RS_ERR_INVALID;
+    }
     return RS_OK;
 }
 
 int32_t rs_knn_predict_batch_device(rs_knn *h, const int32_t *d_left, const int32_t *d_right, int64_t n,
                                     double *d_out) {
-    RS_TRY(enter(h));
+    RS_ENTER(h);
     RS_TRY(require_matrix(h, "rs_knn_predict_batch"));
     if (n == 0) return RS_OK;
     if (!d_left || !d_right || !d_out || n < 0) {
@@ -482,7 +529,7 @@ int32_t rs_knn_predict_batch_device(rs_knn *h, const int32_t *d_left, const int3
 }
 
 int32_t rs_knn_predict_batch(rs_knn *h, const int32_t *left, const int32_t *right, int64_t n, double *out) {
-    RS_TRY(enter(h));
+    RS_ENTER(h);
     RS_TRY(require_matrix(h, "rs_knn_predict_batch"));
     if (n == 0) return RS_OK;
     if (!left || !right || !out || n < 0) {
@@ -503,7 +550,7 @@ int32_t rs_knn_predict_batch(rs_knn *h, const int32_t *left, const int32_t *righ
 
 int32_t rs_knn_predict_neighbors(rs_knn *h, int32_t left, int32_t right, int32_t cap, int32_t *ids, double *sims,
                                  int32_t *n_out) {
-    RS_TRY(enter(h));
+    RS_ENTER(h);
     RS_TRY(require_matrix(h, "rs_knn_predict_neighbors"));
     if (!ids || !sims || !n_out || cap < 1) {
         rs_set_error("rs_knn_predict_neighbors: null argument");
@@ -533,7 +580,7 @@ int32_t rs_knn_predict_neighbors(rs_knn *h, int32_t left, int32_t right, int32_t
 }
 
 int32_t rs_knn_sims_rows(rs_knn *h, int64_t row0, int64_t nrows, double *out) {
-    RS_TRY(enter(h));
+    RS_ENTER(h);
     RS_TRY(require_matrix(h, "rs_knn_sims_rows"));
     if (!out || nrows < 0 || row0 < h->row_begin || row0 + nrows > h->row_end) {
         rs_set_error("rs_knn_sims_rows: rows [%lld,%lld) outside the shard [%lld,%lld)", (long long)row0,
@@ -541,7 +588,17 @@ int32_t rs_knn_sims_rows(rs_knn *h, int64_t row0, int64_t nrows, double *out) {
         return RS_ERR_INVALID;
     }
     if (nrows == 0) return RS_OK;
-    RS_CUDA(cudaMemcpy2DAsync(out, (size_t)h->n_left * 8, h->sims + (row0 - h->row_begin) * h->ld_s,
+    int64_t local0 = row0 - h->row_begin;
+    if (h->cyc_R > 1) {
+        // cyclic shards: the rows asked for must lie in ONE block of RS_CYC_B rows this shard owns
+        if (!rs_cyc_owns(row0, h->cyc_R, h->cyc_r) || row0 / RS_CYC_B != (row0 + nrows - 1) / RS_CYC_B) {
+            rs_set_error("rs_knn_sims_rows: rows [%lld,%lld) are not inside one %d-row block of shard %d of %d",
+                         (long long)row0, (long long)(row0 + nrows), RS_CYC_B, h->cyc_r, h->cyc_R);
+            return RS_ERR_INVALID;
+        }
+        local0 = rs_cyc_local(row0, h->cyc_R);
+    }
+    RS_CUDA(cudaMemcpy2DAsync(out, (size_t)h->n_left * 8, h->sims + local0 * h->ld_s,
                               (size_t)h->ld_s * 8, (size_t)h->n_left * 8, (size_t)nrows, cudaMemcpyDeviceToHost,
                               h->stream));
     RS_CUDA(cudaStreamSynchronize(h->stream));
@@ -549,12 +606,13 @@ int32_t rs_knn_sims_rows(rs_knn *h, int64_t row0, int64_t nrows, double *out) {
 }
 
 int32_t rs_knn_topk_device(rs_knn *h, int32_t k, int32_t *d_idx, double *d_sim) {
-    RS_TRY(enter(h));
+    RS_ENTER(h);
     if (!h->fitted || !d_idx || !d_sim) {
         rs_set_error("rs_knn_topk: not fitted or null argument");
         return RS_ERR_INVALID;
     }
-    const int64_t rows = h->p.store == RS_STORE_TOPK ? h->topk_rows : h->row_end - h->row_begin;
+    const int64_t rows = h->p.store == RS_STORE_TOPK ? h->topk_rows : h->rows_local;
+    if (h->p.store == RS_STORE_MATRIX) RS_TRY(require_matrix(h, "rs_knn_topk"));
     if (h->p.store == RS_STORE_TOPK) {
         const int32_t kk = h->p.topk > 0 ? h->p.topk : h->p.k;
         if (k != kk) {
@@ -569,12 +627,12 @@ int32_t rs_knn_topk_device(rs_knn *h, int32_t k, int32_t *d_idx, double *d_sim) 
 }
 
 int32_t rs_knn_topk(rs_knn *h, int32_t k, int32_t *idx, double *sim) {
-    RS_TRY(enter(h));
+    RS_ENTER(h);
     if (!h->fitted || !idx || !sim || k < 1) {
         rs_set_error("rs_knn_topk: not fitted or bad argument");
         return RS_ERR_INVALID;
     }
-    const int64_t rows = h->p.store == RS_STORE_TOPK ? h->topk_rows : h->row_end - h->row_begin;
+    const int64_t rows = h->p.store == RS_STORE_TOPK ? h->topk_rows : h->rows_local;
     void *di, *ds;
     RS_TRY(rs_scratch_get(h, 3, (size_t)rows * k * 4, &di));
     RS_TRY(rs_scratch_get(h, 4, (size_t)rows * k * 8, &ds));
@@ -586,7 +644,7 @@ int32_t rs_knn_topk(rs_knn *h, int32_t k, int32_t *idx, double *sim) {
 }
 
 int32_t rs_knn_cosums(rs_knn *h, int64_t row0, int64_t nrows, int32_t *out) {
-    RS_TRY(enter(h));
+    RS_ENTER(h);
     if (!h->fitted || !out || nrows < 0 || row0 < 0 || row0 + nrows > h->n_left) {
         rs_set_error("rs_knn_cosums: not fitted or bad argument");
         return RS_ERR_INVALID;
@@ -607,7 +665,7 @@ int32_t rs_knn_cosums(rs_knn *h, int64_t row0, int64_t nrows, int32_t *out) {
 }
 
 static int32_t copy_vec(rs_knn *h, const double *d, double *out, const char *who) {
-    RS_TRY(enter(h));
+    RS_ENTER(h);
     if (!h->fitted || !out || !d) {
         rs_set_error("%s: not fitted or null argument", who);
         return RS_ERR_INVALID;
@@ -628,8 +686,110 @@ int32_t rs_knn_stddevs(rs_knn *h, double *out) {
     return copy_vec(h, h ? h->stddevs : nullptr, out, "rs_knn_stddevs");
 }
 
+int32_t rs_knn_set_k(rs_knn *h, int32_t k, int32_t min_k) {
+    RS_ENTER(h);
+    if (k < 1 || min_k < 0) {
+        rs_set_error("rs_knn_set_k: k >= 1 and min_k >= 0 required");
+        return RS_ERR_INVALID;
+    }
+    h->p.k = k;
+    h->p.min_k = min_k;
+    return RS_OK;
+}
+
+int32_t rs_knn_peer_export(rs_knn *h, unsigned char *handle64, int64_t *offset) {
+    RS_ENTER(h);
+    if (!h->fitted || h->cyc_R < 2 || !handle64 || !offset) {
+        rs_set_error("rs_knn_peer_export: the handle is not a fitted cyclic row shard");
+        return RS_ERR_INVALID;
+    }
+    for (const auto &c : h->chunks) {
+        const char *s0 = reinterpret_cast<const char *>(h->sims);
+        if (s0 >= c.p && s0 < c.p + c.bytes) {
+            cudaIpcMemHandle_t mh;
+            RS_CUDA(cudaIpcGetMemHandle(&mh, c.p));
+            static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+            std::memcpy(handle64, &mh, 64);
+            *offset = (int64_t)(s0 - c.p);
+            return RS_OK;
+        }
+    }
+    rs_set_error("rs_knn_peer_export: the matrix is not in the handle's arena");
+    return RS_ERR_INVALID;
+}
+
+int32_t rs_knn_peer_import(rs_knn *h, int32_t n_peers, const unsigned char *handles, const int64_t *offsets) {
+    RS_ENTER(h);
+    if (!h->fitted || h->cyc_R < 2 || n_peers != h->cyc_R || !handles || !offsets) {
+        rs_set_error("rs_knn_peer_import: needs a fitted cyclic row shard and one (handle, offset) per shard");
+        return RS_ERR_INVALID;
+    }
+    for (int q = 0; q < n_peers; q++) {
+        if (q == h->cyc_r) { h->peer_sims[q] = h->sims; continue; }
+        const unsigned char *hb = handles + (size_t)q * 64;
+        void *base = nullptr;
+        for (const auto &pm : h->peer_cache)
+            if (!std::memcmp(pm.handle, hb, 64)) { base = pm.base; break; }
+        if (!base) {
+            cudaIpcMemHandle_t mh;
+            std::memcpy(&mh, hb, 64);
+            RS_CUDA(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+            rs_knn::PeerMap pm;
+            std::memcpy(pm.handle, hb, 64);
+            pm.base = base;
+            h->peer_cache.push_back(pm);
+        }
+        h->peer_sims[q] = reinterpret_cast<const double *>(static_cast<const char *>(base) + offsets[q]);
+    }
+    return RS_OK;
+}
+
+int32_t rs_knn_peer_import_local(rs_knn *h, int32_t n_peers, rs_knn *const *peers) {
+    RS_ENTER(h);
+    if (!h->fitted || h->cyc_R < 2 || n_peers != h->cyc_R || !peers) {
+        rs_set_error("rs_knn_peer_import_local: needs a fitted cyclic row shard and one handle per shard");
+        return RS_ERR_INVALID;
+    }
+    for (int q = 0; q < n_peers; q++) {
+        const rs_knn *o = peers[q];
+        if (!o || !o->fitted || o->cyc_R != h->cyc_R || o->cyc_r != q || o->n_left != h->n_left || o->ld_s != h->ld_s) {
+            rs_set_error("rs_knn_peer_import_local: peer %d is not shard %d of the same Fit", q, q);
+            return RS_ERR_INVALID;
+        }
+        if (o->device != h->device) {
+            int can = 0;
+            RS_CUDA(cudaDeviceCanAccessPeer(&can, h->device, o->device));
+            if (!can) {
+                rs_set_error("device %d cannot access device %d", h->device, o->device);
+                return RS_ERR_UNSUPPORTED;
+            }
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) RS_CUDA(e);
+            (void)cudaGetLastError();
+        }
+        h->peer_sims[q] = o->sims;
+    }
+    return RS_OK;
+}
+
+int32_t rs_knn_mirror(rs_knn *h) {
+    RS_ENTER(h);
+    if (!h->fitted || h->cyc_R < 2) {
+        rs_set_error("rs_knn_mirror: the handle is not a fitted cyclic row shard");
+        return RS_ERR_INVALID;
+    }
+    for (int q = 0; q < h->cyc_R; q++)
+        if (q != h->cyc_r && !h->peer_sims[q]) {
+            rs_set_error("rs_knn_mirror: shard %d has not been attached (rs_knn_peer_import)", q);
+            return RS_ERR_INVALID;
+        }
+    RS_TRY(rs_mirror_launch(h));
+    h->peers_ready = true;
+    return RS_OK;
+}
+
 int32_t rs_knn_profile_get(rs_knn *h, rs_knn_profile *out) {
-    RS_TRY(enter(h));
+    RS_ENTER(h);
     if (!out) return RS_ERR_INVALID;
     RS_TRY(fold_profile(h));
     *out = h->prof;
@@ -642,7 +802,7 @@ int32_t rs_knn_trim_cache(void) {
 }
 
 int32_t rs_knn_profile_reset(rs_knn *h) {
-    RS_TRY(enter(h));
+    RS_ENTER(h);
     RS_TRY(fold_profile(h));
     int32_t path = h->prof.sim_path_used;
     h->prof = rs_knn_profile{};

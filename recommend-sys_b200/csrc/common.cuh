@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <vector>
 
 #include "rs_knn.h"
@@ -48,7 +49,26 @@ constexpr int RS_TC_BN = 64;
 constexpr int RS_TC_BK = 128;
 constexpr int RS_TC_KBLK = 256;   // bytes of K per block of the K-blocked plane layout [plane][K/256][row][256]
 
+// Cyclic row shards (RS_STORE_MATRIX with shard_count >= 2): rows are dealt to the shards in blocks of
+// RS_CYC_B (block b belongs to shard b % count), so every shard gets the same mix of long and short
+// rows; a shard stores its rows densely in dealing order.
+constexpr int RS_CYC_B = 32;
+constexpr int RS_MAX_PEERS = 16;
+__host__ __device__ inline int64_t rs_cyc_local(int64_t i, int count) {
+    return (i / ((int64_t)RS_CYC_B * count)) * RS_CYC_B + i % RS_CYC_B;
+}
+__host__ __device__ inline bool rs_cyc_owns(int64_t i, int count, int index) {
+    return (i / RS_CYC_B) % count == index;
+}
+inline int64_t rs_cyc_rows(int64_t n, int count, int index) {
+    const int64_t nblk = (n + RS_CYC_B - 1) / RS_CYC_B;
+    int64_t rows = 0;
+    for (int64_t b = index; b < nblk; b += count) rows += (b + 1) * RS_CYC_B <= n ? RS_CYC_B : n - b * RS_CYC_B;
+    return rows;
+}
+
 struct rs_knn {
+    std::recursive_mutex mu;             // serialises the ABI calls on this handle (api.cu Guard)
     rs_knn_params p{};
     int device = 0;
     cudaStream_t own_stream = nullptr;
@@ -67,6 +87,14 @@ struct rs_knn {
     int64_t col_begin = 0;               // symmetric slabs: similarity tiles left of this column are not needed
     bool force_sym = false;              // symmetric slabs: compute only j > i although the rows are a slab
     int64_t topk_rows = 0;               // rows covered by topk_idx / topk_sim
+    // cyclic row shards: cyc_R >= 2 shards, this handle is shard cyc_r and stores rows_local rows
+    int32_t cyc_R = 0, cyc_r = 0;
+    int64_t rows_local = 0;              // rows of `sims` (== row_end - row_begin unless cyclic)
+    int64_t n_work_rows = 0;             // entries of row_order the stream kernel walks
+    const double *peer_sims[RS_MAX_PEERS] = {nullptr};   // the shards' matrices (peer memory over NVLink), [cyc_r] = own
+    bool peers_ready = false;
+    struct PeerMap { unsigned char handle[64]; void *base; };
+    std::vector<PeerMap> peer_cache;     // IPC mappings opened so far (kept until destroy)
     double global_mean = 0.0, global_bias = 0.0;
     int rating_class = RS_CLASS_INT8;
 
@@ -158,6 +186,7 @@ int32_t rs_prep_planes(rs_knn *h);
 // ---- sim_stream.cu ----
 int32_t rs_sim_stream_launch(rs_knn *h);
 int32_t rs_symmetrize_launch(rs_knn *h);
+int32_t rs_mirror_launch(rs_knn *h);
 
 // ---- sim_tensor.cu ----
 int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int64_t cos_nrows);

@@ -43,6 +43,7 @@ struct PredArgs {
     const double *sims;
     int64_t ld_s;
     int64_t row_begin, row_end;
+    int32_t cyc_R, cyc_r;       // cyclic row shards (cyc_R >= 2): the handle holds the rows it owns
     const double *means, *stddevs, *bias;
     double global_mean;
     int32_t n_right;
@@ -158,11 +159,11 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
             if (lane == 0) a.out[p] = a.global_mean;
             continue;
         }
-        if (l < a.row_begin || l >= a.row_end) {           // not in this shard
+        if (l < a.row_begin || l >= a.row_end || (a.cyc_R > 1 && !rs_cyc_owns(l, a.cyc_R, a.cyc_r))) {   // not in this shard
             if (lane == 0) a.out[p] = nan_v;
             continue;
         }
-        const double *row = a.sims + (l - a.row_begin) * a.ld_s;
+        const double *row = a.sims + (a.cyc_R > 1 ? rs_cyc_local(l, a.cyc_R) : l - a.row_begin) * a.ld_s;
         const int64_t cb = a.r_ptr[r];
         const int cnt = (int)(a.r_ptr[r + 1] - cb);        // a right row has at most n_left entries
         const int32_t *ids = a.r_col + cb;
@@ -682,6 +683,7 @@ int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
     a.left = d_left; a.right = d_right; a.n = n; a.out = d_out;
     a.r_ptr = h->r_ptr; a.r_col = h->r_col; a.r_val = h->r_val;
     a.sims = h->sims; a.ld_s = h->ld_s; a.row_begin = h->row_begin; a.row_end = h->row_end;
+    a.cyc_R = h->cyc_R; a.cyc_r = h->cyc_r;
     a.means = h->means; a.stddevs = h->stddevs; a.bias = h->left_bias;
     a.global_mean = h->global_mean; a.n_right = h->n_right;
     a.k = h->p.k; a.min_k = h->p.min_k; a.knn_type = h->p.knn_type;
@@ -692,7 +694,7 @@ int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
     // (MovieLens-20M item shape: 150 test pairs per row, 5.7 GB matrix).  Stable radix sort of
     // (left id, index) — CUB, plumbing — and the kernel walks the permutation.
     a.perm = nullptr;
-    if (n >= 65536 && (size_t)(h->row_end - h->row_begin) * (size_t)h->ld_s * 8 > ((size_t)64 << 20) &&
+    if (n >= 65536 && (size_t)h->rows_local * (size_t)h->ld_s * 8 > ((size_t)64 << 20) &&
         !getenv("RS_KNN_PRED_NOSORT")) {
         void *keys_out, *iota, *perm, *tmp;
         RS_TRY(rs_scratch_get(h, 12, (size_t)n * 4, &keys_out));
@@ -741,7 +743,7 @@ int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
 }
 
 int32_t rs_topk_launch(rs_knn *h, int32_t k, int32_t *d_idx, double *d_sim) {
-    const int64_t rows = h->row_end - h->row_begin;
+    const int64_t rows = h->cyc_R > 1 ? h->rows_local : h->row_end - h->row_begin;
     if (rows <= 0) return RS_OK;
     if (k < 1 || k > TOPK_CAP / 4) {
         rs_set_error("top-k supports 1 <= k <= %d (got %d)", TOPK_CAP / 4, k);

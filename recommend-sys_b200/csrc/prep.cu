@@ -249,6 +249,11 @@ __global__ void scatter_planes_kernel(const int64_t *__restrict__ l_ptr, const i
     }
 }
 
+struct CycOwned {
+    int count, index;
+    __host__ __device__ bool operator()(const int32_t &i) const { return rs_cyc_owns(i, count, index); }
+};
+
 struct SortTmp {
     void *p = nullptr;
     size_t bytes = 0;
@@ -324,7 +329,7 @@ __global__ void right_means_kernel(const int64_t *__restrict__ r_ptr, const doub
 
 static int32_t rs_stream_jc(int32_t n_left) {
     int32_t jc = n_left < 8192 ? 128 : 256;
-    if (const char *e = getenv("RS_KNN_STREAM_JC")) jc = atoi(e) == 128 ? 128 : 256;
+    if (const char *e = getenv("RS_KNN_STREAM_JC")) { const int v = atoi(e); jc = v == 128 ? 128 : v == 512 ? 512 : 256; }
     return jc;
 }
 
@@ -510,6 +515,25 @@ int32_t rs_prep_rt(rs_knn *h) {
         RS_TRY(rs_alloc(h, &h->row_order, (size_t)h->n_left));
         row_len_kernel<<<blocks_for(h->n_left), T, 0, st>>>(h->l_ptr, h->n_left, len, ids);
         h->prof.total_launches++;
+        if (h->cyc_R > 1) {
+            // cyclic shards: all rows ordered longest first, then the owned ones picked out in that order
+            int32_t *all_sorted, *d_num;
+            RS_TRY(rs_alloc(h, &all_sorted, (size_t)h->n_left));
+            RS_TRY(rs_alloc(h, &d_num, 4));
+            size_t need = 0, need2 = 0;
+            RS_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, len, len_sorted, ids, all_sorted,
+                                                              (int)h->n_left, 0, 32, st));
+            CycOwned pred{h->cyc_R, h->cyc_r};
+            RS_CUDA(cub::DeviceSelect::If(nullptr, need2, all_sorted, h->row_order, d_num, (int)h->n_left, pred, st));
+            void *tmp;
+            RS_TRY(rs_dev_alloc(h, &tmp, need > need2 ? need : need2));
+            RS_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, need, len, len_sorted, ids, all_sorted,
+                                                              (int)h->n_left, 0, 32, st));
+            RS_CUDA(cub::DeviceSelect::If(tmp, need2, all_sorted, h->row_order, d_num, (int)h->n_left, pred, st));
+            h->n_work_rows = h->rows_local;
+            RS_CUDA(cudaGetLastError());
+            return RS_OK;
+        }
         if (h->p.store == RS_STORE_TOPK) {
             // rows are produced slab by slab into a slab-sized buffer: keep the natural order
             RS_CUDA(cudaMemcpyAsync(h->row_order, ids, (size_t)h->n_left * 4, cudaMemcpyDeviceToDevice, st));

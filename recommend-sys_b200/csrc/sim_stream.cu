@@ -43,6 +43,8 @@ struct StreamArgs {
     int64_t ld_s;
     int32_t n_left;
     int64_t row_begin, row_end;
+    int64_t n_rows;           // rows of row_order to walk
+    int cyc_R;                // >= 2: cyclic row shards, the output row is rs_cyc_local(i)
     int symmetric;            // 0: full rows; 1: only columns j > i are computed; 2: only j < i (the mirror pass fills the rest)
     unsigned long long *counter;
 };
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
     double *acc = s_acc_all + (size_t)warp * NACC * JC;
     double *s_ra = s_acc_all + (size_t)SW * NACC * JC + warp * 32;
     const int64_t Q = a.n_chunks;
-    const int64_t n_items = (a.row_end - a.row_begin) * Q;
+    const int64_t n_items = a.n_rows * Q;
     const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
     const int32_t *__restrict__ r_col = a.r_col;
     const double *__restrict__ r_dev = a.r_dev;
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
         __syncwarp();
 
         // epilogue: JC similarities of row i, coalesced
-        double *out = a.sims + (int64_t)(i - a.row_begin) * a.ld_s + j0;
+        double *out = a.sims + (a.cyc_R > 1 ? rs_cyc_local(i, a.cyc_R) : (int64_t)(i - a.row_begin)) * a.ld_s + j0;
         for (int j = lane; j < JC; j += 32) {
             const int64_t col = (int64_t)j0 + j;
             if (col >= a.n_left) break;
@@ -220,6 +222,37 @@ __global__ void symmetrize_kernel(double *__restrict__ s, int64_t ld, int32_t n,
     }
 }
 
+// Cyclic row shards: every shard computed one triangle of ITS rows (lower = 1: the cells j < i); the
+// other triangle of a row is the transpose of cells that live in the rows of other shards.  One CTA
+// moves one 32 x 32 tile: it reads the source tile from the owner's matrix — peer memory over NVLink
+// when the owner is another GPU, 256 contiguous bytes per row —, transposes it in shared memory and
+// writes it into this shard's rows.  This is the one exchange step of the sharded Fit: half the
+// matrix crosses the links once, pulled by the consumers (no staging buffer, no pack / unpack).
+struct MirrorArgs {
+    double *self;
+    const double *peer[RS_MAX_PEERS];
+    int64_t ld;
+    int32_t n;
+    int32_t count, index, lower;
+};
+__global__ void mirror_kernel(MirrorArgs a) {
+    __shared__ double tile[32][33];
+    const int64_t bI = blockIdx.y;                           // own block (local index)
+    const int64_t gI = bI * a.count + a.index, gJ = blockIdx.x;
+    if (a.lower ? gJ < gI : gJ > gI) return;                 // destination tiles: right of (left of) the diagonal
+    const double *src = a.peer[gJ % a.count];
+    const int64_t sJ = (gJ / a.count) * RS_CYC_B;            // first local row of block gJ at its owner
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int64_t sr = gJ * 32 + y, sc = gI * 32 + threadIdx.x;   // global (row, col) of the source cell
+        tile[y][threadIdx.x] = (sr < a.n && sc < a.n) ? src[(sJ + y) * a.ld + sc] : 0.0;
+    }
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int64_t r = gI * 32 + y, c = gJ * 32 + threadIdx.x;
+        if (r < a.n && c < a.n && (a.lower ? c > r : c < r)) a.self[(bI * 32 + y) * a.ld + c] = tile[threadIdx.x][y];
+    }
+}
+
 }  // namespace
 
 template <int SIM, bool SHRINK, int SYM, int JC>
@@ -249,18 +282,21 @@ int32_t rs_sim_stream_launch(rs_knn *h) {
     StreamArgs a{};
     a.l_ptr = h->l_ptr; a.l_col = h->l_col; a.l_val = h->l_val; a.l2r = h->l2r;
     a.r_ptr = h->r_ptr; a.r_col = h->r_col; a.r_dev = h->r_dev; a.cp = h->cp; a.n_chunks = h->n_chunks;
-    a.row_order = h->row_order + h->row_begin;
+    const bool cyc = h->cyc_R > 1;
+    a.row_order = cyc ? h->row_order : h->row_order + h->row_begin;
+    a.n_rows = cyc ? h->n_work_rows : h->row_end - h->row_begin;
+    a.cyc_R = h->cyc_R;
     a.pmeans = h->pmeans; a.left_bias = h->left_bias; a.right_bias = h->right_bias;
     a.global_bias = h->global_bias; a.shrinkage = h->p.shrinkage;
     a.sims = h->sims; a.ld_s = h->ld_s; a.n_left = h->n_left;
     a.row_begin = h->row_begin; a.row_end = h->row_end;
-    a.symmetric = h->force_sym ? 1 : (h->row_begin == 0 && h->row_end == h->n_left) ? (h->stream_lower ? 2 : 1) : 0;
-    if (h->row_end <= h->row_begin) return RS_OK;
+    a.symmetric = h->force_sym ? 1 : ((h->row_begin == 0 && h->row_end == h->n_left) || cyc) ? (h->stream_lower ? 2 : 1) : 0;
+    if (a.n_rows <= 0) return RS_OK;
     a.counter = reinterpret_cast<unsigned long long *>(h->d_flags + 2);
     RS_CUDA(cudaMemsetAsync(a.counter, 0, 8, h->stream));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    const int64_t items = (h->row_end - h->row_begin) * (int64_t)h->n_chunks;
+    const int64_t items = a.n_rows * (int64_t)h->n_chunks;
     int64_t grid = (int64_t)sms * 4;          // resident CTAs; warps pull work items from the counter
     if (grid > (items + SW - 1) / SW) grid = (items + SW - 1) / SW;
     switch (h->p.sim) {
@@ -279,7 +315,24 @@ int32_t rs_sim_stream_launch(rs_knn *h) {
     return RS_OK;
 }
 
+int32_t rs_mirror_launch(rs_knn *h) {
+    MirrorArgs a{};
+    a.self = h->sims;
+    for (int q = 0; q < h->cyc_R; q++) a.peer[q] = h->peer_sims[q];
+    a.peer[h->cyc_r] = h->sims;
+    a.ld = h->ld_s; a.n = h->n_left; a.count = h->cyc_R; a.index = h->cyc_r; a.lower = h->stream_lower ? 1 : 0;
+    const int64_t nblk = ((int64_t)h->n_left + RS_CYC_B - 1) / RS_CYC_B;
+    const int64_t own = (nblk - h->cyc_r + h->cyc_R - 1) / h->cyc_R;
+    if (own <= 0) return RS_OK;
+    dim3 grid((unsigned)nblk, (unsigned)own), block(32, 8);
+    mirror_kernel<<<grid, block, 0, h->stream>>>(a);
+    h->prof.total_launches++;
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
 int32_t rs_symmetrize_launch(rs_knn *h) {
+    if (h->cyc_R > 1) return RS_OK;                          // cyclic shards: rs_knn_mirror after the peers are attached
     if (!(h->row_begin == 0 && h->row_end == h->n_left)) return RS_OK;
     const unsigned t = (unsigned)((h->n_left + 31) / 32);
     dim3 grid(t, t), block(32, 8);

@@ -147,7 +147,7 @@ int64_t rs_host_synth_ratings(int32_t n_users, int32_t n_items, int64_t nnz_targ
     return w;
 }
 
-// core/data.go:134 `stat.Mean(rowSet.Ratings, nil)`: sum / n.  The restatement (oracle/knn_oracle.c) sums
+// core/data.go:134 `stat.Mean(rowSet.Ratings, nil)`: sum / n.  The CPU restatement used by the tests sums
 // sequentially; for integer ratings every order gives the same double, for other ratings gonum's
 // summation order is not pinned by any reference test (DESIGN.md "parity unpinned").
 double rs_host_mean_seq(const double *x, int64_t n) {

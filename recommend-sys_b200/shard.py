@@ -1,9 +1,16 @@
-"""Row sharding of the similarity rows across the GPUs of one box.
+"""Sharding of the similarity rows across the GPUs of one box: one process per GPU,
+torch.distributed (NCCL over NVLink; gloo in the CPU tests) is the plumbing, not the product.
 
-Every rank holds the full (replicated) rating matrix and owns a contiguous block of left rows;
-it computes that block against all N rows and selects top-k locally.  The only exchange is one
-all-gather of the fixed-size neighbour lists (int32 idx, float64 sim)[rows][k] over NCCL/NVLink
-(gloo in the CPU tests).  torch.distributed is the plumbing, not the product."""
+Three schemes, all with the rating matrix replicated on every GPU (it replaces the goroutine row
+split of core/knn.go:192-216):
+  * contiguous row shards (`shard_rows`): a rank computes full rows [begin, end) against all N rows
+    (tensor path: 128-aligned) and all-gathers neighbour lists / predictions;
+  * symmetric slabs (top-k only, config 4): slabs dealt in snake order, every pair computed once,
+    partial neighbour lists all-gathered and united;
+  * CYCLIC ROW SHARDS (`ShardedKNN`, the strong-scaling form of Fit + Predict): rows dealt in blocks
+    of 32, every pair computed once by the exact sparse kernel, the other triangle of a rank's rows
+    pulled from the peers' matrices over NVLink (rs_knn_mirror, CUDA IPC), the test pairs routed to
+    the owner of their left row, predictions all-gathered."""
 from __future__ import annotations
 
 
@@ -89,3 +96,129 @@ def allgather_predictions(pred_local, counts, group=None):
     out = torch.empty(world * m, dtype=torch.float64, device=pred_local.device)
     dist.all_gather_into_tensor(out, pad, group=group)
     return torch.cat([out[r * m: r * m + c] for r, c in enumerate(counts)])
+
+
+# ---------------------------------------------------------------------------------------------
+# Cyclic row shards: Fit + Predict of ONE matrix on all ranks (strong scaling)
+# ---------------------------------------------------------------------------------------------
+def route_pairs(left_inner, world):
+    """Owner rank of every test pair: the shard that owns its left row (cyclic, blocks of 32); pairs
+    with an unknown left id (cold start, answered with GlobalMean by any shard) are spread evenly."""
+    import numpy as np
+
+    from . import core
+
+    left_inner = np.asarray(left_inner)
+    owner = core.cyclic_owner(np.maximum(left_inner, 0), world)
+    cold = left_inner < 0
+    if cold.any():
+        owner = owner.copy()
+        owner[cold] = np.arange(int(cold.sum())) % world
+    return owner
+
+
+def attach_peers_and_mirror(handle, group=None):
+    """The exchange step of a cyclic-sharded Fit.  Every rank waits for its own Fit, the 72-byte
+    (CUDA IPC handle, offset) records are all-gathered — which is also the barrier that tells a rank
+    every peer's triangle is complete — and the rank pulls the other triangle of its rows from the
+    peers' matrices (rs_knn_mirror: P2P loads over NVLink)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    hb, off = handle.peer_export()
+    rec = np.concatenate([hb, np.array([off], dtype=np.int64).view(np.uint8)])
+    handle.synchronize()                      # own triangle complete before anybody is told so
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mine = torch.from_numpy(rec).to(dev)
+    allr = torch.empty(world * 72, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allr, mine, group=group)
+    allr = allr.cpu().numpy().reshape(world, 72)
+    handle.peer_import(allr[:, :64].copy(), allr[:, 64:].copy().view(np.int64).reshape(world))
+    handle.mirror()
+
+
+class ShardedKNN:
+    """KNN.Fit / DataSet.Predict of ONE training set on all ranks of the process group — the
+    multi-GPU form of core/knn.go:143-217 + core/data.go:98-105.  Wraps a core.KNN:
+
+        est = ShardedKNN(rs.NewKNNWithMean(params))      # same constructors, same Parameters
+        est.Fit(train)                                   # every rank passes the same TrainSet
+        preds = est.PredictBatch(users, items)           # full prediction vector on every rank
+
+    Fit uploads 1/world of the ratings per rank from (pinned) host memory and all-gathers them over
+    NVLink, so the host->device traffic is divided by the number of GPUs."""
+
+    def __init__(self, knn, group=None):
+        import torch.distributed as dist
+
+        self.knn = knn
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def Fit(self, trainSet):
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        k = self.knn
+        sim, left, right, n_left, n_right, lb, rbias, gb = k._prepare(trainSet)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nnz = len(left)
+        per = (nnz + self.world - 1) // self.world
+        lo, hi = min(nnz, self.rank * per), min(nnz, (self.rank + 1) * per)
+
+        def gather(a, dtype):
+            part = torch.zeros(per, dtype=dtype, device=dev)
+            part[: hi - lo].copy_(torch.from_numpy(a[lo:hi]), non_blocking=True)     # H2D of this rank's slice only
+            out = torch.empty(per * self.world, dtype=dtype, device=dev)
+            dist.all_gather_into_tensor(out, part, group=self.group)
+            return out
+
+        d_left, d_right = gather(left, torch.int32), gather(right, torch.int32)
+        d_rating = gather(trainSet.Ratings, torch.float64)
+        d_lb = torch.from_numpy(np.ascontiguousarray(lb, dtype=np.float64)).to(dev) if lb is not None else None
+        d_rb = torch.from_numpy(np.ascontiguousarray(rbias, dtype=np.float64)).to(dev) if rbias is not None else None
+        k.Close()
+        k._h = k._new_handle(sim, shard_count=self.world, shard_index=self.rank, device=dev.index)
+        k._h.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        k._h.fit_device(d_left.data_ptr(), d_right.data_ptr(), d_rating.data_ptr(), nnz, n_left, n_right,
+                        trainSet.GlobalMean, d_lb.data_ptr() if d_lb is not None else 0,
+                        d_rb.data_ptr() if d_rb is not None else 0, gb)
+        self._keep = (d_left, d_right, d_rating, d_lb, d_rb)
+        attach_peers_and_mirror(k._h, self.group)
+        k._after_fit()
+        return self
+
+    def PredictBatch(self, userIDs, itemIDs):
+        import numpy as np
+        import torch
+
+        k = self.knn
+        iu = k.Data.convert_users(userIDs)
+        ii = k.Data.convert_items(itemIDs)
+        left, right = (iu, ii) if k._userBased else (ii, iu)
+        owner = route_pairs(left, self.world)
+        order = np.argsort(owner, kind="stable")
+        counts = np.bincount(owner, minlength=self.world).tolist()
+        mine = order[sum(counts[: self.rank]): sum(counts[: self.rank + 1])]
+        dev = torch.device("cuda", torch.cuda.current_device())
+        d_l = torch.from_numpy(np.ascontiguousarray(left[mine], dtype=np.int32)).to(dev)
+        d_r = torch.from_numpy(np.ascontiguousarray(right[mine], dtype=np.int32)).to(dev)
+        d_o = torch.empty(max(1, len(mine)), dtype=torch.float64, device=dev)
+        if len(mine):
+            k._h.predict_batch_device(d_l.data_ptr(), d_r.data_ptr(), len(mine), d_o.data_ptr())
+        allp = allgather_predictions(d_o[: len(mine)], counts, group=self.group)
+        out = np.empty(len(left), dtype=np.float64)
+        out[order] = allp.cpu().numpy()
+        return out
+
+    def Predict(self, userID, itemID):
+        import numpy as np
+
+        return float(self.PredictBatch(np.array([userID]), np.array([itemID]))[0])
+
+    def Close(self):
+        self.knn.Close()

@@ -81,6 +81,81 @@ def test_sims_bit_exact_both_triangles(ml100k, sim, user_based, tri, monkeypatch
     assert bits_equal(got, got.T)
 
 
+# ---- cyclic row shards (the multi-GPU Fit + Predict): every shard computes one triangle of its rows,
+# the mirror step pulls the other one from the peers; here all shards live on one GPU ----
+@pytest.mark.parametrize("tri", ["upper", "lower"])
+@pytest.mark.parametrize("count", [2, 3])
+def test_cyclic_row_shards_equal_full(ml100k, count, tri, monkeypatch):
+    monkeypatch.setenv("RS_KNN_STREAM_TRI", tri)
+    u, i, r = split(ml100k["u1_base"])
+    ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
+    base = {"sim": rs.Pearson, "userBased": False, "k": 40}
+    full = rs.NewKNNWithMean(rs.Parameters(base))
+    full.Fit(ts)
+    want = full.Sims
+    tu, ti, _ = split(ml100k["u1_test"])
+    want_pred = full.PredictBatch(tu, ti)
+    shards = []
+    for q in range(count):
+        est = rs.NewKNNWithMean(rs.Parameters(dict(base, shardCount=count, shardIndex=q)))
+        est.Fit(ts)
+        shards.append(est)
+    with pytest.raises(rs.core.RsError):          # one triangle only until the mirror step has run
+        shards[0].PredictBatch(tu[:4], ti[:4])
+    for est in shards:
+        est._h.synchronize()
+    for est in shards:
+        est._h.peer_import_local([x._h for x in shards])
+        est._h.mirror()
+    got_pred = np.full(len(tu), np.nan)
+    left = ts.convert_items(ti)
+    owner = rs.shard.route_pairs(left, count)
+    for q, est in enumerate(shards):
+        rows = est._h.owned_rows()
+        assert bits_equal(est.Sims, want[rows]), (q, count, tri)
+        mine = np.flatnonzero(owner == q)
+        got_pred[mine] = est.PredictBatch(tu[mine], ti[mine])
+        other = np.flatnonzero((owner != q) & (left >= 0))[:16]
+        assert np.isnan(est.PredictBatch(tu[other], ti[other])).all()     # rows of another shard: NaN
+    assert bits_equal(got_pred, want_pred)
+    assert sorted(np.concatenate([e._h.owned_rows() for e in shards]).tolist()) == list(range(want.shape[0]))
+    for est in shards:
+        est.Close()
+
+
+def test_k_is_read_at_predict_time(ml100k):
+    # core/knn.go:80-81: k / mink are read by Predict, so SetParams after Fit changes the answer
+    est, ref = fit_pair(ml100k["u2_base"], "msd", "basic", True, k=40)
+    _, ref10 = None, None
+    u, i, r = split(ml100k["u2_test"])
+    before = est.PredictBatch(u, i)
+    est.Params["k"] = 10
+    after = est.PredictBatch(u, i)
+    est10, ref10 = fit_pair(ml100k["u2_base"], "msd", "basic", True, k=10)
+    assert bits_equal(after, ref10.predict_batch(u, i, n_threads=8))
+    assert not bits_equal(before, after)
+
+
+def test_concurrent_predict_on_one_handle(ml100k):
+    # the reference's Predict is read-only and goroutine-safe; calls on one handle are serialised here
+    import threading
+
+    est, ref = fit_pair(ml100k["u3_base"], "cosine", "basic", True)
+    u, i, r = split(ml100k["u3_test"])
+    want = ref.predict_batch(u, i, n_threads=8)
+    parts = np.array_split(np.arange(len(u)), 8)
+    out = [None] * len(parts)
+
+    def work(t):
+        for _ in range(5):
+            out[t] = est.PredictBatch(u[parts[t]], i[parts[t]])
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(len(parts))]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert bits_equal(np.concatenate(out), want)
+
+
 # ---- arbitrary float64 ratings (continuous values, thousands of distinct ones): the stream path
 # reads the values themselves, so anything the reference accepts is fitted (core/sim.go has no
 # notion of a rating scale) ----
