@@ -53,6 +53,8 @@ void free_fit_state(rs_knn *h) {
     h->cp = nullptr;
     h->l2r = nullptr;
     h->row_order = nullptr;
+    h->n_heavy = 0;
+    h->avec = nullptr;
     h->planes = nullptr;
     h->row_cnt = h->row_sum = nullptr;
     h->sims = nullptr;

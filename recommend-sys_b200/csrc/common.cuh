@@ -127,6 +127,7 @@ struct rs_knn {
     int32_t *row_cnt = nullptr;   // ratings per left row and their integer sum (tensor path, Pearson)
     int32_t *row_sum = nullptr;
     int64_t max_row_cnt = 0;
+    int32_t max_right_len = 0;    // longest right row = most candidates one prediction can have
     double triples = 0.0;         // co-rated triples of the full matrix: sum over right rows of cnt*(cnt-1)/2
     double *right_bias = nullptr;
     // Slope One: the right rows (users) in DATASET order — left ids only — and their means
@@ -144,6 +145,8 @@ struct rs_knn {
     int64_t *l2r = nullptr;
     int32_t *perm_lr = nullptr, *perm_rl = nullptr, *perm_tmp = nullptr;  // CSR position -> input row (arena, valid until the next Fit)
     int32_t *row_order = nullptr;  // left rows sorted by descending length
+    int32_t n_heavy = 0;           // the first n_heavy of them run in dense-row mode (sim_stream.cu)
+    double *avec = nullptr;        // [n_heavy][n_right] a-side vectors of the heavy rows
     // int8 planes X^2, M, X of the left matrix, [3][k_pad / 256][n_pad][256] (tensor path)
     int8_t *planes = nullptr;
     int64_t tc_npad = 0, tc_kpad = 0;

@@ -52,6 +52,8 @@ struct PredArgs {
     double *nb_sims;
     int32_t *nb_count;
     int32_t nb_cap;
+    uint64_t *gstage;       // per-warp spill of the staged keys beyond the shared-memory capacity
+    int64_t gcap;           // keys per warp in gstage
 };
 
 // =====================================================================================
@@ -138,6 +140,10 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
     uint64_t *ckey = s_key[warp];
     uint32_t *cpos = s_pos[warp];
     uint64_t *sbuf = reinterpret_cast<uint64_t *>(s_stage) + (size_t)warp * scap;
+    // keys that do not fit the shared-memory stage are parked in a per-warp slice of global memory
+    // (written once, re-read coalesced by the selection passes — it stays in L2), NOT gathered again:
+    // a second dependent gather per pass was 39 % of this kernel's stall samples (profiles/r02_predict_notes.md)
+    uint64_t *gbuf = a.gstage + ((size_t)blockIdx.x * SEL_WARPS + warp) * (size_t)a.gcap - scap;
     const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
     const uint32_t lt_mask = (1u << lane) - 1u;
 
@@ -188,6 +194,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
                 const double sv = sv4[u];
                 const uint64_t key = (sv == sv) ? rs_sim_key(sv) : 0ull;
                 if (e < scap) sbuf[e] = key;
+                else if (e < cnt) gbuf[e] = key;
                 if (key) { valid++; klo = key < klo ? key : klo; khi = key > khi ? key : khi; }
             }
         }
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
                 for (int x = lane; x < 256; x += 32) hist[x] = 0;
                 __syncwarp();
                 for (int e = lane; e < cnt; e += 32) {
-                    const uint64_t key = e < scap ? sbuf[e] : sim_key_or_zero(row[ids[e]]);
+                    const uint64_t key = e < scap ? sbuf[e] : gbuf[e];
                     if (key >= wlo && key <= khi) atomicAdd(&hist[(uint32_t)((key - wlo) >> sh)], 1u);
                 }
                 __syncwarp();
@@ -281,7 +288,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
                 const uint64_t b_hi = b_lo + ((1ull << sh) - 1ull);
                 uint64_t nlo = ~0ull, nhi = 0ull;
                 for (int e = lane; e < cnt; e += 32) {
-                    const uint64_t key = e < scap ? sbuf[e] : sim_key_or_zero(row[ids[e]]);
+                    const uint64_t key = e < scap ? sbuf[e] : gbuf[e];
                     if (key >= b_lo && key <= b_hi && key <= khi) { nlo = key < nlo ? key : nlo; nhi = key > nhi ? key : nhi; }
                 }
 #pragma unroll
@@ -306,7 +313,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
         for (int base = 0; base < cnt; base += 32) {
             const int e = base + lane;
             uint64_t key = 0ull;
-            if (e < cnt) key = e < scap ? sbuf[e] : sim_key_or_zero(row[ids[e]]);
+            if (e < cnt) key = e < scap ? sbuf[e] : gbuf[e];
             bool take = key >= thr;
             if (tie_take >= 0) {
                 const bool tie = key == tie_key;
@@ -732,6 +739,14 @@ int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
     const size_t smem = (size_t)SEL_WARPS * scap * sizeof(double);
     const int64_t per_sm = smem ? (int64_t)(200 * 1024) / (int64_t)(smem + 16 * 1024) : 8;
     if (blocks > (int64_t)sms * (per_sm > 0 ? per_sm : 1)) blocks = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
+    {
+        // global spill of the staged keys: one slice per resident warp, sized by the longest right row
+        const int64_t gcap = h->max_right_len > scap ? (((int64_t)h->max_right_len - scap + 31) / 32 * 32) : 32;
+        void *g;
+        RS_TRY(rs_scratch_get(h, 17, (size_t)blocks * SEL_WARPS * (size_t)gcap * 8, &g));
+        a.gstage = reinterpret_cast<uint64_t *>(g);
+        a.gcap = gcap;
+    }
     // register capacity of the selection kernel: room for k plus a boundary bucket
     if (h->p.k <= 44) RS_TRY(launch_select<2>(a, (unsigned)blocks, smem, scap, h->stream));
     else if (h->p.k <= 104) RS_TRY(launch_select<4>(a, (unsigned)blocks, smem, scap, h->stream));

@@ -249,6 +249,15 @@ __global__ void scatter_planes_kernel(const int64_t *__restrict__ l_ptr, const i
     }
 }
 
+// number of leading rows of the longest-first order whose length reaches `min_len`
+__global__ void count_heavy_kernel(const int32_t *__restrict__ row_order, int64_t n, const int64_t *__restrict__ l_ptr,
+                                   int64_t min_len, int32_t *out) {
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    const int32_t i = row_order[x];
+    if (l_ptr[i + 1] - l_ptr[i] >= min_len) atomicAdd(out, 1);
+}
+
 struct CycOwned {
     int count, index;
     __host__ __device__ bool operator()(const int32_t &i) const { return rs_cyc_owns(i, count, index); }
@@ -282,12 +291,18 @@ int bits_for(int32_t n) {
 
 // sum over right rows of cnt*(cnt-1)/2 = co-rated triples (i < j, common right id): the work of the
 // stream path, used by the Fit path model (api.cu)
-__global__ void triples_kernel(const int32_t *__restrict__ rcount, int32_t nr, unsigned long long *out) {
+__global__ void triples_kernel(const int32_t *__restrict__ rcount, int32_t nr, unsigned long long *out,
+                               int32_t *max_len) {
     unsigned long long acc = 0;
+    int32_t mx = 0;
     for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nr; c += (int64_t)gridDim.x * blockDim.x) {
         const unsigned long long n = (unsigned long long)rcount[c];
         acc += n * (n - (n ? 1 : 0)) / 2;
+        mx = rcount[c] > mx ? rcount[c] : mx;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const int32_t v = __shfl_xor_sync(0xffffffffu, mx, o); mx = v > mx ? v : mx; }
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_len, mx);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
@@ -360,7 +375,7 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
 
     iota_validate_kernel<<<blocks_for(nnz), T, 0, st>>>(d_left, d_right, d_rating, nnz, nl, nr, idx, lcount,
                                                        rcount, h->d_flags);
-    triples_kernel<<<148, T, 0, st>>>(rcount, nr, reinterpret_cast<unsigned long long *>(h->d_flags + 6));
+    triples_kernel<<<148, T, 0, st>>>(rcount, nr, reinterpret_cast<unsigned long long *>(h->d_flags + 6), h->d_flags + 15);
     h->stream_jc = rs_stream_jc(nl);
     incidence_kernel<<<148, T, 0, st>>>(lcount, nl, h->stream_jc, reinterpret_cast<unsigned long long *>(h->d_flags + 8));
     h->prof.total_launches += 3;
@@ -370,6 +385,7 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     RS_CUDA(cudaStreamSynchronize(st));
     flags = fl8[0];
     { unsigned long long t; memcpy(&t, fl8 + 6, 8); h->triples = (double)t; }
+    h->max_right_len = fl8[15];
     { unsigned long long t[2]; memcpy(t, fl8 + 8, 16); h->inc_upper = (double)t[0]; h->inc_lower = (double)t[1]; }
     h->stream_lower = h->inc_lower < h->inc_upper;
     if (const char *e = getenv("RS_KNN_STREAM_TRI")) h->stream_lower = !strcmp(e, "lower");   // tests: force a triangle
@@ -490,6 +506,35 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     return RS_OK;
 }
 
+// Dense-row mode (sim_stream.cu): rows of at least RS_KNN_DENSE_MIN entries — the leading rows of the
+// longest-first order — are probed instead of walked.  OFF unless the variable is set: the probe costs one
+// L2 gather per entry of every column visited, so it only pays at hit rates no rating matrix of the
+// BASELINE shapes reaches.  Measured on the MovieLens-20M shape (profiles/r02_stream_notes.md): rows of
+// >= 1/32 of the right ids probed: Fit 44 -> 82 ms; >= 8000 entries: 64 ms; only the two rows rated by half
+// of all users: 54 ms (the probe kernel's own serial tail).  Kept because it is bit-exact, tested, and the
+// right tool for a matrix with genuinely dense rows.
+static int32_t pick_heavy_rows(rs_knn *h, const int32_t *order, int64_t n_rows) {
+    cudaStream_t st = h->stream;
+    int64_t min_len = (int64_t)1 << 40;
+    if (const char *e = getenv("RS_KNN_DENSE_MIN")) min_len = atoll(e);      // experiments / tests; 0 = every row
+    h->n_heavy = 0;
+    h->avec = nullptr;
+    if (n_rows <= 0) return RS_OK;
+    int32_t *d_cnt = h->d_flags + 14;
+    RS_CUDA(cudaMemsetAsync(d_cnt, 0, 4, st));
+    count_heavy_kernel<<<blocks_for(n_rows), T, 0, st>>>(order, n_rows, h->l_ptr, min_len, d_cnt);
+    int32_t cnt = 0;
+    RS_CUDA(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+    RS_CUDA(cudaStreamSynchronize(st));
+    // bounded scratch: at most 2 GiB of a-side vectors
+    const int64_t cap = (int64_t)(2ll << 30) / ((int64_t)h->n_right * 8);
+    if (cnt > cap) cnt = (int32_t)cap;
+    h->n_heavy = cnt;
+    h->prof.total_launches++;
+    if (cnt > 0) RS_TRY(rs_alloc(h, &h->avec, (size_t)cnt * (size_t)h->n_right));
+    return RS_OK;
+}
+
 int32_t rs_prep_rt(rs_knn *h) {
     cudaStream_t st = h->stream;
     h->n_chunks = (int32_t)(((int64_t)h->n_left + h->stream_jc - 1) / h->stream_jc);
@@ -531,6 +576,7 @@ int32_t rs_prep_rt(rs_knn *h) {
                                                               (int)h->n_left, 0, 32, st));
             RS_CUDA(cub::DeviceSelect::If(tmp, need2, all_sorted, h->row_order, d_num, (int)h->n_left, pred, st));
             h->n_work_rows = h->rows_local;
+            RS_TRY(pick_heavy_rows(h, h->row_order, h->n_work_rows));
             RS_CUDA(cudaGetLastError());
             return RS_OK;
         }
@@ -547,6 +593,7 @@ int32_t rs_prep_rt(rs_knn *h) {
         RS_TRY(rs_dev_alloc(h, &tmp, need));
         RS_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, need, len + rb, len_sorted + rb, ids + rb,
                                                           h->row_order + rb, (int)rows, 0, 32, st));
+        RS_TRY(pick_heavy_rows(h, h->row_order + rb, rows));
     }
     RS_CUDA(cudaGetLastError());
     return RS_OK;

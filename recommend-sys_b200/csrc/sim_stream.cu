@@ -47,6 +47,14 @@ struct StreamArgs {
     int cyc_R;                // >= 2: cyclic row shards, the output row is rs_cyc_local(i)
     int symmetric;            // 0: full rows; 1: only columns j > i are computed; 2: only j < i (the mirror pass fills the rest)
     unsigned long long *counter;
+    // dense-row mode (sim_dense_rows_kernel): the first n_heavy rows of row_order, their a-side vectors
+    const int32_t *heavy_rows;
+    int32_t n_heavy;
+    const double *avec;       // [n_heavy][n_right]: a-side term of (row, c), NaN = not rated
+    int32_t n_right;
+    const double *l_pmeans_b; // b-side mean of a column (== pmeans)
+    int sim;
+    unsigned long long *counter2;
 };
 
 constexpr int G = 8;   // columns whose first 32 raters are loaded together (must divide 32)
@@ -200,6 +208,107 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Dense-row mode.  A row that holds a sizeable fraction of all right ids (a blockbuster item: 78 k of
+// 138 k users on the MovieLens-20M shape) is a bad work item for the column walk above — one warp
+// walks its tens of thousands of entries serially, a tail of > 20 ms that no amount of GPUs
+// shortens — and a good one for a probe: its a-side terms are laid out as a dense vector over the
+// right ids (NaN = not rated, L2 resident), and every LANE owns one column j of the triangle, walks
+// j's own id-sorted entries and probes the vector.  The accumulators live in registers, each
+// receives its terms in ascending right id — the reference's order (core/sim.go:65-79) — and no
+// lane ever waits for another.  Work = the entries of the columns visited, worth it when the hit
+// rate (the row's density) is a few per cent or more; rs_prep_rt picks the rows.
+template <int SIM, bool SHRINK>
+__global__ void __launch_bounds__(256) sim_dense_rows_kernel(StreamArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t QD = ((int64_t)a.n_left + 31) / 32;
+    const int64_t n_items = (int64_t)a.n_heavy * QD;
+    const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(a.counter2, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if ((int64_t)item >= n_items) break;
+        const int32_t hx = (int32_t)((int64_t)item / QD);
+        const int32_t i = a.heavy_rows[hx];
+        const int64_t j0 = ((int64_t)item % QD) * 32;
+        if (a.symmetric == 1 && j0 + 32 <= i) continue;      // only j > i (and the diagonal cell)
+        if (a.symmetric == 2 && j0 > i) continue;            // only j < i (and the diagonal cell)
+        const int64_t j = j0 + lane;
+        bool want = j < a.n_left && j != i;
+        if (a.symmetric == 1) want = want && j > i;
+        if (a.symmetric == 2) want = want && j < i;
+        const double *__restrict__ av = a.avec + (int64_t)hx * a.n_right;
+        double m = 0.0, n = 0.0, l = 0.0, cnt = 0.0;
+        if (want) {
+            const int64_t b = a.l_ptr[j], e = a.l_ptr[j + 1];
+            double bj = 0.0;
+            if (SIM == RS_SIM_PEARSON) bj = a.pmeans[j];
+            if (SIM == RS_SIM_PEARSON_BASELINE) bj = a.global_bias + a.left_bias[j];
+            int64_t x = b;
+            for (; x + 4 <= e; x += 4) {                     // 4 probes in flight per lane
+                int32_t c4[4];
+                double y4[4], ra4[4];
+#pragma unroll
+                for (int v = 0; v < 4; v++) { c4[v] = a.l_col[x + v]; y4[v] = a.l_val[x + v]; }
+#pragma unroll
+                for (int v = 0; v < 4; v++) ra4[v] = av[c4[v]];
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    const double ra = ra4[v];
+                    if (ra == ra) {
+                        double rb = y4[v];
+                        if (SIM == RS_SIM_PEARSON) rb = y4[v] - bj;                                   // core/sim.go:74
+                        if (SIM == RS_SIM_PEARSON_BASELINE) { const double bb = bj + a.right_bias[c4[v]]; rb = y4[v] - bb; }
+                        if (SIM == RS_SIM_MSD) { const double d = ra - rb; m += d * d; n += 1.0; }   // core/sim.go:37-38
+                        else { m += ra * ra; n += rb * rb; l += ra * rb; if (SHRINK) cnt += 1.0; }   // core/sim.go:19-21 / :75-77
+                    }
+                }
+            }
+            for (; x < e; x++) {
+                const int32_t c = a.l_col[x];
+                const double y = a.l_val[x];
+                const double ra = av[c];
+                if (ra == ra) {
+                    double rb = y;
+                    if (SIM == RS_SIM_PEARSON) rb = y - bj;
+                    if (SIM == RS_SIM_PEARSON_BASELINE) { const double bb = bj + a.right_bias[c]; rb = y - bb; }
+                    if (SIM == RS_SIM_MSD) { const double d = ra - rb; m += d * d; n += 1.0; }
+                    else { m += ra * ra; n += rb * rb; l += ra * rb; if (SHRINK) cnt += 1.0; }
+                }
+            }
+        }
+        double s;
+        if (SIM == RS_SIM_MSD) s = 1.0 / (m / n + 1.0);                               // core/sim.go:43
+        else s = l / (sqrt(m) * sqrt(n));                                            // core/sim.go:24 / :80
+        if (SHRINK) s = (cnt - 1.0) / (cnt - 1.0 + a.shrinkage) * s;
+        if (j == i) { s = nan_v; want = true; }                                       // diagonal stays NaN
+        if (want && j < a.n_left)
+            a.sims[(a.cyc_R > 1 ? rs_cyc_local(i, a.cyc_R) : (int64_t)(i - a.row_begin)) * a.ld_s + j] = s;
+    }
+}
+
+// a-side vector of a heavy row: avec[hx][c] = the term the reference combines for (row, c)
+// (core/sim.go:18 / :73), NaN where the row has no rating
+template <int SIM>
+__global__ void fill_avec_kernel(StreamArgs a, double *__restrict__ avec) {
+    const int32_t hx = blockIdx.y;
+    const int32_t i = a.heavy_rows[hx];
+    double ai = 0.0;
+    if (SIM == RS_SIM_PEARSON) ai = a.pmeans[i];
+    if (SIM == RS_SIM_PEARSON_BASELINE) ai = a.global_bias + a.left_bias[i];
+    const int64_t b = a.l_ptr[i], e = a.l_ptr[i + 1];
+    for (int64_t x = b + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < e; x += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t c = a.l_col[x];
+        const double v = a.l_val[x];
+        double ra = v;
+        if (SIM == RS_SIM_PEARSON) ra = v - ai;                                                       // core/sim.go:73
+        if (SIM == RS_SIM_PEARSON_BASELINE) { const double bb = ai + a.right_bias[c]; ra = v - bb; }
+        avec[(int64_t)hx * a.n_right + c] = ra;
+    }
+}
+
 // Mirror the computed upper block-triangle into the lower one: the three similarities are
 // bit-symmetric (sums and products commute), which is why the reference can write
 // Sims[j][i] = Sims[i][j] (core/knn.go:205-208).  32x32 tiles through shared memory,
@@ -278,6 +387,31 @@ static int32_t launch_stream(rs_knn *h, const StreamArgs &s, int grid) {
     return s.symmetric ? launch_stream_sym<SIM, SHRINK, 1>(h, s, grid) : launch_stream_sym<SIM, SHRINK, 0>(h, s, grid);
 }
 
+template <int SIM, bool SHRINK>
+static int32_t launch_dense(rs_knn *h, const StreamArgs &a) {
+    cudaStream_t st = h->stream;
+    RS_CUDA(cudaMemsetAsync(h->avec, 0xFF, (size_t)a.n_heavy * (size_t)a.n_right * 8, st));     // NaN = not rated
+    dim3 fgrid(8, (unsigned)a.n_heavy);
+    fill_avec_kernel<SIM><<<fgrid, 256, 0, st>>>(a, h->avec);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    sim_dense_rows_kernel<SIM, SHRINK><<<sms * 8, 256, 0, st>>>(a);
+    h->prof.total_launches += 2;
+    return RS_OK;
+}
+
+static int32_t rs_dense_rows_launch(rs_knn *h, const StreamArgs &a) {
+    switch (h->p.sim) {
+    case RS_SIM_COSINE: return launch_dense<RS_SIM_COSINE, false>(h, a);
+    case RS_SIM_MSD: return launch_dense<RS_SIM_MSD, false>(h, a);
+    case RS_SIM_PEARSON: return launch_dense<RS_SIM_PEARSON, false>(h, a);
+    case RS_SIM_PEARSON_BASELINE:
+        return h->p.shrinkage > 0.0 ? launch_dense<RS_SIM_PEARSON_BASELINE, true>(h, a)
+                                    : launch_dense<RS_SIM_PEARSON_BASELINE, false>(h, a);
+    default: rs_set_error("unknown similarity %d", h->p.sim); return RS_ERR_INVALID;
+    }
+}
+
 int32_t rs_sim_stream_launch(rs_knn *h) {
     StreamArgs a{};
     a.l_ptr = h->l_ptr; a.l_col = h->l_col; a.l_val = h->l_val; a.l2r = h->l2r;
@@ -291,14 +425,26 @@ int32_t rs_sim_stream_launch(rs_knn *h) {
     a.sims = h->sims; a.ld_s = h->ld_s; a.n_left = h->n_left;
     a.row_begin = h->row_begin; a.row_end = h->row_end;
     a.symmetric = h->force_sym ? 1 : ((h->row_begin == 0 && h->row_end == h->n_left) || cyc) ? (h->stream_lower ? 2 : 1) : 0;
-    if (a.n_rows <= 0) return RS_OK;
+    // the first n_heavy rows of the (longest-first) order go to the dense-row kernel
+    const int32_t n_heavy = h->n_heavy;
+    a.heavy_rows = a.row_order;
+    a.n_heavy = n_heavy;
+    a.avec = h->avec;
+    a.n_right = h->n_right;
+    a.row_order += n_heavy;
+    a.n_rows -= n_heavy;
+    a.counter2 = reinterpret_cast<unsigned long long *>(h->d_flags + 12);
+    if (a.n_rows + n_heavy <= 0) return RS_OK;
     a.counter = reinterpret_cast<unsigned long long *>(h->d_flags + 2);
     RS_CUDA(cudaMemsetAsync(a.counter, 0, 8, h->stream));
+    RS_CUDA(cudaMemsetAsync(a.counter2, 0, 8, h->stream));
+    if (n_heavy > 0) RS_TRY(rs_dense_rows_launch(h, a));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const int64_t items = a.n_rows * (int64_t)h->n_chunks;
     int64_t grid = (int64_t)sms * 4;          // resident CTAs; warps pull work items from the counter
     if (grid > (items + SW - 1) / SW) grid = (items + SW - 1) / SW;
+    if (a.n_rows <= 0) { RS_CUDA(cudaGetLastError()); return RS_OK; }
     switch (h->p.sim) {
     case RS_SIM_COSINE: RS_TRY((launch_stream<RS_SIM_COSINE, false>(h, a, (int)grid))); break;
     case RS_SIM_MSD: RS_TRY((launch_stream<RS_SIM_MSD, false>(h, a, (int)grid))); break;

@@ -87,6 +87,7 @@ def test_sims_bit_exact_both_triangles(ml100k, sim, user_based, tri, monkeypatch
 @pytest.mark.parametrize("count", [2, 3])
 def test_cyclic_row_shards_equal_full(ml100k, count, tri, monkeypatch):
     monkeypatch.setenv("RS_KNN_STREAM_TRI", tri)
+    monkeypatch.setenv("RS_KNN_DENSE_MIN", "200")      # some rows of every shard in dense-row mode
     u, i, r = split(ml100k["u1_base"])
     ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
     base = {"sim": rs.Pearson, "userBased": False, "k": 40}
@@ -154,6 +155,27 @@ def test_concurrent_predict_on_one_handle(ml100k):
     [t.start() for t in ths]
     [t.join() for t in ths]
     assert bits_equal(np.concatenate(out), want)
+
+
+# ---- dense-row mode of the exact sparse Fit (rows holding a large share of the right ids are probed
+# instead of walked): every row (min 0), a mix (rows of >= 150 entries), both triangles, a row shard ----
+@pytest.mark.parametrize("dense_min", ["0", "150"])
+@pytest.mark.parametrize("tri", ["upper", "lower"])
+@pytest.mark.parametrize("sim", ["cosine", "msd", "pearson"])
+def test_dense_row_mode_bit_exact(ml100k, sim, tri, dense_min, monkeypatch):
+    monkeypatch.setenv("RS_KNN_STREAM_TRI", tri)
+    monkeypatch.setenv("RS_KNN_DENSE_MIN", dense_min)
+    est, ref = fit_pair(ml100k["u2_base"], sim, "basic", False, extra={"simPath": "stream"})
+    got, want = est.Sims, ref.sims()
+    assert np.isnan(np.diag(got)).all()
+    assert bits_equal(got, want)
+    n = got.shape[0]
+    b, e = n // 4, n // 4 + 300
+    part = rs.NewKNN(rs.Parameters({"sim": SIMS[sim], "userBased": False, "simPath": "stream",
+                                    "rowBegin": b, "rowEnd": e}))
+    u, i, r = split(ml100k["u2_base"])
+    part.Fit(rs.NewTrainSet(rs.NewRawSet(u, i, r)))
+    assert bits_equal(part.Sims, want[b:e])
 
 
 # ---- arbitrary float64 ratings (continuous values, thousands of distinct ones): the stream path
