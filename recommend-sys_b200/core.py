@@ -137,6 +137,14 @@ def host_lib():
                                         C.c_void_p]
     L.rs_host_mean_seq.restype = C.c_double
     L.rs_host_mean_seq.argtypes = [C.c_void_p, C.c_int64]
+    L.rs_host_save_neighbors.restype = C.c_int32
+    L.rs_host_save_neighbors.argtypes = [C.c_char_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    L.rs_host_load_neighbors.restype = C.c_int32
+    L.rs_host_load_neighbors.argtypes = [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_void_p,
+                                         C.c_void_p]
+    L.rs_host_load_ratings.restype = C.c_int64
+    L.rs_host_load_ratings.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int64]
     L.rs_host_convert_dense.restype = None
     L.rs_host_convert_dense.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     _host_lib = L
@@ -209,6 +217,7 @@ Cosine = Sim("cosine")            # core/sim.go:10
 MSD = Sim("msd")                  # core/sim.go:28
 Pearson = Sim("pearson")          # core/sim.go:47
 PearsonBaseline = Sim("pearson_baseline")  # extension (north star), not in the reference
+_SIMS_BY_NAME = {s_.name: s_ for s_ in (Cosine, MSD, Pearson, PearsonBaseline)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -396,23 +405,94 @@ def NewTrainSet(rowSet: DataSet) -> TrainSet:
     return TrainSet(rowSet)
 
 
-def LoadDataFromFile(fileName, sep="\t"):
-    """core/data.go:287-310: fields 0..2 through Atoi (non-integers become 0)."""
-    users, items, ratings = [], [], []
-
-    def atoi(s):
-        try:
-            return int(s.strip())
-        except ValueError:
-            return 0
-
-    with open(fileName) as f:
-        for line in f:
-            fields = line.rstrip("\n").split(sep)
-            users.append(atoi(fields[0]))
-            items.append(atoi(fields[1]))
-            ratings.append(float(atoi(fields[2])))
+def LoadDataFromFile(fileName, sep="\t", floatRatings=False, hasHeader=False):
+    """core/data.go:287-310.  With the defaults this IS the reference's loader: fields 0..2 through
+    strconv.Atoi, so half-star ratings ("3.5") and header lines silently become 0.  floatRatings=True
+     keeps fractional ratings — the device path fits any float64 rating —, hasHeader
+    drops the first line (MovieLens-20M's ratings.csv has both).  Parsed by librs_host.so."""
+    L = host_lib()
+    path, bsep = os.fsencode(fileName), sep.encode()
+    n = L.rs_host_load_ratings(path, bsep, int(floatRatings), int(hasHeader), None, None, None, 0)
+    if n < 0:
+        raise OSError(f"cannot read {fileName}")          # the reference log.Fatal()s here (core/data.go:294)
+    users = np.empty(n, dtype=np.int64)
+    items = np.empty(n, dtype=np.int64)
+    ratings = np.empty(n, dtype=np.float64)
+    L.rs_host_load_ratings(path, bsep, int(floatRatings), int(hasHeader), _ptr(users), _ptr(items), _ptr(ratings), n)
     return NewRawSet(users, items, ratings)
+
+
+# --------------------------------------------------------------------------------------------
+# core/dump.go — persistence (SURVEY.md §8 f-4)
+# --------------------------------------------------------------------------------------------
+def SaveNeighbors(fileName, idx, sim):
+    """Neighbour lists (int32 idx, float64 sim)[n_rows][k] -> one checksummed binary file (rs_host.h)."""
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    sim = np.ascontiguousarray(sim, dtype=np.float64)
+    if idx.ndim != 2 or idx.shape != sim.shape:
+        raise ValueError("idx and sim must be (n_rows, k) arrays of the same shape")
+    d = os.path.dirname(os.fspath(fileName))
+    if d:
+        os.makedirs(d, exist_ok=True)                     # core/dump.go:25 MkdirAll
+    rc = host_lib().rs_host_save_neighbors(os.fsencode(fileName), idx.shape[0], idx.shape[1], _ptr(idx), _ptr(sim))
+    if rc != 0:
+        raise OSError(f"cannot write {fileName}")
+
+
+def LoadNeighbors(fileName):
+    L = host_lib()
+    n, k = C.c_int64(0), C.c_int32(0)
+    rc = L.rs_host_load_neighbors(os.fsencode(fileName), C.byref(n), C.byref(k), None, None)
+    if rc == -1:
+        raise OSError(f"cannot read {fileName}")
+    if rc != 0:
+        raise ValueError(f"{fileName} is not a neighbour-list file")
+    idx = np.empty((n.value, k.value), dtype=np.int32)
+    sim = np.empty((n.value, k.value), dtype=np.float64)
+    rc = L.rs_host_load_neighbors(os.fsencode(fileName), C.byref(n), C.byref(k), _ptr(idx), _ptr(sim))
+    if rc != 0:
+        raise ValueError(f"{fileName}: truncated file or checksum mismatch")
+    return idx, sim
+
+
+def Save(fileName, estimator):
+    """core/dump.go:23-36 for the estimators of this path.  gob writes the exported fields — for a KNN
+    that includes the N x N Sims (5.7 GB at the MovieLens-20M shape).  Here the record is what is needed
+    to REBUILD the estimator bit for bit: constructor, Parameters and the training triples in dataset
+    order; Load refits on the device (76 ms at that shape — less than reading the matrix back)."""
+    import json
+
+    d = os.path.dirname(os.fspath(fileName))
+    if d:
+        os.makedirs(d, exist_ok=True)
+    params = {}
+    for key, val in (estimator.Params or {}).items():
+        params[key] = {"__sim__": val.name} if isinstance(val, Sim) else val
+    kind = "slope_one" if isinstance(estimator, SlopeOne) else "knn"
+    meta = {"kind": kind, "knn_type": getattr(estimator, "KNNType", ""), "params": params,
+            "fitted": estimator.Data is not None}
+    ts = estimator.Data
+    with open(fileName, "wb") as f:
+        np.savez(f, meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8),
+                 users=ts.Users if ts is not None else np.empty(0, np.int64),
+                 items=ts.Items if ts is not None else np.empty(0, np.int64),
+                 ratings=ts.Ratings if ts is not None else np.empty(0, np.float64))
+
+
+def Load(fileName):
+    """core/dump.go:11-20: returns the estimator Save wrote, fitted (on the device) if it was."""
+    import json
+
+    with np.load(fileName, allow_pickle=False) as z:
+        meta = json.loads(bytes(z["meta"]).decode())
+        users, items, ratings = z["users"], z["items"], z["ratings"]
+    params = Parameters()
+    for key, val in meta["params"].items():
+        params[key] = _SIMS_BY_NAME[val["__sim__"]] if isinstance(val, dict) and "__sim__" in val else val
+    est = NewSlopeOne(params) if meta["kind"] == "slope_one" else KNN(meta["knn_type"], params)
+    if meta["fitted"]:
+        est.Fit(NewTrainSet(NewRawSet(users, items, ratings)))
+    return est
 
 
 CYC_B = 32   # RS_CYC_B of csrc/common.cuh: rows are dealt to cyclic shards in blocks of 32

@@ -54,12 +54,19 @@ void free_fit_state(rs_knn *h) {
     h->l2r = nullptr;
     h->row_order = nullptr;
     h->n_heavy = 0;
-    h->avec = nullptr;
+    h->row_heavy = nullptr;
+    h->cp32 = nullptr;
     h->planes = nullptr;
     h->row_cnt = h->row_sum = nullptr;
     h->sims = nullptr;
     h->topk_idx = nullptr;
     h->topk_sim = nullptr;
+    h->thr_key = nullptr;
+    h->thr_id = nullptr;
+    h->cand_cnt = nullptr;
+    h->cand_id = nullptr;
+    h->cand_sim = nullptr;
+    h->row_flag = nullptr;
     h->d_flags = nullptr;
 }
 
@@ -113,6 +120,8 @@ int32_t init_handle(rs_knn *h) {
     RS_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     RS_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
     RS_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    RS_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    RS_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     h->stream = h->own_stream;
     RS_CUDA(cudaEventCreate(&h->ev_a));
     RS_CUDA(cudaEventCreate(&h->ev_b));
@@ -207,6 +216,7 @@ int32_t rs_knn_destroy(rs_knn *h) {
     h->chunks.clear();
     for (auto &pm : h->peer_cache) cudaIpcCloseMemHandle(pm.base);
     if (h->tile_buf) cudaFree(h->tile_buf);
+    if (h->band_buf) cudaFree(h->band_buf);
     if (h->ovf) rs_cached_free(h->device, h->ovf, h->ovf_bytes);
     for (size_t i = 0; i < h->scratch.size(); i++) rs_cached_free(h->device, h->scratch[i], h->scratch_bytes[i]);
     if (h->ev_a) cudaEventDestroy(h->ev_a);
@@ -217,6 +227,8 @@ int32_t rs_knn_destroy(rs_knn *h) {
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return RS_OK;
 }
@@ -340,6 +352,58 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
             rc = rs_symmetrize_launch(h);
             if (rc != RS_OK) { free_fit_state(h); return rc; }
         }
+    } else if (h->p.shard_count >= 1 && path == RS_PATH_TENSOR && rs_tensor_topk_fused(h)) {
+        // top-k only, FUSED: the tensor kernel's epilogue tests every similarity against the current k-th
+        // best of its two rows and appends the survivors to per-row candidate buffers; the buffers are merged
+        // into the running lists between the bands of the tile schedule (sim_tensor.cu).  No similarity row,
+        // slab or transpose is ever written: the only N-proportional buffers are the lists (N x k) and the
+        // candidate buffers (N x cap).  Every pair is computed once; a multi-GPU Fit deals the tiles of each
+        // band to the shards, every shard ends with PARTIAL lists for all rows (united after an all-gather).
+        const int32_t k = h->p.topk > 0 ? h->p.topk : h->p.k;
+        const int64_t n = n_left;
+        h->cand_cap = 1792;                          // band 0 brings at most 2 * (512 + 256) entries per row
+        if (const char *e = getenv("RS_KNN_TOPK_CAP")) h->cand_cap = atoi(e);   // tests: force the overflow path
+        if (k > 256 || h->cand_cap + k > 2048 || h->cand_cap < 1) {
+            rs_set_error("fused top-k: k <= 256 and candidate capacity + k <= 2048 (k=%d cap=%d)", k, h->cand_cap);
+            free_fit_state(h);
+            return RS_ERR_UNSUPPORTED;
+        }
+        RS_TRY(rs_alloc(h, &h->topk_idx, (size_t)n * k));
+        RS_TRY(rs_alloc(h, &h->topk_sim, (size_t)n * k));
+        RS_TRY(rs_alloc(h, &h->thr_key, (size_t)n));
+        RS_TRY(rs_alloc(h, &h->thr_id, (size_t)n));
+        RS_TRY(rs_alloc(h, &h->cand_cnt, (size_t)n));
+        RS_TRY(rs_alloc(h, &h->row_flag, (size_t)n));
+        RS_TRY(rs_alloc(h, &h->cand_id, (size_t)n * h->cand_cap));
+        RS_TRY(rs_alloc(h, &h->cand_sim, (size_t)n * h->cand_cap));
+        h->topk_rows = n;
+        RS_CUDA(cudaMemsetAsync(h->topk_idx, 0xFF, (size_t)n * k * 4, h->stream));   // -1 = empty
+        RS_CUDA(cudaMemsetAsync(h->topk_sim, 0xFF, (size_t)n * k * 8, h->stream));   // NaN
+        RS_CUDA(cudaMemsetAsync(h->thr_key, 0, (size_t)n * 8, h->stream));           // accept every valid similarity
+        RS_CUDA(cudaMemsetAsync(h->thr_id, 0xFF, (size_t)n * 4, h->stream));
+        RS_CUDA(cudaMemsetAsync(h->cand_cnt, 0, (size_t)n * 4, h->stream));
+        RS_CUDA(cudaMemsetAsync(h->row_flag, 0, (size_t)n * 4, h->stream));
+        int32_t *d_over = h->d_flags + 14;
+        RS_CUDA(cudaEventRecord(h->ev_b, h->stream));
+        const int n_waves = rs_tensor_band_count(h);
+        for (int w = 0; w < n_waves && rc == RS_OK; w++) {
+            int rerun = 0;
+            for (;;) {
+                RS_CUDA(cudaMemsetAsync(d_over, 0, 4, h->stream));
+                rc = rs_sim_tensor_band_launch(h, w);
+                if (rc == RS_OK) rc = rs_topk_compact_launch(h, k, d_over, rerun);
+                if (rc != RS_OK) break;
+                int32_t over = 0;
+                RS_CUDA(cudaMemcpyAsync(&over, d_over, 4, cudaMemcpyDeviceToHost, h->stream));
+                RS_CUDA(cudaStreamSynchronize(h->stream));
+                if (rerun) rc = rs_topk_mask_launch(h, k, 1);      // thresholds of the rows that sat the pass out
+                if (over == 0 || rc != RS_OK) break;
+                rc = rs_topk_mask_launch(h, k, 0);                 // run the band again for the flagged rows only
+                rerun = 1;
+            }
+        }
+        if (rc != RS_OK) { free_fit_state(h); return rc; }
+        RS_CUDA(cudaEventRecord(h->ev_c, h->stream));
     } else if (h->p.shard_count >= 1) {
         // top-k only, SYMMETRIC SLABS (see rs_knn_params::shard_count): slab s = rows [s*m, s*m+m);
         // of each slab only the part right of the diagonal is computed, the slab feeds the lists of

@@ -61,7 +61,11 @@ __global__ void als_side_kernel(const unsigned long long *__restrict__ ptr, cons
 struct Blocks {
     int device;
     std::vector<std::pair<void *, size_t>> v;
-    ~Blocks() { for (auto &b : v) rs_cached_free(device, b.first, b.second); }
+    cudaStream_t drain = nullptr;   // synchronised before the blocks are released
+    ~Blocks() {
+        if (drain) cudaStreamSynchronize(drain);
+        for (auto &b : v) rs_cached_free(device, b.first, b.second);
+    }
     template <typename U> int32_t get(U **out, size_t count) {
         void *p = nullptr;
         size_t got = 0;
@@ -95,8 +99,11 @@ extern "C" int32_t rs_baseline_als(int32_t device, const int32_t *users, const i
     RS_CUDA(cudaSetDevice(device));
     cudaStream_t st;
     RS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{st};
+    // destroyed AFTER `mem` (declared first): the stream is drained before its blocks go back to the shared
+    // cache, so an error return can never hand out memory that queued work still touches
+    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } guard{st};
     Blocks mem{device, {}};
+    mem.drain = st;
 
     int32_t *d_u, *d_i, *idx, *keys, *perm, *u_other, *i_other, *bad;
     double *d_r, *u_val, *i_val, *bu, *bi;

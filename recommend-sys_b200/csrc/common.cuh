@@ -75,6 +75,7 @@ struct rs_knn {
     cudaStream_t stream = nullptr;
     cudaStream_t aux_stream = nullptr;   // read-backs of Fit statistics that must not wait for the similarity kernel
     cudaEvent_t ev_in = nullptr;         // the host inputs of rs_knn_fit have been consumed
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // heavy-row kernel on aux_stream beside the column walk
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr;
     rs_knn_profile prof{};
     // pending event pairs whose elapsed time has not been folded into prof yet
@@ -108,6 +109,18 @@ struct rs_knn {
     size_t tile_buf_bytes = 0;
     int64_t tile_key[5] = {-1, -1, -1, -1, -1};
     int32_t tile_count = 0;
+    // fused top-k: band tile lists (all waves, concatenated) and the per-row selection state
+    void *band_buf = nullptr;
+    size_t band_buf_bytes = 0;
+    int64_t band_key[4] = {-1, -1, -1, -1};
+    std::vector<int64_t> band_off;
+    unsigned long long *thr_key = nullptr;   // [n_left] k-th best key of the row's running list (0 = not full)
+    int32_t *thr_id = nullptr;
+    int32_t *cand_cnt = nullptr;             // [n_left] candidates appended since the last merge
+    int32_t *cand_id = nullptr;              // [n_left][cand_cap]
+    double *cand_sim = nullptr;
+    int32_t cand_cap = 0;
+    int32_t *row_flag = nullptr;             // [n_left] the row's buffer overflowed in the current band
 
     // CSR of the left rows, entries ascending by right id (core/data.go:236-243)
     int64_t *l_ptr = nullptr;
@@ -145,8 +158,10 @@ struct rs_knn {
     int64_t *l2r = nullptr;
     int32_t *perm_lr = nullptr, *perm_rl = nullptr, *perm_tmp = nullptr;  // CSR position -> input row (arena, valid until the next Fit)
     int32_t *row_order = nullptr;  // left rows sorted by descending length
-    int32_t n_heavy = 0;           // the first n_heavy of them run in dense-row mode (sim_stream.cu)
-    double *avec = nullptr;        // [n_heavy][n_right] a-side vectors of the heavy rows
+    int32_t *row_heavy = nullptr;  // heavy rows split off that order (sim_stream.cu: sim_stream_heavy_kernel)
+    int32_t n_heavy = 0;
+    int32_t *cp32 = nullptr;       // [n_right][h32_n + 1] 32-column boundaries inside the heavy rows' column window
+    int32_t h32_lo = 0, h32_n = 0;
     // int8 planes X^2, M, X of the left matrix, [3][k_pad / 256][n_pad][256] (tensor path)
     int8_t *planes = nullptr;
     int64_t tc_npad = 0, tc_kpad = 0;
@@ -193,6 +208,9 @@ int32_t rs_mirror_launch(rs_knn *h);
 
 // ---- sim_tensor.cu ----
 int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int64_t cos_nrows);
+int32_t rs_tensor_band_count(const rs_knn *h);
+int32_t rs_sim_tensor_band_launch(rs_knn *h, int32_t wave);
+bool rs_tensor_topk_fused(const rs_knn *h);
 
 // ---- predict.cu ----
 int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_right, int64_t n, double *d_out,
@@ -200,6 +218,8 @@ int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
 int32_t rs_topk_launch(rs_knn *h, int32_t k, int32_t *d_idx, double *d_sim);
 int32_t rs_slope_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_right, int64_t n, double *d_out);
 int32_t rs_topk_slab_launch(rs_knn *h, int64_t g0, int32_t m, double *tbuf, int64_t ld_t, int32_t k);
+int32_t rs_topk_compact_launch(rs_knn *h, int32_t k, int32_t *d_overflow, int rerun);
+int32_t rs_topk_mask_launch(rs_knn *h, int32_t k, int restore);
 
 // order-preserving map double -> uint64 (larger similarity = larger key); -0.0 folded to +0.0
 __host__ __device__ inline uint64_t rs_sim_key(double s) {

@@ -1,4 +1,5 @@
 // devmem.cu — see common.cuh.  A small best-fit cache of device blocks per device.
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -44,10 +45,40 @@ int32_t rs_cached_malloc(int device, void **out, size_t bytes, size_t *got) {
     return RS_OK;
 }
 
+// Parked bytes are capped (RS_KNN_CACHE_BYTES, default 16 GiB per process): beyond the cap the
+// oldest parked blocks go back to the driver, so a co-resident allocator (torch, another library)
+// is not starved by arenas of estimators that no longer exist.
+static size_t cache_cap() {
+    static size_t cap = [] {
+        const char *e = getenv("RS_KNN_CACHE_BYTES");
+        return e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)16 << 30);
+    }();
+    return cap;
+}
+
 void rs_cached_free(int device, void *p, size_t bytes) {
     if (!p) return;
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_free.push_back({device, p, bytes});
+    std::vector<Block> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_free.push_back({device, p, bytes});
+        size_t total = 0;
+        for (const Block &b : g_free) total += b.bytes;
+        while (total > cache_cap() && !g_free.empty()) {     // oldest first
+            total -= g_free.front().bytes;
+            drop.push_back(g_free.front());
+            g_free.erase(g_free.begin());
+        }
+    }
+    if (!drop.empty()) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (const Block &b : drop) {
+            cudaSetDevice(b.device);
+            cudaFree(b.p);
+        }
+        cudaSetDevice(cur);
+    }
 }
 
 void rs_cache_trim(void) {

@@ -555,6 +555,80 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_merge_kernel(const double *
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused top-k (sim_tensor.cu appends the survivors of each band to per-row candidate buffers): merge a
+// row's buffer into its running list — top k of (list U candidates) under (similarity desc, id asc) —,
+// publish the new k-th best as the row's threshold and empty the buffer.  A buffer that overflowed
+// (more than `cap` survivors since the last merge: impossible unless the similarities are ordered
+// adversarially along the diagonal distance) is NOT merged: what it holds only raises the threshold —
+// every entry is a real similarity of the row, so the k-th best of (list U buffer) is a valid lower
+// bound of the final one —, the row is flagged, and the band is run again for the flagged rows.
+__global__ void __launch_bounds__(TOPK_THREADS) topk_compact_kernel(
+    const int32_t *__restrict__ cand_id, const double *__restrict__ cand_sim, int32_t *__restrict__ cand_cnt,
+    int32_t cap, int32_t k, int32_t *__restrict__ idx, double *__restrict__ sim, unsigned long long *__restrict__ thr_key,
+    int32_t *__restrict__ thr_id, int32_t *__restrict__ row_flag, int32_t *__restrict__ overflow, int rerun) {
+    __shared__ uint64_t keys[TOPK_CAP];
+    __shared__ uint32_t pos[TOPK_CAP];
+    const int64_t g = blockIdx.x;
+    if (rerun && !row_flag[g]) return;                         // second pass of a band: flagged rows only
+    const int cnt_all = cand_cnt[g];
+    const bool over = cnt_all > cap;
+    const int cnt = over ? cap : cnt_all;
+    if (cnt == 0 && !rerun) return;                            // nothing new: list and threshold stay
+    int have = 0;                                              // the list is stored best first: its entries are a prefix
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const int32_t id = idx[g * k + t];
+        keys[t] = id >= 0 ? rs_sim_key(sim[g * k + t]) : 0ull;
+        pos[t] = id >= 0 ? (uint32_t)id : 0xffffffffu;
+    }
+    __syncthreads();
+    // number of list entries (prefix length)
+    __shared__ int s_have;
+    if (threadIdx.x == 0) s_have = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < k; t += blockDim.x)
+        if (pos[t] != 0xffffffffu) atomicAdd(&s_have, 1);
+    __syncthreads();
+    have = s_have;
+    for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+        keys[have + t] = rs_sim_key(cand_sim[g * cap + t]);
+        pos[have + t] = (uint32_t)cand_id[g * cap + t];
+    }
+    const int total = have + cnt;
+    int n_pad = 32;
+    while (n_pad < total) n_pad <<= 1;
+    __syncthreads();
+    for (int t = total + threadIdx.x; t < n_pad; t += blockDim.x) { keys[t] = 0; pos[t] = 0xffffffffu; }
+    block_bitonic(keys, pos, n_pad);
+    if (!over) {
+        for (int t = threadIdx.x; t < k; t += blockDim.x) {
+            const int64_t o = g * k + t;
+            if (t < total) { idx[o] = (int32_t)pos[t]; sim[o] = rs_key_sim(keys[t]); }
+            else { idx[o] = -1; sim[o] = __longlong_as_double(0x7ff8000000000001ll); }
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (total >= k) { thr_key[g] = keys[k - 1]; thr_id[g] = (int32_t)pos[k - 1]; }
+        else { thr_key[g] = 0ull; thr_id[g] = -1; }            // list not full: accept every valid similarity
+        cand_cnt[g] = 0;
+        row_flag[g] = over ? 1 : 0;
+        if (over) atomicAdd(overflow, 1);
+    }
+}
+
+// Second pass of a band: rows that did NOT overflow already hold the band's entries — their threshold is
+// raised to "accept nothing" for the pass (restore = 0) and recomputed from their list afterwards (restore = 1).
+__global__ void topk_mask_kernel(const int32_t *__restrict__ row_flag, const int32_t *__restrict__ idx,
+                                 const double *__restrict__ sim, int32_t k, int64_t n, int restore,
+                                 unsigned long long *__restrict__ thr_key, int32_t *__restrict__ thr_id) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n || row_flag[g]) return;
+    if (!restore) { thr_key[g] = ~0ull; thr_id[g] = 0; return; }
+    const int32_t id = idx[g * k + (k - 1)];
+    if (id >= 0) { thr_key[g] = rs_sim_key(sim[g * k + (k - 1)]); thr_id[g] = id; }
+    else { thr_key[g] = 0ull; thr_id[g] = -1; }
+}
+
 // T[(c - c0)][r] = S[r][c] for r in [0, m), c in [c0, n): 32 x 32 tiles through shared memory
 __global__ void transpose_slab_kernel(const double *__restrict__ s, int64_t ld_s, int32_t m, int64_t c0, int32_t n,
                                       double *__restrict__ t, int64_t ld_t) {
@@ -789,6 +863,27 @@ int32_t rs_topk_slab_launch(rs_knn *h, int64_t g0, int32_t m, double *tbuf, int6
         h->prof.total_launches += 2;
     }
     h->prof.total_launches += 1;
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
+int32_t rs_topk_compact_launch(rs_knn *h, int32_t k, int32_t *d_overflow, int rerun) {
+    if (k < 1 || k > TOPK_CAP / 4 || h->cand_cap + k > TOPK_CAP) {
+        rs_set_error("fused top-k supports k <= %d and cap + k <= %d (got k=%d cap=%d)", TOPK_CAP / 4, TOPK_CAP, k, h->cand_cap);
+        return RS_ERR_UNSUPPORTED;
+    }
+    topk_compact_kernel<<<(unsigned)h->n_left, TOPK_THREADS, 0, h->stream>>>(
+        h->cand_id, h->cand_sim, h->cand_cnt, h->cand_cap, k, h->topk_idx, h->topk_sim, h->thr_key, h->thr_id,
+        h->row_flag, d_overflow, rerun);
+    h->prof.total_launches++;
+    RS_CUDA(cudaGetLastError());
+    return RS_OK;
+}
+
+int32_t rs_topk_mask_launch(rs_knn *h, int32_t k, int restore) {
+    topk_mask_kernel<<<(unsigned)((h->n_left + 255) / 256), 256, 0, h->stream>>>(h->row_flag, h->topk_idx, h->topk_sim, k,
+                                                                                h->n_left, restore, h->thr_key, h->thr_id);
+    h->prof.total_launches++;
     RS_CUDA(cudaGetLastError());
     return RS_OK;
 }

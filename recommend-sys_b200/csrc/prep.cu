@@ -249,15 +249,6 @@ __global__ void scatter_planes_kernel(const int64_t *__restrict__ l_ptr, const i
     }
 }
 
-// number of leading rows of the longest-first order whose length reaches `min_len`
-__global__ void count_heavy_kernel(const int32_t *__restrict__ row_order, int64_t n, const int64_t *__restrict__ l_ptr,
-                                   int64_t min_len, int32_t *out) {
-    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= n) return;
-    const int32_t i = row_order[x];
-    if (l_ptr[i + 1] - l_ptr[i] >= min_len) atomicAdd(out, 1);
-}
-
 struct CycOwned {
     int count, index;
     __host__ __device__ bool operator()(const int32_t &i) const { return rs_cyc_owns(i, count, index); }
@@ -506,32 +497,81 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     return RS_OK;
 }
 
-// Dense-row mode (sim_stream.cu): rows of at least RS_KNN_DENSE_MIN entries — the leading rows of the
-// longest-first order — are probed instead of walked.  OFF unless the variable is set: the probe costs one
-// L2 gather per entry of every column visited, so it only pays at hit rates no rating matrix of the
-// BASELINE shapes reaches.  Measured on the MovieLens-20M shape (profiles/r02_stream_notes.md): rows of
-// >= 1/32 of the right ids probed: Fit 44 -> 82 ms; >= 8000 entries: 64 ms; only the two rows rated by half
-// of all users: 54 ms (the probe kernel's own serial tail).  Kept because it is bit-exact, tested, and the
-// right tool for a matrix with genuinely dense rows.
-static int32_t pick_heavy_rows(rs_knn *h, const int32_t *order, int64_t n_rows) {
+// Heavy rows (sim_stream.cu: sim_stream_heavy_kernel): rows of >= 4096 entries whose triangle lies
+// inside a window of 4096 columns are split off the longest-first order; they are walked in 32-column
+// sub-chunks with register accumulators, which needs the 32-column boundaries of every right row
+// inside that window (cp32).  `order`: the rows to process, longest first.  Writes h->row_order (the
+// other rows, same order), h->row_heavy, the counts, and cp32.
+struct HeavyPred {
+    const int64_t *l_ptr;
+    int64_t min_len;
+    int32_t id_lo, id_hi;
+    bool negate;
+    __host__ __device__ bool operator()(const int32_t &i) const {
+        const bool heavy = (l_ptr[i + 1] - l_ptr[i] >= min_len) && i >= id_lo && i < id_hi;
+        return heavy != negate;
+    }
+};
+
+__global__ void build_cp32_kernel(const int64_t *__restrict__ r_ptr, const int32_t *__restrict__ r_col,
+                                  int32_t n_right, int32_t sub_lo, int32_t n_sub, int32_t *__restrict__ cp) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = n_sub + 1;
+    if (t >= (int64_t)n_right * per) return;
+    const int32_t c = (int32_t)(t / per), q = (int32_t)(t % per);
+    const int64_t b = r_ptr[c], e = r_ptr[c + 1];
+    const int64_t target = ((int64_t)sub_lo + q) * 32;
+    int64_t lo = b, hi = e;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (r_col[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    cp[t] = (int32_t)(lo - b);
+}
+
+static int32_t split_heavy_rows(rs_knn *h, const int32_t *order, int64_t n_rows, bool allow) {
     cudaStream_t st = h->stream;
-    int64_t min_len = (int64_t)1 << 40;
-    if (const char *e = getenv("RS_KNN_DENSE_MIN")) min_len = atoll(e);      // experiments / tests; 0 = every row
+    constexpr int32_t WINDOW = 4096;                       // columns covered by cp32
+    int64_t min_len = 4096;
+    if (const char *e = getenv("RS_KNN_HEAVY_MIN")) min_len = atoll(e);      // tests: 0 = every row in the window
     h->n_heavy = 0;
-    h->avec = nullptr;
+    h->row_heavy = nullptr;
+    h->cp32 = nullptr;
+    h->n_work_rows = n_rows;
     if (n_rows <= 0) return RS_OK;
-    int32_t *d_cnt = h->d_flags + 14;
-    RS_CUDA(cudaMemsetAsync(d_cnt, 0, 4, st));
-    count_heavy_kernel<<<blocks_for(n_rows), T, 0, st>>>(order, n_rows, h->l_ptr, min_len, d_cnt);
+    RS_TRY(rs_alloc(h, &h->row_order, (size_t)n_rows));
+    if (!allow || min_len < 0) {
+        RS_CUDA(cudaMemcpyAsync(h->row_order, order, (size_t)n_rows * 4, cudaMemcpyDeviceToDevice, st));
+        return RS_OK;
+    }
+    // the triangle of a heavy row must lie inside the window: the first (lower triangle) or the last
+    // (upper triangle) WINDOW columns
+    int32_t id_lo = 0, id_hi = h->n_left;
+    if (h->stream_lower) id_hi = h->n_left < WINDOW ? h->n_left : WINDOW;
+    else id_lo = h->n_left > WINDOW ? (h->n_left - WINDOW) / 32 * 32 : 0;
+    RS_TRY(rs_alloc(h, &h->row_heavy, (size_t)n_rows));
+    int32_t *d_num;
+    RS_TRY(rs_alloc(h, &d_num, 4));
+    HeavyPred yes{h->l_ptr, min_len, id_lo, id_hi, false}, no{h->l_ptr, min_len, id_lo, id_hi, true};
+    size_t need = 0;
+    RS_CUDA(cub::DeviceSelect::If(nullptr, need, order, h->row_heavy, d_num, (int)n_rows, yes, st));
+    void *tmp;
+    RS_TRY(rs_dev_alloc(h, &tmp, need + 256));
+    RS_CUDA(cub::DeviceSelect::If(tmp, need, order, h->row_heavy, d_num, (int)n_rows, yes, st));
+    RS_CUDA(cub::DeviceSelect::If(tmp, need, order, h->row_order, d_num + 1, (int)n_rows, no, st));
     int32_t cnt = 0;
-    RS_CUDA(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+    RS_CUDA(cudaMemcpyAsync(&cnt, d_num, 4, cudaMemcpyDeviceToHost, st));
     RS_CUDA(cudaStreamSynchronize(st));
-    // bounded scratch: at most 2 GiB of a-side vectors
-    const int64_t cap = (int64_t)(2ll << 30) / ((int64_t)h->n_right * 8);
-    if (cnt > cap) cnt = (int32_t)cap;
     h->n_heavy = cnt;
-    h->prof.total_launches++;
-    if (cnt > 0) RS_TRY(rs_alloc(h, &h->avec, (size_t)cnt * (size_t)h->n_right));
+    h->n_work_rows = n_rows - cnt;
+    if (cnt > 0) {
+        h->h32_lo = id_lo / 32;
+        h->h32_n = (id_hi - id_lo + 31) / 32;
+        RS_TRY(rs_alloc(h, &h->cp32, (size_t)h->n_right * ((size_t)h->h32_n + 1)));
+        build_cp32_kernel<<<blocks_for((int64_t)h->n_right * (h->h32_n + 1)), T, 0, st>>>(
+            h->r_ptr, h->r_col, h->n_right, h->h32_lo, h->h32_n, h->cp32);
+        h->prof.total_launches++;
+    }
     return RS_OK;
 }
 
@@ -549,51 +589,48 @@ int32_t rs_prep_rt(rs_knn *h) {
     invert_perm_kernel<<<blocks_for(h->nnz), T, 0, st>>>(h->perm_rl, h->nnz, h->perm_tmp);
     compose_l2r_kernel<<<blocks_for(h->nnz), T, 0, st>>>(h->perm_lr, h->perm_tmp, h->nnz, h->l2r);
     h->prof.total_launches += 4;
-    // rows of every possible shard ordered longest first: a stable descending sort of the row
-    // lengths inside the shard keeps the order deterministic
+    // rows of the shard ordered longest first (a stable descending sort of the row lengths keeps the
+    // order deterministic), then split into heavy rows and the rest
     {
         const int64_t rb = h->row_begin, rows = h->row_end - h->row_begin;
-        int32_t *len, *len_sorted, *ids;
+        int32_t *len, *len_sorted, *ids, *sorted;
         RS_TRY(rs_alloc(h, &len, (size_t)h->n_left));
         RS_TRY(rs_alloc(h, &len_sorted, (size_t)h->n_left));
         RS_TRY(rs_alloc(h, &ids, (size_t)h->n_left));
-        RS_TRY(rs_alloc(h, &h->row_order, (size_t)h->n_left));
+        RS_TRY(rs_alloc(h, &sorted, (size_t)h->n_left));
         row_len_kernel<<<blocks_for(h->n_left), T, 0, st>>>(h->l_ptr, h->n_left, len, ids);
         h->prof.total_launches++;
-        if (h->cyc_R > 1) {
-            // cyclic shards: all rows ordered longest first, then the owned ones picked out in that order
-            int32_t *all_sorted, *d_num;
-            RS_TRY(rs_alloc(h, &all_sorted, (size_t)h->n_left));
-            RS_TRY(rs_alloc(h, &d_num, 4));
-            size_t need = 0, need2 = 0;
-            RS_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, len, len_sorted, ids, all_sorted,
-                                                              (int)h->n_left, 0, 32, st));
-            CycOwned pred{h->cyc_R, h->cyc_r};
-            RS_CUDA(cub::DeviceSelect::If(nullptr, need2, all_sorted, h->row_order, d_num, (int)h->n_left, pred, st));
-            void *tmp;
-            RS_TRY(rs_dev_alloc(h, &tmp, need > need2 ? need : need2));
-            RS_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, need, len, len_sorted, ids, all_sorted,
-                                                              (int)h->n_left, 0, 32, st));
-            RS_CUDA(cub::DeviceSelect::If(tmp, need2, all_sorted, h->row_order, d_num, (int)h->n_left, pred, st));
-            h->n_work_rows = h->rows_local;
-            RS_TRY(pick_heavy_rows(h, h->row_order, h->n_work_rows));
-            RS_CUDA(cudaGetLastError());
-            return RS_OK;
-        }
         if (h->p.store == RS_STORE_TOPK) {
             // rows are produced slab by slab into a slab-sized buffer: keep the natural order
-            RS_CUDA(cudaMemcpyAsync(h->row_order, ids, (size_t)h->n_left * 4, cudaMemcpyDeviceToDevice, st));
+            h->row_order = ids;
+            h->n_work_rows = -1;                 // the launcher takes [row_begin, row_end) of the natural order
+            h->n_heavy = 0;
             RS_CUDA(cudaGetLastError());
             return RS_OK;
         }
         size_t need = 0;
         RS_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, len + rb, len_sorted + rb, ids + rb,
-                                                          h->row_order + rb, (int)rows, 0, 32, st));
+                                                          sorted, (int)rows, 0, 32, st));
         void *tmp;
         RS_TRY(rs_dev_alloc(h, &tmp, need));
         RS_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, need, len + rb, len_sorted + rb, ids + rb,
-                                                          h->row_order + rb, (int)rows, 0, 32, st));
-        RS_TRY(pick_heavy_rows(h, h->row_order + rb, rows));
+                                                          sorted, (int)rows, 0, 32, st));
+        const bool full = h->row_begin == 0 && h->row_end == h->n_left;
+        if (h->cyc_R > 1) {
+            // cyclic shards: the owned rows picked out of the longest-first order
+            int32_t *owned, *d_num;
+            RS_TRY(rs_alloc(h, &owned, (size_t)h->n_left));
+            RS_TRY(rs_alloc(h, &d_num, 4));
+            size_t need2 = 0;
+            CycOwned pred{h->cyc_R, h->cyc_r};
+            RS_CUDA(cub::DeviceSelect::If(nullptr, need2, sorted, owned, d_num, (int)h->n_left, pred, st));
+            void *tmp2;
+            RS_TRY(rs_dev_alloc(h, &tmp2, need2 + 256));
+            RS_CUDA(cub::DeviceSelect::If(tmp2, need2, sorted, owned, d_num, (int)h->n_left, pred, st));
+            RS_TRY(split_heavy_rows(h, owned, h->rows_local, true));
+        } else {
+            RS_TRY(split_heavy_rows(h, sorted, rows, full));
+        }
     }
     RS_CUDA(cudaGetLastError());
     return RS_OK;

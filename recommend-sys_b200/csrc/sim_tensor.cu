@@ -37,9 +37,11 @@
 //               (throttle in the TMA producer) so that shared operand rows hit in L2.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -252,6 +254,16 @@ struct TcArgs {
     // blocks, a CTA may run at most `sync_slack` chunks ahead of the grid's average progress.
     unsigned long long *progress;
     int sync_chunk, sync_slack, sync_timeout;
+    // Fused top-k (pair kernel, RS_STORE_TOPK): no similarity is stored.  Every pair {i, j}, j > i, is tested
+    // against the current k-th best of row i and of row j (thr_*; key 0 = list not full, accept) and the
+    // survivors are appended to the rows' candidate buffers, merged between waves (predict.cu).
+    int topk_mode;
+    const unsigned long long *thr_key;
+    const int32_t *thr_id;
+    int32_t *cand_cnt;
+    int32_t *cand_id;
+    double *cand_sim;
+    int32_t cand_cap;
 };
 
 __device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long *p) {
@@ -570,7 +582,8 @@ constexpr int P_A_PLANE = BM * P_BK;              // 8 KB  (128 rows of this CTA
 constexpr int P_B_PLANE = (P_BN / 2) * P_BK;      // 4 KB  (this CTA's 64 of the 128 B rows)
 constexpr int P_A_STAGE = 3 * P_A_PLANE, P_B_STAGE = 3 * P_B_PLANE;
 constexpr int P_STAGE = P_A_STAGE + P_B_STAGE;    // 36 KB
-constexpr int P_SMEM = P_STAGES * P_STAGE + 1024 + 256;
+constexpr int P_THR_BYTES = 2 * P_BN * 12;          // double-buffered (key, id) thresholds of a tile's columns
+constexpr int P_SMEM = P_STAGES * P_STAGE + 1024 + 256 + P_THR_BYTES;
 static_assert(P_SMEM <= 227 * 1024, "pair pipeline does not fit in shared memory");
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;       // shared::cluster address of the same offset in the even CTA
 
@@ -746,10 +759,27 @@ sim_tensor_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         uint32_t acc_phase = 0;
         const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
         const uint32_t tempty_leader = tempty_bar & PEER_MASK;
+        unsigned long long *s_thrk = reinterpret_cast<unsigned long long *>(smem_gen + P_STAGES * P_STAGE + 256);
+        uint32_t *s_thri = reinterpret_cast<uint32_t *>(s_thrk + 2 * P_BN);
+        int tbuf = 0;
         for (int t = pair_id; t < a.num_tiles; t += n_pairs) {
             const int2 tile = a.tiles[t];
             const int64_t i = ((int64_t)tile.x * 2 + rank) * BM + r_in_tile;
             const int64_t j0 = (int64_t)tile.y * P_BN;
+            unsigned long long trk_i = ~0ull;
+            uint32_t tri_i = 0u;
+            if (a.topk_mode) {
+                // thresholds of the tile's 128 columns -> shared memory (while the MMAs of the tile run), of
+                // this thread's row -> registers.  Stale values only admit extra candidates.
+                const int e = (int)threadIdx.x - 64;
+                if (e < P_BN) {
+                    const int64_t jc = j0 + e;
+                    s_thrk[tbuf * P_BN + e] = jc < a.n_left ? a.thr_key[jc] : ~0ull;
+                    s_thri[tbuf * P_BN + e] = jc < a.n_left ? (uint32_t)a.thr_id[jc] : 0u;
+                }
+                if (i < a.n_left) { trk_i = a.thr_key[i]; tri_i = (uint32_t)a.thr_id[i]; }
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+            }
             mbar_wait(tfull_bar, acc_phase, 3);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -780,6 +810,34 @@ sim_tensor_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     }
                     if (MODE != TC_SLOPE && j == i) s[c] = nan_v;   // diagonal stays unset (core/knn.go:202)
                 }
+                if (a.topk_mode) {
+                    // selection fused into the epilogue: one compare against each of the two rows' thresholds,
+                    // the rare survivor is appended to that row's candidate buffer
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const int64_t j = j0 + c0 + c;
+                        const double sv = s[c];
+                        if (i < a.n_left && j < a.n_left && j > i && sv == sv) {
+                            const unsigned long long key = rs_sim_key(sv);
+                            if (key > trk_i || (key == trk_i && (uint32_t)j < tri_i)) {
+                                const int slot = atomicAdd(a.cand_cnt + i, 1);
+                                if (slot < a.cand_cap) {
+                                    a.cand_id[i * a.cand_cap + slot] = (int32_t)j;
+                                    a.cand_sim[i * a.cand_cap + slot] = sv;
+                                }
+                            }
+                            const unsigned long long tk = s_thrk[tbuf * P_BN + c0 + c];
+                            if (key > tk || (key == tk && (uint32_t)i < s_thri[tbuf * P_BN + c0 + c])) {
+                                const int slot = atomicAdd(a.cand_cnt + j, 1);
+                                if (slot < a.cand_cap) {
+                                    a.cand_id[j * a.cand_cap + slot] = (int32_t)i;
+                                    a.cand_sim[j * a.cand_cap + slot] = sv;
+                                }
+                            }
+                        }
+                    }
+                    continue;
+                }
                 if (row_ok) {
                     double *o = a.sims + (i - a.row_begin) * a.ld_s + j0 + c0;
                     if (j0 + c0 + 8 <= a.n_left) {
@@ -803,6 +861,7 @@ sim_tensor_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             tc_fence_before();
             mbar_arrive_cluster(tempty_leader);    // 2 x 256 arrivals release the accumulators of the pair
             acc_phase ^= 1u;
+            tbuf ^= 1;
         }
     }
 
@@ -947,6 +1006,115 @@ int32_t launch_shape(rs_knn *h, const TcArgs &a, bool cosums) {
 }
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Fused top-k (RS_STORE_TOPK on the tensor path, large problems): the block-triangular tile set of the
+// pair kernel is cut into BANDS by the distance of a tile from the diagonal, band w covering column
+// distances [D_w, D_w+1) with D = -128, 512, 1024, 2048, ... (doubling).  A row therefore meets at most
+// ~1.5 k new columns in band 0 — all of them candidates, there is no threshold yet — and in every later
+// band about as many columns as it has seen before, of which only ~k beat its current k-th best: the
+// candidate buffers stay small (cand_cap per row) and the N x N matrix, or any slab of it, never exists.
+// The tiles of a band are dealt round-robin to the shards of a multi-GPU Fit (equal cost per tile).
+int32_t rs_tensor_band_count(const rs_knn *h) {
+    int w = 1;
+    for (int64_t d = 512; d < (int64_t)h->n_left + 128; d *= 2) w++;
+    return w;
+}
+
+int32_t rs_sim_tensor_band_launch(rs_knn *h, int32_t wave) {
+    if (!h->planes) {
+        rs_set_error("tensor path: int8 planes were not built");
+        return RS_ERR_INVALID;
+    }
+    const int mode = h->p.sim == RS_SIM_COSINE ? TC_COSINE : TC_MSD;
+    const int n_waves = rs_tensor_band_count(h);
+    const int shard_count = h->p.shard_count > 1 ? h->p.shard_count : 1, shard_index = h->p.shard_count > 1 ? h->p.shard_index : 0;
+    const int64_t key[4] = {h->n_left, shard_count, shard_index, n_waves};
+    if (memcmp(key, h->band_key, sizeof(key)) != 0) {
+        // cluster tiles: cbi = 256 rows, cbj = 128 columns; needed iff the tile holds a pair with j > i
+        const int ncbi = (int)((h->n_left + 2 * BM - 1) / (2 * BM)), ncbj = (int)((h->n_left + pair::P_BN - 1) / pair::P_BN);
+        // rasterised in supertiles of 4 x 8 cluster tiles (1024 x 1024 similarities) so that the pairs running
+        // at the same time share operand rows in L2, as in the matrix schedule below
+        std::vector<std::vector<int2>> bands(n_waves);
+        std::vector<int64_t> dealt(n_waves, 0);
+        std::vector<char> seen(n_waves);
+        constexpr int SI = 4, SJ = 8;
+        for (int sbi = 0; sbi < ncbi; sbi += SI)
+            for (int sbj = 0; sbj < ncbj; sbj += SJ) {
+                // whole supertiles are dealt to the shards (a band's share of one supertile stays on one GPU)
+                std::fill(seen.begin(), seen.end(), 0);
+                for (int cbi = sbi; cbi < sbi + SI && cbi < ncbi; cbi++)
+                    for (int cbj = sbj; cbj < sbj + SJ && cbj < ncbj; cbj++) {
+                        const int64_t d = (int64_t)cbj * pair::P_BN - (int64_t)cbi * 2 * BM;   // column distance of the tile
+                        if (d + pair::P_BN <= 0) continue;                                     // every column <= every row
+                        int w = 0;
+                        for (int64_t lim = 512; d >= lim; lim *= 2) w++;
+                        if (!seen[w]) { seen[w] = 1; dealt[w]++; }
+                        if ((dealt[w] - 1) % shard_count == shard_index) bands[w].push_back(make_int2(cbi, cbj));
+                    }
+            }
+        std::vector<int2> flat;
+        h->band_off.assign(n_waves + 1, 0);
+        for (int w = 0; w < n_waves; w++) {
+            h->band_off[w] = (int64_t)flat.size();
+            flat.insert(flat.end(), bands[w].begin(), bands[w].end());
+        }
+        h->band_off[n_waves] = (int64_t)flat.size();
+        const size_t bytes = flat.size() * sizeof(int2);
+        if (bytes > h->band_buf_bytes) {
+            RS_CUDA(cudaStreamSynchronize(h->stream));
+            if (h->band_buf) cudaFree(h->band_buf);
+            h->band_buf = nullptr;
+            h->band_buf_bytes = 0;
+            RS_CUDA(cudaMalloc(&h->band_buf, bytes + 256));
+            h->band_buf_bytes = bytes + 256;
+        }
+        if (bytes) {
+            RS_CUDA(cudaMemcpyAsync(h->band_buf, flat.data(), bytes, cudaMemcpyHostToDevice, h->stream));
+            RS_CUDA(cudaStreamSynchronize(h->stream));  // `flat` is a pageable temporary
+        }
+        memcpy(h->band_key, key, sizeof(key));
+    }
+    const int64_t t0 = h->band_off[wave], t1 = h->band_off[wave + 1];
+    if (t1 <= t0) return RS_OK;
+    TcArgs a{};
+    a.tiles = reinterpret_cast<const int2 *>(h->band_buf) + t0;
+    a.num_tiles = (int32_t)(t1 - t0);
+    a.k_blocks = (int32_t)(h->tc_kpad / pair::P_BK);
+    a.n_left = h->n_left;
+    a.row_begin = 0;
+    a.row_end = h->n_left;
+    a.mirror = 0;
+    a.sims = nullptr;
+    a.ld_s = 0;
+    a.topk_mode = 1;
+    a.thr_key = h->thr_key;
+    a.thr_id = h->thr_id;
+    a.cand_cnt = h->cand_cnt;
+    a.cand_id = h->cand_id;
+    a.cand_sim = h->cand_sim;
+    a.cand_cap = h->cand_cap;
+    if (const char *e = getenv("RS_KNN_TC_DEBUG")) a.debug = atoi(e);
+    a.progress = reinterpret_cast<unsigned long long *>(h->d_flags + 4);
+    a.sync_chunk = (a.k_blocks >= 256 && a.num_tiles > 148) ? 32 : 0;
+    a.sync_slack = 1;
+    a.sync_timeout = 40000;
+    if (const char *e = getenv("RS_KNN_TC_SYNC")) sscanf(e, "%d,%d,%d", &a.sync_chunk, &a.sync_slack, &a.sync_timeout);
+    if (a.sync_chunk > 0) RS_CUDA(cudaMemsetAsync(a.progress, 0, 8, h->stream));
+    RS_TRY(mode == TC_COSINE ? launch_pair<TC_COSINE>(h, a) : launch_pair<TC_MSD>(h, a));
+    h->prof.sim_launches++;
+    h->prof.total_launches++;
+    return RS_OK;
+}
+
+// Is the fused top-k path available for this Fit?  (Cosine / MSD on integer ratings, large enough for the
+// pair kernel; everything else reduces bounded slabs of similarity rows, see api.cu.)
+bool rs_tensor_topk_fused(const rs_knn *h) {
+    if (h->p.sim != RS_SIM_COSINE && h->p.sim != RS_SIM_MSD) return false;
+    if (const char *e = getenv("RS_KNN_TOPK_FUSED")) return atoi(e) != 0;
+    const int64_t plain_tiles = (((int64_t)h->n_left + BM - 1) / BM) * (((int64_t)h->n_left + pair::P_BN - 1) / pair::P_BN) / 2;
+    return plain_tiles >= 4 * 148;
+}
 
 int32_t rs_sim_tensor_launch(rs_knn *h, int32_t *d_cosums, int64_t cos_row0, int64_t cos_nrows) {
     if (!h->planes) {

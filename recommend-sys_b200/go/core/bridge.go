@@ -95,6 +95,10 @@ func newDeviceKNN(p Parameters, knnType string) *deviceKNN {
 	cp.row_begin = C.int64_t(p.GetInt("rowBegin", 0))
 	cp.row_end = C.int64_t(p.GetInt("rowEnd", 0))
 	cp.shrinkage = C.double(p.GetFloat64("shrinkage", 0))
+	// sharding over the GPUs of one box (rs_knn.h: symmetric slabs for RS_STORE_TOPK, cyclic row
+	// shards for RS_STORE_MATRIX); 0 = this handle computes everything
+	cp.shard_count = C.int32_t(p.GetInt("shardCount", 0))
+	cp.shard_index = C.int32_t(p.GetInt("shardIndex", 0))
 	d := &deviceKNN{}
 	check(C.rs_knn_create(&cp, &d.h))
 	runtime.SetFinalizer(d, func(d *deviceKNN) { d.close() })
@@ -143,6 +147,41 @@ func baselineALS(device int, users, items []int32, rating []float64, nUsers, nIt
 		C.int32_t(nEpochs), f64(ub), f64(ib)))
 	return ub, ib
 }
+
+// setK forwards Parameters["k"] / ["mink"], which the reference reads at Predict time
+// (core/knn.go:80-81), to a fitted handle.
+func (d *deviceKNN) setK(k, minK int) { check(C.rs_knn_set_k(d.h, C.int32_t(k), C.int32_t(minK))) }
+
+// Cyclic row shards (one estimator per GPU, Parameters["shardCount"] >= 2 with the matrix kept):
+// peerExport returns the 64-byte CUDA IPC handle + offset of this shard's matrix, peerImport
+// attaches all shards' matrices (gathered by whatever transport joins the processes), mirror pulls
+// the triangle this shard did not compute over NVLink.  With all shards in ONE process
+// (goroutine per GPU, like the reference's nJobs) peerImportLocal takes the handles directly.
+func (d *deviceKNN) peerExport() ([64]byte, int64) {
+	var hb [64]byte
+	var off C.int64_t
+	check(C.rs_knn_peer_export(d.h, (*C.uchar)(unsafe.Pointer(&hb[0])), &off))
+	return hb, int64(off)
+}
+
+func (d *deviceKNN) peerImport(handles [][64]byte, offsets []int64) {
+	flat := make([]byte, 64*len(handles))
+	for i := range handles {
+		copy(flat[64*i:], handles[i][:])
+	}
+	check(C.rs_knn_peer_import(d.h, C.int32_t(len(handles)), (*C.uchar)(unsafe.Pointer(&flat[0])),
+		(*C.int64_t)(unsafe.Pointer(&offsets[0]))))
+}
+
+func (d *deviceKNN) peerImportLocal(peers []*deviceKNN) {
+	hs := make([]*C.rs_knn, len(peers))
+	for i, p := range peers {
+		hs[i] = p.h
+	}
+	check(C.rs_knn_peer_import_local(d.h, C.int32_t(len(hs)), &hs[0]))
+}
+
+func (d *deviceKNN) mirror() { check(C.rs_knn_mirror(d.h)) }
 
 func (d *deviceKNN) predictBatch(left, right []int32) []float64 {
 	out := make([]float64, len(left))

@@ -11,22 +11,27 @@ const (
 	baseline = "baseline"
 )
 
-// KNN keeps the reference's exported fields (core/knn.go:17-27).  Sims is no longer filled by
-// Fit: the N x N matrix lives in HBM and SimsRows / MaterializeSims copy it out on demand
-// (e.g. before Save, core/dump.go:11).  LeftRatings / RightRatings are not duplicated on the
-// host; the TrainSet in Base.Data still has them.
+// KNN keeps ALL of the reference's exported fields (core/knn.go:17-27), so gob Save/Load
+// (core/dump.go:11-36) writes the same record.  Sims is no longer filled by Fit: the N x N matrix
+// lives in HBM and MaterializeSims copies it out on demand (e.g. before Save).  LeftRatings /
+// RightRatings are the TrainSet's adjacency lists exactly as the reference assigns them
+// (core/knn.go:154-162; the left ones id-sorted in place by `sorts`, core/data.go:236-243) — slice
+// headers onto the TrainSet's own storage, no copy.
 type KNN struct {
 	Base
-	KNNType    string
-	GlobalMean float64
-	Sims       [][]float64
-	Means      []float64
-	StdDevs    []float64
-	Bias       []float64
+	KNNType      string
+	GlobalMean   float64
+	Sims         [][]float64
+	LeftRatings  [][]IDRating
+	RightRatings [][]IDRating
+	Means        []float64
+	StdDevs      []float64
+	Bias         []float64
 
 	dev       *deviceKNN // unexported: invisible to gob, so Copy() never aliases a device handle
 	userBased bool
 	nLeft     int
+	kk        [2]int // k, mink the handle currently holds
 }
 
 func NewKNN(params Parameters) *KNN          { return &KNN{Base: Base{Params: params}, KNNType: basic} }
@@ -96,10 +101,17 @@ func (K *KNN) Fit(trainSet TrainSet) {
 			rightBias = nil
 		}
 	}
+	if K.userBased { // core/knn.go:154-162
+		K.LeftRatings, K.RightRatings = trainSet.UserRatings(), trainSet.ItemRatings()
+	} else {
+		K.LeftRatings, K.RightRatings = trainSet.ItemRatings(), trainSet.UserRatings()
+	}
+	sorts(K.LeftRatings) // core/knn.go:190 sorts the TrainSet's cached rows in place; callers may rely on it
 	K.Close()
 	K.dev = newDeviceKNN(K.Params, K.KNNType)
 	K.dev.fit(left, right, trainSet.Ratings, nLeft, nRight, trainSet.GlobalMean, leftBias, rightBias, globalBias)
 	K.nLeft = nLeft
+	K.kk = [2]int{K.Params.GetInt("k", 40), K.Params.GetInt("mink", 1)}
 	if K.KNNType == centered || K.KNNType == zScore {
 		K.Means = K.dev.means(nLeft)
 	}
@@ -121,6 +133,11 @@ func (K *KNN) PredictBatch(userIDs, itemIDs []int) []float64 {
 		} else {
 			left[i], right[i] = it, u
 		}
+	}
+	// core/knn.go:80-81 reads k / mink in Predict: SetParams after Fit takes effect here
+	if kk := [2]int{K.Params.GetInt("k", 40), K.Params.GetInt("mink", 1)}; kk != K.kk {
+		K.dev.setK(kk[0], kk[1])
+		K.kk = kk
 	}
 	return K.dev.predictBatch(left, right)
 }

@@ -11,6 +11,8 @@ package core
 */
 import "C"
 
+import "runtime"
+
 type SlopeOne struct {
 	Base
 	globalMean float64
@@ -68,5 +70,7 @@ func newDeviceSlopeOne(p Parameters) *deviceKNN {
 	cp.device = C.int32_t(p.GetInt("device", -1))
 	d := &deviceKNN{}
 	check(C.rs_knn_create(&cp, &d.h))
+	// CrossValidate's copies (core/eval.go:29-35) are never Closed: release the device memory with the object
+	runtime.SetFinalizer(d, func(d *deviceKNN) { d.close() })
 	return d
 }

@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <string>
 #include <cstring>
 #include <unordered_map>
 #include <vector>
@@ -161,6 +163,117 @@ void rs_host_convert_dense(const int32_t *table, int64_t n_table, const int64_t 
         const int64_t r = raw[x];
         inner_out[x] = (r >= 0 && r < n_table) ? table[r] : -1;     // -1 = newID (core/data.go:129)
     }
+}
+
+// ---- on-disk neighbour lists and a rating loader that keeps half-stars ----
+// File format (little endian):  magic "RSKNNL01" | int64 n_rows | int32 k | int32 reserved |
+// uint64 checksum (FNV-1a 64 of the payload) | int32 idx[n_rows*k] | float64 sim[n_rows*k].
+// idx -1 / sim NaN = unused slot (rs_knn_topk).  Return codes: 0 ok, -1 io error, -2 bad file.
+static uint64_t fnv1a(const void *p, size_t n, uint64_t h) {
+    const unsigned char *b = (const unsigned char *)p;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+int32_t rs_host_save_neighbors(const char *path, int64_t n_rows, int32_t k, const int32_t *idx, const double *sim) {
+    FILE *f = fopen(path, "wb");
+    if (!f) return -1;
+    const size_t cells = (size_t)n_rows * (size_t)k;
+    uint64_t sum = fnv1a(idx, cells * 4, 1469598103934665603ull);
+    sum = fnv1a(sim, cells * 8, sum);
+    const int32_t reserved = 0;
+    bool ok = fwrite("RSKNNL01", 1, 8, f) == 8 && fwrite(&n_rows, 8, 1, f) == 1 && fwrite(&k, 4, 1, f) == 1 &&
+              fwrite(&reserved, 4, 1, f) == 1 && fwrite(&sum, 8, 1, f) == 1 &&
+              fwrite(idx, 4, cells, f) == cells && fwrite(sim, 8, cells, f) == cells;
+    ok = (fclose(f) == 0) && ok;
+    return ok ? 0 : -1;
+}
+
+// Two-step load: header first (idx == NULL: only n_rows / k are returned), then the payload.
+int32_t rs_host_load_neighbors(const char *path, int64_t *n_rows, int32_t *k, int32_t *idx, double *sim) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return -1;
+    char magic[8];
+    int32_t reserved = 0;
+    uint64_t sum = 0;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "RSKNNL01", 8) != 0 || fread(n_rows, 8, 1, f) != 1 ||
+        fread(k, 4, 1, f) != 1 || fread(&reserved, 4, 1, f) != 1 || fread(&sum, 8, 1, f) != 1 || *n_rows < 0 || *k < 1) {
+        fclose(f);
+        return -2;
+    }
+    if (!idx || !sim) { fclose(f); return 0; }
+    const size_t cells = (size_t)*n_rows * (size_t)*k;
+    const bool ok = fread(idx, 4, cells, f) == cells && fread(sim, 8, cells, f) == cells;
+    fclose(f);
+    if (!ok) return -2;
+    uint64_t got = fnv1a(idx, cells * 4, 1469598103934665603ull);
+    got = fnv1a(sim, cells * 8, got);
+    return got == sum ? 0 : -2;
+}
+
+// Rating file -> COO.  core/data.go:287-310 pushes field 2 through strconv.Atoi, so "3.5" and header
+// lines silently become 0; `float_ratings` != 0 parses the rating with strtod instead (half-stars kept)
+// and `skip_header` drops the first line.  Fields 0 and 1 keep the reference's Atoi semantics (0 when
+// not an integer).  Pass users == NULL to count the rows.  Returns the number of rows, -1 on io error.
+static long long atoi_go(const char *b, const char *e) {      // strconv.Atoi: optional sign + digits only, else 0
+    const char *p = b;
+    bool neg = false;
+    if (p < e && (*p == '+' || *p == '-')) { neg = *p == '-'; p++; }
+    if (p == e) return 0;
+    long long v = 0;
+    for (; p < e; p++) {
+        if (*p < '0' || *p > '9') return 0;
+        v = v * 10 + (*p - '0');
+    }
+    return neg ? -v : v;
+}
+
+int64_t rs_host_load_ratings(const char *path, const char *sep, int32_t float_ratings, int32_t skip_header,
+                             int64_t *users, int64_t *items, double *ratings, int64_t cap) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return -1;
+    const size_t sl = strlen(sep);
+    std::string line;
+    int64_t n = 0;
+    bool first = true;
+    int ch;
+    auto flush = [&]() {
+        if (first && skip_header) { first = false; line.clear(); return; }
+        first = false;
+        const char *b = line.data(), *e = b + line.size();
+        if (e > b && e[-1] == '\r') e--;
+        const char *fb[3], *fe[3];
+        int nf = 0;
+        const char *p = b;
+        while (nf < 3) {
+            const char *q = sl ? std::search(p, e, sep, sep + sl) : e;
+            fb[nf] = p; fe[nf] = q; nf++;
+            if (q == e) break;
+            p = q + sl;
+        }
+        if (nf == 3) {        // the reference indexes fields[2] and would panic on a shorter line: such lines are skipped
+            if (users && n < cap) {
+                users[n] = atoi_go(fb[0], fe[0]);
+                items[n] = atoi_go(fb[1], fe[1]);
+                if (float_ratings) {
+                    std::string t(fb[2], fe[2]);
+                    char *end = nullptr;
+                    const double v = strtod(t.c_str(), &end);
+                    ratings[n] = (end && end != t.c_str()) ? v : 0.0;
+                } else {
+                    ratings[n] = (double)atoi_go(fb[2], fe[2]);
+                }
+            }
+            n++;
+        }
+        line.clear();
+    };
+    while ((ch = fgetc(f)) != EOF) {
+        if (ch == '\n') flush(); else line.push_back((char)ch);
+    }
+    if (!line.empty()) flush();
+    fclose(f);
+    return n;
 }
 
 }  // extern "C"

@@ -25,6 +25,15 @@ void rs_host_baseline_sgd(const int32_t *inner_user, const int32_t *inner_item, 
 
 /* Batch ConvertUserID / ConvertItemID (core/data.go:157-183) through a dense raw -> inner table
  * (table[raw] = inner id or -1; raw ids outside [0, n_table) are new ids = -1). */
+/* SURVEY.md §8 f-4.  Neighbour lists (int32 idx, float64 sim)[n_rows][k] on disk, checksummed; replaces
+ * gob Save/Load (core/dump.go:11-36) for the one artefact of a top-k-only Fit.  load with idx == NULL
+ * returns the header only.  0 ok, -1 io error, -2 not a neighbour-list file / checksum mismatch. */
+int32_t rs_host_save_neighbors(const char *path, int64_t n_rows, int32_t k, const int32_t *idx, const double *sim);
+int32_t rs_host_load_neighbors(const char *path, int64_t *n_rows, int32_t *k, int32_t *idx, double *sim);
+/* LoadDataFromFile (core/data.go:287-310).  float_ratings = 0 reproduces the reference (strconv.Atoi on the
+ * rating: half-stars and headers become 0); != 0 keeps fractional ratings.  users == NULL counts rows. */
+int64_t rs_host_load_ratings(const char *path, const char *sep, int32_t float_ratings, int32_t skip_header,
+                             int64_t *users, int64_t *items, double *ratings, int64_t cap);
 /* TrainSet.GlobalMean (core/data.go:134): sequential sum / n. */
 double rs_host_mean_seq(const double *x, int64_t n);
 void rs_host_convert_dense(const int32_t *table, int64_t n_table, const int64_t *raw, int64_t n, int32_t *inner_out);

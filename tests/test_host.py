@@ -110,3 +110,46 @@ def test_shard_rows_cover_everything():
             assert parts[0][0] == 0 and parts[-1][1] == n
             assert all(parts[x][1] == parts[x + 1][0] for x in range(w - 1))
             assert max(b - a for a, b in parts) - min(b - a for a, b in parts) <= 128
+
+
+# ---- persistence of neighbour lists, and the loaders ----
+def test_neighbor_lists_round_trip(tmp_path):
+    rng = np.random.RandomState(3)
+    idx = rng.randint(-1, 5000, size=(777, 40)).astype(np.int32)
+    sim = rng.uniform(-1, 1, size=(777, 40))
+    sim[idx < 0] = np.nan
+    sim[5, 3] = -0.0
+    f = tmp_path / "sub" / "lists.rsknn"          # core/dump.go:25 creates the directory
+    rs.SaveNeighbors(f, idx, sim)
+    i2, s2 = rs.LoadNeighbors(f)
+    assert np.array_equal(i2, idx)
+    assert np.array_equal(s2.view(np.uint64), sim.view(np.uint64))     # bit for bit, NaN payloads and -0.0 included
+    raw = bytearray(f.read_bytes())
+    raw[100] ^= 0x40                                # a flipped payload bit is caught by the checksum
+    f.write_bytes(bytes(raw))
+    with pytest.raises(ValueError):
+        rs.LoadNeighbors(f)
+    f.write_bytes(b"not a list")
+    with pytest.raises(ValueError):
+        rs.LoadNeighbors(f)
+    with pytest.raises(OSError):
+        rs.LoadNeighbors(tmp_path / "missing")
+
+
+def test_loader_reference_semantics_and_half_stars(tmp_path):
+    f = tmp_path / "ratings.csv"
+    f.write_text("userId,movieId,rating,timestamp\n1,31,2.5,1260759144\n1,1029,3.0,1260759179\n7,31,4,1\n9,x,5,2\n")
+    # the reference's loader (core/data.go:302-304): Atoi -> the header line and "2.5"/"3.0" become 0
+    d = rs.LoadDataFromFile(f, sep=",")
+    assert d.Users.tolist() == [0, 1, 1, 7, 9] and d.Items.tolist() == [0, 31, 1029, 31, 0]
+    assert d.Ratings.tolist() == [0.0, 0.0, 0.0, 4.0, 5.0]
+    # the extension keeps half-stars and drops the header
+    d = rs.LoadDataFromFile(f, sep=",", floatRatings=True, hasHeader=True)
+    assert d.Users.tolist() == [1, 1, 7, 9] and d.Ratings.tolist() == [2.5, 3.0, 4.0, 5.0]
+    # tab-separated, CRLF, no trailing newline (the ml-100k u.data form)
+    g = tmp_path / "u.data"
+    g.write_bytes(b"196\t242\t3\t881250949\r\n186\t302\t3\t891717742")
+    d = rs.LoadDataFromFile(g)
+    assert d.Users.tolist() == [196, 186] and d.Items.tolist() == [242, 302] and d.Ratings.tolist() == [3.0, 3.0]
+    with pytest.raises(OSError):
+        rs.LoadDataFromFile(tmp_path / "nope")

@@ -144,3 +144,76 @@ def test_two_rank_symmetric_slabs(tmp_path):
     port = _free_port()
     mp.spawn(_worker_symmetric, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok_sym").read_text() == "ok"
+
+
+def _worker_cyclic(rank, world, port, out_dir):
+    """Cyclic row shards (RS_STORE_MATRIX, shard_count >= 2; ShardedKNN): rows dealt in blocks of 32, every rank
+    computes ONE triangle of its rows, the other triangle is the transpose of cells other ranks computed
+    (here exchanged with an all-gather, on the device pulled from peer memory), test pairs are routed to the
+    owner of their left row and the predictions all-gathered.  The oracle stands in for the device."""
+    sys.path.insert(0, str(ROOT))
+    import torch
+    import torch.distributed as dist
+
+    import recommend_sys_b200 as rs
+    from oracle import binding as ob
+    from recommend_sys_b200.shard import allgather_predictions, route_pairs
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = np.load(ROOT / "tests" / "golden" / "ml100k.npz")
+    tr = g["u1_base"].astype(np.int64)[:30000]
+    te = g["u1_test"].astype(np.int64)[:3000]
+    ts = ob.TrainSet(tr[:, 0], tr[:, 1], tr[:, 2].astype(float))
+    full = ob.KNN(sim="pearson", knn_type="centered", k=10, user_based=True).fit(ts)
+    S = full.sims()
+    n = S.shape[0]
+    rows = rs.core.cyclic_rows(n, world, rank)
+    assert np.array_equal(rs.core.cyclic_owner(rows, world), np.full(len(rows), rank))
+    # this rank's lower triangle only (what the device kernel leaves before rs_knn_mirror)
+    mine = np.full((len(rows), n), np.nan)
+    for li, i in enumerate(rows):
+        mine[li, :i] = S[i, :i]
+    # exchange: every rank publishes its triangle; a rank fills (i, j > i) from the owner of row j
+    sizes = [len(rs.core.cyclic_rows(n, world, r)) for r in range(world)]
+    pad = torch.full((max(sizes), n), float("nan"), dtype=torch.float64)     # shard sizes differ by up to 32 rows
+    pad[: len(rows)] = torch.from_numpy(mine)
+    allp = [torch.empty((max(sizes), n), dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(allp, pad)
+    parts = [allp[r][: sizes[r]] for r in range(world)]
+    local_of = {}
+    for r in range(world):
+        for li, i in enumerate(rs.core.cyclic_rows(n, world, r)):
+            local_of[int(i)] = (r, li)
+    for li, i in enumerate(rows):
+        for j in range(int(i) + 1, n):
+            r, lj = local_of[j]
+            mine[li, j] = parts[r][lj, i]
+    assert np.array_equal(np.nan_to_num(mine), np.nan_to_num(S[rows]))
+    # predictions: routed to the owner of the left row, cold-start pairs spread evenly, all-gathered
+    L = ob.lib()
+    left = np.array([L.or_trainset_convert_user(ts.h, int(u)) for u in te[:, 0]])
+    owner = route_pairs(left, world)
+    assert ((left < 0) | (owner == rs.core.cyclic_owner(np.maximum(left, 0), world))).all()
+    order = np.argsort(owner, kind="stable")
+    counts = np.bincount(owner, minlength=world).tolist()
+    sel = order[sum(counts[:rank]): sum(counts[:rank + 1])]
+    pred = full.predict_batch(te[sel, 0], te[sel, 1])
+    gathered = allgather_predictions(torch.from_numpy(pred), counts).numpy()
+    out = np.empty(len(te))
+    out[order] = gathered
+    want = full.predict_batch(te[:, 0], te[:, 1])
+    assert np.array_equal(np.nan_to_num(out), np.nan_to_num(want))
+    if rank == 0:
+        (Path(out_dir) / "ok_cyc").write_text("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_cyclic_row_shards(tmp_path):
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mp.spawn(_worker_cyclic, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok_cyc").read_text() == "ok"

@@ -87,7 +87,7 @@ def test_sims_bit_exact_both_triangles(ml100k, sim, user_based, tri, monkeypatch
 @pytest.mark.parametrize("count", [2, 3])
 def test_cyclic_row_shards_equal_full(ml100k, count, tri, monkeypatch):
     monkeypatch.setenv("RS_KNN_STREAM_TRI", tri)
-    monkeypatch.setenv("RS_KNN_DENSE_MIN", "200")      # some rows of every shard in dense-row mode
+    monkeypatch.setenv("RS_KNN_HEAVY_MIN", "200")      # some rows of every shard in dense-row mode
     u, i, r = split(ml100k["u1_base"])
     ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
     base = {"sim": rs.Pearson, "userBased": False, "k": 40}
@@ -124,6 +124,30 @@ def test_cyclic_row_shards_equal_full(ml100k, count, tri, monkeypatch):
         est.Close()
 
 
+def test_save_load_estimator_and_neighbor_lists(ml100k, tmp_path):
+    # core/dump_test.go:9-29 (TestSave) for the estimators of this path: the restored model predicts the same
+    u, i, r = split(ml100k["u4_base"])
+    tu, ti, tr = split(ml100k["u4_test"])
+    ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
+    est1 = rs.NewKNNWithZScore(rs.Parameters({"sim": rs.Pearson, "userBased": False, "k": 30}))
+    est1.Fit(ts)
+    err1 = rs.RMSE(np.nan_to_num(rs.NewRawSet(tu, ti, tr).Predict(est1)), tr)
+    rs.Save(tmp_path / "m" / "knn.m", est1)
+    est2 = rs.Load(tmp_path / "m" / "knn.m")
+    p1, p2 = rs.NewRawSet(tu, ti, tr).Predict(est1), rs.NewRawSet(tu, ti, tr).Predict(est2)
+    assert bits_equal(p1, p2) and err1 == rs.RMSE(np.nan_to_num(p2), tr)
+    assert est2.KNNType == "zscore" and est2.Params["sim"] is rs.Pearson and bits_equal(est1.StdDevs, est2.StdDevs)
+    # the neighbour lists of a top-k-only Fit, device -> file -> host
+    idx, sim = est1.TopK(25)
+    rs.SaveNeighbors(tmp_path / "lists.rsknn", idx, sim)
+    i2, s2 = rs.LoadNeighbors(tmp_path / "lists.rsknn")
+    assert np.array_equal(idx, i2) and bits_equal(sim, s2)
+    so = rs.NewSlopeOne(None)
+    so.Fit(ts)
+    rs.Save(tmp_path / "so.m", so)
+    assert bits_equal(rs.NewRawSet(tu, ti, tr).Predict(so), rs.NewRawSet(tu, ti, tr).Predict(rs.Load(tmp_path / "so.m")))
+
+
 def test_k_is_read_at_predict_time(ml100k):
     # core/knn.go:80-81: k / mink are read by Predict, so SetParams after Fit changes the answer
     est, ref = fit_pair(ml100k["u2_base"], "msd", "basic", True, k=40)
@@ -157,14 +181,15 @@ def test_concurrent_predict_on_one_handle(ml100k):
     assert bits_equal(np.concatenate(out), want)
 
 
-# ---- dense-row mode of the exact sparse Fit (rows holding a large share of the right ids are probed
-# instead of walked): every row (min 0), a mix (rows of >= 150 entries), both triangles, a row shard ----
-@pytest.mark.parametrize("dense_min", ["0", "150"])
+# ---- heavy-row mode of the exact sparse Fit (long rows are walked in 32-column sub-chunks with register
+# accumulators instead of one warp per 256-column chunk): every row (min 0), a mix (rows of >= 150
+# entries), both triangles; the row shard takes the plain path ----
+@pytest.mark.parametrize("heavy_min", ["0", "150"])
 @pytest.mark.parametrize("tri", ["upper", "lower"])
 @pytest.mark.parametrize("sim", ["cosine", "msd", "pearson"])
-def test_dense_row_mode_bit_exact(ml100k, sim, tri, dense_min, monkeypatch):
+def test_heavy_row_mode_bit_exact(ml100k, sim, tri, heavy_min, monkeypatch):
     monkeypatch.setenv("RS_KNN_STREAM_TRI", tri)
-    monkeypatch.setenv("RS_KNN_DENSE_MIN", dense_min)
+    monkeypatch.setenv("RS_KNN_HEAVY_MIN", heavy_min)
     est, ref = fit_pair(ml100k["u2_base"], sim, "basic", False, extra={"simPath": "stream"})
     got, want = est.Sims, ref.sims()
     assert np.isnan(np.diag(got)).all()
@@ -318,6 +343,44 @@ def test_symmetric_slab_topk(ml100k, sim, path, monkeypatch):
     k = 50
     base = {"sim": SIMS[sim], "userBased": True, "simPath": path}
     full = rs.NewKNN(rs.Parameters(base))
+    full.Fit(ts)
+    want_i, want_s = full.TopK(k)
+    one = rs.NewKNN(rs.Parameters(dict(base, store="topk", topk=k, shardCount=1)))
+    one.Fit(ts)
+    got_i, got_s = one.TopK(k)
+    assert np.array_equal(got_i, want_i) and bits_equal(got_s, want_s)
+    parts = []
+    for rank in range(3):
+        p = rs.NewKNN(rs.Parameters(dict(base, store="topk", topk=k, shardCount=3, shardIndex=rank)))
+        p.Fit(ts)
+        parts.append(p.TopK(k))
+        p.Close()
+    all_i = torch.from_numpy(np.stack([a for a, _ in parts])).cuda()
+    all_s = torch.from_numpy(np.stack([b for _, b in parts])).cuda()
+    uni_i, uni_s = union_topk_device(all_i, all_s)
+    torch.cuda.synchronize()
+    assert np.array_equal(uni_i.cpu().numpy(), want_i) and bits_equal(uni_s.cpu().numpy(), want_s)
+
+
+@pytest.mark.parametrize("cap", ["1792", "96"])
+@pytest.mark.parametrize("user_based", [True, False])
+@pytest.mark.parametrize("sim", ["cosine", "msd"])
+def test_fused_topk_epilogue(ml100k, sim, user_based, cap, monkeypatch):
+    """RS_STORE_TOPK on the tensor path with the selection FUSED into the pair kernel's epilogue (threshold
+    compare -> candidate append -> merge between the bands of the tile schedule): no similarity row is ever
+    stored.  Forced on the small fixture (large problems take it by themselves); cap = 96 < the band width
+    drives every row through the overflow path (threshold raised, band re-run for the flagged rows)."""
+    import torch
+
+    from recommend_sys_b200.shard import union_topk_device
+
+    monkeypatch.setenv("RS_KNN_TOPK_FUSED", "1")
+    monkeypatch.setenv("RS_KNN_TOPK_CAP", cap)
+    u, i, r = split(ml100k["u3_base"])
+    ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
+    k = 40
+    base = {"sim": SIMS[sim], "userBased": user_based, "simPath": "tensor"}
+    full = rs.NewKNN(rs.Parameters(dict(base, simPath="stream")))
     full.Fit(ts)
     want_i, want_s = full.TopK(k)
     one = rs.NewKNN(rs.Parameters(dict(base, store="topk", topk=k, shardCount=1)))
