@@ -115,6 +115,28 @@ bool tensor_faster(const rs_knn *h) {
     return t_tensor <= t_stream;
 }
 
+// Peer matrices are mapped once per process and device: estimator copies are created and destroyed per
+// fold / per Fit, but their arenas come out of the block cache (devmem.cu), so the same allocations — and
+// the same IPC handles — come back; opening a multi-GB mapping costs milliseconds.
+struct IpcMap { int device; unsigned char handle[64]; void *base; };
+std::mutex g_ipc_mu;
+std::vector<IpcMap> g_ipc;
+
+int32_t ipc_open_cached(int device, const unsigned char *hb, void **base) {
+    std::lock_guard<std::mutex> lk(g_ipc_mu);
+    for (const auto &m : g_ipc)
+        if (m.device == device && !std::memcmp(m.handle, hb, 64)) { *base = m.base; return RS_OK; }
+    cudaIpcMemHandle_t mh;
+    std::memcpy(&mh, hb, 64);
+    RS_CUDA(cudaIpcOpenMemHandle(base, mh, cudaIpcMemLazyEnablePeerAccess));
+    IpcMap m;
+    m.device = device;
+    std::memcpy(m.handle, hb, 64);
+    m.base = *base;
+    g_ipc.push_back(m);
+    return RS_OK;
+}
+
 int32_t init_handle(rs_knn *h) {
     RS_CUDA(cudaSetDevice(h->device));
     RS_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -214,7 +236,6 @@ int32_t rs_knn_destroy(rs_knn *h) {
     free_fit_state(h);
     for (auto &c : h->chunks) rs_cached_free(h->device, c.p, c.bytes);
     h->chunks.clear();
-    for (auto &pm : h->peer_cache) cudaIpcCloseMemHandle(pm.base);
     if (h->tile_buf) cudaFree(h->tile_buf);
     if (h->band_buf) cudaFree(h->band_buf);
     if (h->ovf) rs_cached_free(h->device, h->ovf, h->ovf_bytes);
@@ -794,17 +815,7 @@ int32_t rs_knn_peer_import(rs_knn *h, int32_t n_peers, const unsigned char *hand
         if (q == h->cyc_r) { h->peer_sims[q] = h->sims; continue; }
         const unsigned char *hb = handles + (size_t)q * 64;
         void *base = nullptr;
-        for (const auto &pm : h->peer_cache)
-            if (!std::memcmp(pm.handle, hb, 64)) { base = pm.base; break; }
-        if (!base) {
-            cudaIpcMemHandle_t mh;
-            std::memcpy(&mh, hb, 64);
-            RS_CUDA(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
-            rs_knn::PeerMap pm;
-            std::memcpy(pm.handle, hb, 64);
-            pm.base = base;
-            h->peer_cache.push_back(pm);
-        }
+        RS_TRY(ipc_open_cached(h->device, hb, &base));
         h->peer_sims[q] = reinterpret_cast<const double *>(static_cast<const char *>(base) + offsets[q]);
     }
     return RS_OK;
@@ -864,6 +875,15 @@ int32_t rs_knn_profile_get(rs_knn *h, rs_knn_profile *out) {
 
 int32_t rs_knn_trim_cache(void) {
     rs_cache_trim();
+    std::lock_guard<std::mutex> lk(g_ipc_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (const auto &m : g_ipc) {
+        cudaSetDevice(m.device);
+        cudaIpcCloseMemHandle(m.base);
+    }
+    g_ipc.clear();
+    cudaSetDevice(cur);
     return RS_OK;
 }
 

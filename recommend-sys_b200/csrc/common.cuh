@@ -94,8 +94,6 @@ struct rs_knn {
     int64_t n_work_rows = 0;             // entries of row_order the stream kernel walks
     const double *peer_sims[RS_MAX_PEERS] = {nullptr};   // the shards' matrices (peer memory over NVLink), [cyc_r] = own
     bool peers_ready = false;
-    struct PeerMap { unsigned char handle[64]; void *base; };
-    std::vector<PeerMap> peer_cache;     // IPC mappings opened so far (kept until destroy)
     double global_mean = 0.0, global_bias = 0.0;
     int rating_class = RS_CLASS_INT8;
 

@@ -157,6 +157,7 @@ class ShardedKNN:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self._need_mirror = False
 
     def Fit(self, trainSet):
         import numpy as np
@@ -188,9 +189,17 @@ class ShardedKNN:
                         trainSet.GlobalMean, d_lb.data_ptr() if d_lb is not None else 0,
                         d_rb.data_ptr() if d_rb is not None else 0, gb)
         self._keep = (d_left, d_right, d_rating, d_lb, d_rb)
-        attach_peers_and_mirror(k._h, self.group)
-        k._after_fit()
+        # like rs_knn_fit, Fit returns while the similarity kernel runs: the exchange step (which waits for
+        # it, here and on every peer) is deferred to the first call that needs the whole rows, so the host
+        # work in between — converting and routing the test set's ids — overlaps the kernel
+        self._need_mirror = True
         return self
+
+    def _finish_fit(self):
+        if self._need_mirror:
+            attach_peers_and_mirror(self.knn._h, self.group)
+            self.knn._after_fit()
+            self._need_mirror = False
 
     def PredictBatch(self, userIDs, itemIDs):
         import numpy as np
@@ -208,6 +217,7 @@ class ShardedKNN:
         d_l = torch.from_numpy(np.ascontiguousarray(left[mine], dtype=np.int32)).to(dev)
         d_r = torch.from_numpy(np.ascontiguousarray(right[mine], dtype=np.int32)).to(dev)
         d_o = torch.empty(max(1, len(mine)), dtype=torch.float64, device=dev)
+        self._finish_fit()
         if len(mine):
             k._h.predict_batch_device(d_l.data_ptr(), d_r.data_ptr(), len(mine), d_o.data_ptr())
         allp = allgather_predictions(d_o[: len(mine)], counts, group=self.group)

@@ -148,6 +148,29 @@ def test_save_load_estimator_and_neighbor_lists(ml100k, tmp_path):
     assert bits_equal(rs.NewRawSet(tu, ti, tr).Predict(so), rs.NewRawSet(tu, ti, tr).Predict(rs.Load(tmp_path / "so.m")))
 
 
+def test_cpp_host_mirror_benchmark_on_ml100k(ml100k, tmp_path):
+    """host/core.hpp + host/benchmark.cc — the compiled mirror of the reference's Go API and of benchmark.go —
+    run end to end over the same C ABI on the real MovieLens-100K: 5-fold cross-validation with params = nil,
+    held to the reference's own acceptance bounds (core/base_test.go:46-64, RMSE/MAE <= expect + 0.008)."""
+    import subprocess
+    from pathlib import Path
+
+    exe = Path(rs.core.__file__).resolve().parent / "rs_benchmark"
+    assert exe.exists(), "run __graft_entry__.build() (host/Makefile builds rs_benchmark)"
+    data = tmp_path / "u.data"
+    np.savetxt(data, ml100k["u_data"][:, :3], fmt="%d", delimiter="\t")
+    out = subprocess.run([str(exe), str(data)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    rows = {}
+    for line in out.stdout.splitlines()[1:]:
+        parts = line.rsplit(None, 3)
+        rows[parts[0].strip()] = (float(parts[1]), float(parts[2]))
+    bounds = {"KNN": (0.980, 0.774), "Centered K-NN": (0.951, 0.749), "K-NN Z-Score": (0.951, 0.746),
+              "K-NN Baseline": (0.931, 0.733), "Slope One": (0.946, 0.743)}
+    for name, (rmse, mae) in bounds.items():
+        assert rows[name][0] <= rmse + 0.008 and rows[name][1] <= mae + 0.008, (name, rows[name])
+
+
 def test_k_is_read_at_predict_time(ml100k):
     # core/knn.go:80-81: k / mink are read by Predict, so SetParams after Fit changes the answer
     est, ref = fit_pair(ml100k["u2_base"], "msd", "basic", True, k=40)
