@@ -608,7 +608,11 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_compact_kernel(
         }
     }
     if (threadIdx.x == 0) {
-        if (total >= k) { thr_key[g] = keys[k - 1]; thr_id[g] = (int32_t)pos[k - 1]; }
+        // merged: the k-th best is IN the list, only strictly better entries matter from here on.  Overflowed:
+        // the buffer is discarded, so the k-th best of (list U buffer) itself — a real entry that may belong
+        // to the final list — and everything above it must be admitted again: threshold = just below it
+        // (same key, id + 1).
+        if (total >= k) { thr_key[g] = keys[k - 1]; thr_id[g] = (int32_t)pos[k - 1] + (over ? 1 : 0); }
         else { thr_key[g] = 0ull; thr_id[g] = -1; }            // list not full: accept every valid similarity
         cand_cnt[g] = 0;
         row_flag[g] = over ? 1 : 0;

@@ -198,21 +198,29 @@ __global__ void row_len_kernel(const int64_t *__restrict__ l_ptr, int32_t n_left
     ids[i] = i;
 }
 
-// cp[c][q] = number of entries of right row c with left id < q*JC (lower bound by binary search)
+// cp[c][q] = number of entries of right row c with left id < (q0 + q) * jc, for q = 0 .. n_q (the chunk
+// boundaries inside every right row).  One warp per right row walks the row once: an entry whose chunk
+// differs from its predecessor's closes the boundaries in between (no binary searches: 14.6 M of them, 7
+// dependent loads each, were the largest kernel of the ML-20M prep).
 __global__ void build_cp_kernel(const int64_t *__restrict__ r_ptr, const int32_t *__restrict__ r_col,
-                                int32_t n_right, int32_t n_chunks, int32_t jc, int32_t *__restrict__ cp) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t per = n_chunks + 1;
-    if (t >= (int64_t)n_right * per) return;
-    const int32_t c = (int32_t)(t / per), q = (int32_t)(t % per);
+                                int32_t n_right, int32_t q0, int32_t n_q, int32_t jc, int32_t *__restrict__ cp) {
+    const int32_t c = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= n_right) return;
     const int64_t b = r_ptr[c], e = r_ptr[c + 1];
-    const int64_t target = (int64_t)q * jc;
-    int64_t lo = b, hi = e;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (r_col[mid] < target) lo = mid + 1; else hi = mid;
+    int32_t *out = cp + (int64_t)c * (n_q + 1);
+    // boundary q is closed by the first entry whose chunk index (relative to q0, clamped) is >= q
+    auto rel = [&](int32_t col) {
+        const int32_t q = col / jc - q0;
+        return q < 0 ? -1 : (q >= n_q ? n_q : q);            // -1: before the window, n_q: beyond it
+    };
+    for (int64_t x0 = b; x0 <= e; x0 += 32) {                 // x == e is the sentinel that closes the tail
+        const int64_t x = x0 + lane;
+        if (x > e) continue;
+        const int32_t cur = x < e ? rel(r_col[x]) : n_q;      // sentinel after the last entry
+        const int32_t prev = x > b ? rel(r_col[x - 1]) : -1;
+        for (int32_t q = prev + 1; q <= cur; q++) out[q] = (int32_t)(x - b);
     }
-    cp[t] = (int32_t)(lo - b);
 }
 
 // l2r[e] for the left-CSR entry e = (i, c): position of (c, i) in the right CSR.  Both CSRs are
@@ -497,84 +505,6 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     return RS_OK;
 }
 
-// Heavy rows (sim_stream.cu: sim_stream_heavy_kernel): rows of >= 4096 entries whose triangle lies
-// inside a window of 4096 columns are split off the longest-first order; they are walked in 32-column
-// sub-chunks with register accumulators, which needs the 32-column boundaries of every right row
-// inside that window (cp32).  `order`: the rows to process, longest first.  Writes h->row_order (the
-// other rows, same order), h->row_heavy, the counts, and cp32.
-struct HeavyPred {
-    const int64_t *l_ptr;
-    int64_t min_len;
-    int32_t id_lo, id_hi;
-    bool negate;
-    __host__ __device__ bool operator()(const int32_t &i) const {
-        const bool heavy = (l_ptr[i + 1] - l_ptr[i] >= min_len) && i >= id_lo && i < id_hi;
-        return heavy != negate;
-    }
-};
-
-__global__ void build_cp32_kernel(const int64_t *__restrict__ r_ptr, const int32_t *__restrict__ r_col,
-                                  int32_t n_right, int32_t sub_lo, int32_t n_sub, int32_t *__restrict__ cp) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t per = n_sub + 1;
-    if (t >= (int64_t)n_right * per) return;
-    const int32_t c = (int32_t)(t / per), q = (int32_t)(t % per);
-    const int64_t b = r_ptr[c], e = r_ptr[c + 1];
-    const int64_t target = ((int64_t)sub_lo + q) * 32;
-    int64_t lo = b, hi = e;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (r_col[mid] < target) lo = mid + 1; else hi = mid;
-    }
-    cp[t] = (int32_t)(lo - b);
-}
-
-static int32_t split_heavy_rows(rs_knn *h, const int32_t *order, int64_t n_rows, bool allow) {
-    cudaStream_t st = h->stream;
-    constexpr int32_t WINDOW = 4096;                       // columns covered by cp32
-    int64_t min_len = 4096;
-    if (const char *e = getenv("RS_KNN_HEAVY_MIN")) min_len = atoll(e);      // tests: 0 = every row in the window
-    h->n_heavy = 0;
-    h->row_heavy = nullptr;
-    h->cp32 = nullptr;
-    h->n_work_rows = n_rows;
-    if (n_rows <= 0) return RS_OK;
-    RS_TRY(rs_alloc(h, &h->row_order, (size_t)n_rows));
-    if (!allow || min_len < 0) {
-        RS_CUDA(cudaMemcpyAsync(h->row_order, order, (size_t)n_rows * 4, cudaMemcpyDeviceToDevice, st));
-        return RS_OK;
-    }
-    // the triangle of a heavy row must lie inside the window: the first (lower triangle) or the last
-    // (upper triangle) WINDOW columns
-    int32_t id_lo = 0, id_hi = h->n_left;
-    if (h->stream_lower) id_hi = h->n_left < WINDOW ? h->n_left : WINDOW;
-    else id_lo = h->n_left > WINDOW ? (h->n_left - WINDOW) / 32 * 32 : 0;
-    RS_TRY(rs_alloc(h, &h->row_heavy, (size_t)n_rows));
-    int32_t *d_num;
-    RS_TRY(rs_alloc(h, &d_num, 4));
-    HeavyPred yes{h->l_ptr, min_len, id_lo, id_hi, false}, no{h->l_ptr, min_len, id_lo, id_hi, true};
-    size_t need = 0;
-    RS_CUDA(cub::DeviceSelect::If(nullptr, need, order, h->row_heavy, d_num, (int)n_rows, yes, st));
-    void *tmp;
-    RS_TRY(rs_dev_alloc(h, &tmp, need + 256));
-    RS_CUDA(cub::DeviceSelect::If(tmp, need, order, h->row_heavy, d_num, (int)n_rows, yes, st));
-    RS_CUDA(cub::DeviceSelect::If(tmp, need, order, h->row_order, d_num + 1, (int)n_rows, no, st));
-    int32_t cnt = 0;
-    RS_CUDA(cudaMemcpyAsync(&cnt, d_num, 4, cudaMemcpyDeviceToHost, st));
-    RS_CUDA(cudaStreamSynchronize(st));
-    h->n_heavy = cnt;
-    h->n_work_rows = n_rows - cnt;
-    if (cnt > 0) {
-        h->h32_lo = id_lo / 32;
-        h->h32_n = (id_hi - id_lo + 31) / 32;
-        RS_TRY(rs_alloc(h, &h->cp32, (size_t)h->n_right * ((size_t)h->h32_n + 1)));
-        build_cp32_kernel<<<blocks_for((int64_t)h->n_right * (h->h32_n + 1)), T, 0, st>>>(
-            h->r_ptr, h->r_col, h->n_right, h->h32_lo, h->h32_n, h->cp32);
-        h->prof.total_launches++;
-    }
-    return RS_OK;
-}
-
 int32_t rs_prep_rt(rs_knn *h) {
     cudaStream_t st = h->stream;
     h->n_chunks = (int32_t)(((int64_t)h->n_left + h->stream_jc - 1) / h->stream_jc);
@@ -584,13 +514,13 @@ int32_t rs_prep_rt(rs_knn *h) {
     build_rdev_kernel<<<blocks_for((int64_t)h->n_right * 32), T, 0, st>>>(
         h->r_ptr, h->r_col, h->r_val, h->n_right, h->p.sim, h->pmeans, h->left_bias, h->right_bias, h->global_bias,
         h->r_dev);
-    build_cp_kernel<<<blocks_for((int64_t)h->n_right * (h->n_chunks + 1)), T, 0, st>>>(
-        h->r_ptr, h->r_col, h->n_right, h->n_chunks, h->stream_jc, h->cp);
+    build_cp_kernel<<<blocks_for((int64_t)h->n_right * 32), T, 0, st>>>(h->r_ptr, h->r_col, h->n_right, 0, h->n_chunks,
+                                                                         h->stream_jc, h->cp);
     invert_perm_kernel<<<blocks_for(h->nnz), T, 0, st>>>(h->perm_rl, h->nnz, h->perm_tmp);
     compose_l2r_kernel<<<blocks_for(h->nnz), T, 0, st>>>(h->perm_lr, h->perm_tmp, h->nnz, h->l2r);
     h->prof.total_launches += 4;
     // rows of the shard ordered longest first (a stable descending sort of the row lengths keeps the
-    // order deterministic), then split into heavy rows and the rest
+    // order deterministic): the longest work items start first
     {
         const int64_t rb = h->row_begin, rows = h->row_end - h->row_begin;
         int32_t *len, *len_sorted, *ids, *sorted;
@@ -604,7 +534,6 @@ int32_t rs_prep_rt(rs_knn *h) {
             // rows are produced slab by slab into a slab-sized buffer: keep the natural order
             h->row_order = ids;
             h->n_work_rows = -1;                 // the launcher takes [row_begin, row_end) of the natural order
-            h->n_heavy = 0;
             RS_CUDA(cudaGetLastError());
             return RS_OK;
         }
@@ -615,7 +544,6 @@ int32_t rs_prep_rt(rs_knn *h) {
         RS_TRY(rs_dev_alloc(h, &tmp, need));
         RS_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, need, len + rb, len_sorted + rb, ids + rb,
                                                           sorted, (int)rows, 0, 32, st));
-        const bool full = h->row_begin == 0 && h->row_end == h->n_left;
         if (h->cyc_R > 1) {
             // cyclic shards: the owned rows picked out of the longest-first order
             int32_t *owned, *d_num;
@@ -627,9 +555,11 @@ int32_t rs_prep_rt(rs_knn *h) {
             void *tmp2;
             RS_TRY(rs_dev_alloc(h, &tmp2, need2 + 256));
             RS_CUDA(cub::DeviceSelect::If(tmp2, need2, sorted, owned, d_num, (int)h->n_left, pred, st));
-            RS_TRY(split_heavy_rows(h, owned, h->rows_local, true));
+            h->row_order = owned;
+            h->n_work_rows = h->rows_local;
         } else {
-            RS_TRY(split_heavy_rows(h, sorted, rows, full));
+            h->row_order = sorted;
+            h->n_work_rows = rows;
         }
     }
     RS_CUDA(cudaGetLastError());

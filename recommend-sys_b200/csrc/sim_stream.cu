@@ -201,110 +201,6 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// Heavy rows.  The column walk above gives one warp a whole (row, 256-column chunk): for a
-// blockbuster row (78 k entries on the MovieLens-20M shape) that is a serial chain of 78 k dependent
-// shared-memory read-modify-write steps — 25 ms, whatever the number of GPUs (profiles/
-// r02_stream_notes.md).  Heavy rows are therefore walked in 32-column sub-chunks with the
-// accumulators in REGISTERS: lane l owns column j0 + l.  For every entry c the (<= 32) raters of c
-// inside the sub-chunk are loaded coalesced, a warp-wide OR of (1 << column) tells every lane whether
-// its column is among them and — the run being sorted by column — the popcount below its bit is the
-// lane that holds its b-side term.  No shared memory, no ordering barrier; each accumulator still
-// receives its terms in ascending right id, the reference's order (core/sim.go:65-79).
-struct HeavyArgs {
-    const int32_t *rows;      // heavy rows, longest first
-    int32_t n_rows;
-    const int32_t *cp32;      // [n_right][n_sub + 1] offsets of the 32-column boundaries inside each right row
-    int32_t sub_lo, n_sub;    // covered sub-chunks [sub_lo, sub_lo + n_sub)
-    unsigned long long *counter;
-};
-
-constexpr int HG = 8;
-
-template <int SIM, bool SHRINK>
-__global__ void __launch_bounds__(256) sim_stream_heavy_kernel(StreamArgs a, HeavyArgs hv) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const int64_t n_items = (int64_t)hv.n_rows * hv.n_sub;
-    const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
-    const int32_t *__restrict__ r_col = a.r_col;
-    const double *__restrict__ r_dev = a.r_dev;
-    for (;;) {
-        unsigned long long item = 0;
-        if (lane == 0) item = atomicAdd(hv.counter, 1ull);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if ((int64_t)item >= n_items) break;
-        const int32_t i = hv.rows[(int64_t)item / hv.n_sub];
-        const int32_t sx = (int32_t)((int64_t)item % hv.n_sub);
-        const int64_t j0 = (int64_t)(hv.sub_lo + sx) * 32;
-        if (a.symmetric == 1 && j0 + 32 <= i) continue;      // every column of the sub-chunk is < i
-        if (a.symmetric == 2 && j0 > i) continue;            // every column of the sub-chunk is > i
-        const int64_t j = j0 + lane;
-        bool want = j < a.n_left && j != i;                  // the diagonal pair is never accumulated
-        if (a.symmetric == 1) want = want && j > i;
-        if (a.symmetric == 2) want = want && j < i;
-        double ai = 0.0;
-        if (SIM == RS_SIM_PEARSON) ai = a.pmeans[i];
-        if (SIM == RS_SIM_PEARSON_BASELINE) ai = a.global_bias + a.left_bias[i];
-        double m = 0.0, n = 0.0, l = 0.0, cnt = 0.0;
-        const int64_t eb = a.l_ptr[i], ee = a.l_ptr[i + 1];
-        for (int64_t x0 = eb; x0 < ee; x0 += 32) {
-            const int64_t e = x0 + lane;
-            double ra = 0.0;
-            uint32_t lo = 0;
-            int nr = 0;
-            if (e < ee) {
-                const int32_t c = a.l_col[e];
-                const double v = a.l_val[e];
-                if (SIM == RS_SIM_PEARSON) ra = v - ai;                           // core/sim.go:73
-                else if (SIM == RS_SIM_PEARSON_BASELINE) { const double bb = ai + a.right_bias[c]; ra = v - bb; }
-                else ra = v;
-                const int32_t *cpc = hv.cp32 + (int64_t)c * (hv.n_sub + 1) + sx;
-                const int32_t o0 = cpc[0], o1 = cpc[1];
-                lo = (uint32_t)(a.r_ptr[c] + o0);
-                nr = o1 - o0;                                                     // <= 32: one rater per column
-            }
-            const int lim = (ee - x0) < 32 ? (int)(ee - x0) : 32;
-            for (int u0 = 0; u0 < lim; u0 += HG) {
-                uint32_t bit[HG];
-                double rbv[HG];
-                int nn[HG];
-#pragma unroll
-                for (int g = 0; g < HG; g++) {
-                    const int u = u0 + g;                                         // < 32 always (HG divides 32)
-                    nn[g] = __shfl_sync(0xffffffffu, nr, u);                      // 0 for u >= lim
-                    const uint32_t lo_u = __shfl_sync(0xffffffffu, lo, u);
-                    bit[g] = 0u;
-                    rbv[g] = 0.0;
-                    if (lane < nn[g]) {
-                        bit[g] = 1u << (r_col[lo_u + (uint32_t)lane] - (int32_t)j0);
-                        rbv[g] = r_dev[lo_u + (uint32_t)lane];                    // jr | jr - meanB (core/sim.go:74)
-                    }
-                }
-#pragma unroll
-                for (int g = 0; g < HG; g++) {
-                    if (nn[g] == 0) continue;                                     // warp-uniform
-                    const uint32_t mask = __reduce_or_sync(0xffffffffu, bit[g]);
-                    const int src = __popc(mask & lt_mask);                       // the run is sorted by column
-                    const double rb = __shfl_sync(0xffffffffu, rbv[g], src);
-                    const double ra_u = __shfl_sync(0xffffffffu, ra, u0 + g);
-                    if (want && ((mask >> lane) & 1u)) {
-                        if (SIM == RS_SIM_MSD) { const double d = ra_u - rb; m += d * d; n += 1.0; }      // core/sim.go:37-38
-                        else { m += ra_u * ra_u; n += rb * rb; l += ra_u * rb; if (SHRINK) cnt += 1.0; }  // core/sim.go:19-21 / :75-77
-                    }
-                }
-            }
-        }
-        double s;
-        if (SIM == RS_SIM_MSD) s = 1.0 / (m / n + 1.0);                           // core/sim.go:43
-        else s = l / (sqrt(m) * sqrt(n));                                        // core/sim.go:24 / :80
-        if (SHRINK) s = (cnt - 1.0) / (cnt - 1.0 + a.shrinkage) * s;
-        if (j == i) { s = nan_v; want = true; }                                   // diagonal stays NaN
-        if (want && j < a.n_left)
-            a.sims[(a.cyc_R > 1 ? rs_cyc_local(i, a.cyc_R) : (int64_t)(i - a.row_begin)) * a.ld_s + j] = s;
-    }
-}
-
 // Mirror the computed upper block-triangle into the lower one: the three similarities are
 // bit-symmetric (sums and products commute), which is why the reference can write
 // Sims[j][i] = Sims[i][j] (core/knn.go:205-208).  32x32 tiles through shared memory,
@@ -383,36 +279,12 @@ static int32_t launch_stream(rs_knn *h, const StreamArgs &s, int grid) {
     return s.symmetric ? launch_stream_sym<SIM, SHRINK, 1>(h, s, grid) : launch_stream_sym<SIM, SHRINK, 0>(h, s, grid);
 }
 
-template <int SIM, bool SHRINK>
-static int32_t launch_heavy(rs_knn *h, const StreamArgs &a, const HeavyArgs &hv) {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    int64_t grid = ((int64_t)hv.n_rows * hv.n_sub + 7) / 8;
-    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
-    // on the auxiliary stream, side by side with the column walk of the other rows
-    sim_stream_heavy_kernel<SIM, SHRINK><<<(unsigned)grid, 256, 0, h->aux_stream>>>(a, hv);
-    h->prof.total_launches += 1;
-    return RS_OK;
-}
-
-static int32_t rs_heavy_rows_launch(rs_knn *h, const StreamArgs &a, const HeavyArgs &hv) {
-    switch (h->p.sim) {
-    case RS_SIM_COSINE: return launch_heavy<RS_SIM_COSINE, false>(h, a, hv);
-    case RS_SIM_MSD: return launch_heavy<RS_SIM_MSD, false>(h, a, hv);
-    case RS_SIM_PEARSON: return launch_heavy<RS_SIM_PEARSON, false>(h, a, hv);
-    case RS_SIM_PEARSON_BASELINE:
-        return h->p.shrinkage > 0.0 ? launch_heavy<RS_SIM_PEARSON_BASELINE, true>(h, a, hv)
-                                    : launch_heavy<RS_SIM_PEARSON_BASELINE, false>(h, a, hv);
-    default: rs_set_error("unknown similarity %d", h->p.sim); return RS_ERR_INVALID;
-    }
-}
-
 int32_t rs_sim_stream_launch(rs_knn *h) {
     StreamArgs a{};
     a.l_ptr = h->l_ptr; a.l_col = h->l_col; a.l_val = h->l_val; a.l2r = h->l2r;
     a.r_ptr = h->r_ptr; a.r_col = h->r_col; a.r_dev = h->r_dev; a.cp = h->cp; a.n_chunks = h->n_chunks;
     const bool cyc = h->cyc_R > 1;
-    // rs_prep_rt leaves the rows to walk (longest first, heavy rows split off) in row_order; in top-k-only
+    // rs_prep_rt leaves the rows to walk (longest first) in row_order; in top-k-only
     // mode (n_work_rows < 0) it is the natural order and the current slab is a slice of it
     a.row_order = h->n_work_rows >= 0 ? h->row_order : h->row_order + h->row_begin;
     a.n_rows = h->n_work_rows >= 0 ? h->n_work_rows : h->row_end - h->row_begin;
@@ -424,23 +296,7 @@ int32_t rs_sim_stream_launch(rs_knn *h) {
     a.symmetric = h->force_sym ? 1 : ((h->row_begin == 0 && h->row_end == h->n_left) || cyc) ? (h->stream_lower ? 2 : 1) : 0;
     a.counter = reinterpret_cast<unsigned long long *>(h->d_flags + 2);
     RS_CUDA(cudaMemsetAsync(a.counter, 0, 8, h->stream));
-    // heavy rows (rs_prep_rt split them off the order) run on the auxiliary stream beside the column walk
-    const bool heavy = h->n_heavy > 0 && a.symmetric != 0 && !h->force_sym;
-    if (heavy) {
-        HeavyArgs hv{};
-        hv.rows = h->row_heavy; hv.n_rows = h->n_heavy; hv.cp32 = h->cp32; hv.sub_lo = h->h32_lo; hv.n_sub = h->h32_n;
-        hv.counter = reinterpret_cast<unsigned long long *>(h->d_flags + 12);
-        RS_CUDA(cudaMemsetAsync(hv.counter, 0, 8, h->stream));
-        RS_CUDA(cudaEventRecord(h->ev_fork, h->stream));
-        RS_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
-        RS_TRY(rs_heavy_rows_launch(h, a, hv));
-        RS_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
-    }
-    if (a.n_rows <= 0) {
-        if (heavy) RS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-        RS_CUDA(cudaGetLastError());
-        return RS_OK;
-    }
+    if (a.n_rows <= 0) return RS_OK;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const int64_t items = a.n_rows * (int64_t)h->n_chunks;
@@ -456,7 +312,6 @@ int32_t rs_sim_stream_launch(rs_knn *h) {
         break;
     default: rs_set_error("unknown similarity %d", h->p.sim); return RS_ERR_INVALID;
     }
-    if (heavy) RS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     h->prof.sim_launches++;
     h->prof.total_launches++;
     RS_CUDA(cudaGetLastError());

@@ -38,6 +38,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1008,17 +1009,34 @@ int32_t launch_shape(rs_knn *h, const TcArgs &a, bool cosums) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-// Fused top-k (RS_STORE_TOPK on the tensor path, large problems): the block-triangular tile set of the
-// pair kernel is cut into BANDS by the distance of a tile from the diagonal, band w covering column
-// distances [D_w, D_w+1) with D = -128, 512, 1024, 2048, ... (doubling).  A row therefore meets at most
-// ~1.5 k new columns in band 0 — all of them candidates, there is no threshold yet — and in every later
-// band about as many columns as it has seen before, of which only ~k beat its current k-th best: the
-// candidate buffers stay small (cand_cap per row) and the N x N matrix, or any slab of it, never exists.
-// The tiles of a band are dealt round-robin to the shards of a multi-GPU Fit (equal cost per tile).
-int32_t rs_tensor_band_count(const rs_knn *h) {
-    int w = 1;
-    for (int64_t d = 512; d < (int64_t)h->n_left + 128; d *= 2) w++;
-    return w;
+// Fused top-k (RS_STORE_TOPK on the tensor path, large problems): the pair kernel tests every similarity
+// against thresholds that are refreshed only BETWEEN launches, so the block-triangular tile set is cut into
+// waves that keep the number of survivors per row small:
+//   wave 0      the tiles within 512 columns of the diagonal: every row meets ~1.5 k columns, all of them
+//               candidates (there is no threshold yet) — the bootstrap sample;
+//   waves 1..W  all other tiles, grouped in supertiles of 4 x 8 cluster tiles (1024 x 1024 similarities, the
+//               unit of L2 sharing) taken in a PSEUDO-RANDOM order, wave w ending at the fraction 2^(w-W) of
+//               them: a wave brings a row about as many new columns as it has seen before, in an order that
+//               is independent of the ids — of which ~k beat the row's current k-th best.
+// The order matters because ties are broken by id: user-based MSD is 1.0 for thousands of pairs per row (one
+// co-rated item, equal ratings), and a schedule that feeds a row ids in DESCENDING order (plain bands by distance
+// did, for the columns left of the diagonal) makes every one of those ties a survivor.
+// The N x N matrix, or any slab of it, never exists.  The supertiles of each wave are dealt round-robin to the
+// shards of a multi-GPU Fit (equal cost per tile).
+static int32_t band_waves(int64_t n_left) {
+    // two extra small waves at the start: the thresholds of the bootstrap band are weak for rows with thousands
+    // of tied similarities, and a re-run of a small wave is cheap but not free (13 ms each on config 4)
+    int w = 0;
+    for (int64_t seen = 1536; seen < n_left; seen *= 2) w++;
+    return w < 1 ? 1 : w + 2;
+}
+int32_t rs_tensor_band_count(const rs_knn *h) { return 1 + band_waves(h->n_left); }
+
+static inline uint64_t mix64(uint64_t x) {     // splitmix64 finaliser
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
 }
 
 int32_t rs_sim_tensor_band_launch(rs_knn *h, int32_t wave) {
@@ -1033,26 +1051,44 @@ int32_t rs_sim_tensor_band_launch(rs_knn *h, int32_t wave) {
     if (memcmp(key, h->band_key, sizeof(key)) != 0) {
         // cluster tiles: cbi = 256 rows, cbj = 128 columns; needed iff the tile holds a pair with j > i
         const int ncbi = (int)((h->n_left + 2 * BM - 1) / (2 * BM)), ncbj = (int)((h->n_left + pair::P_BN - 1) / pair::P_BN);
-        // rasterised in supertiles of 4 x 8 cluster tiles (1024 x 1024 similarities) so that the pairs running
-        // at the same time share operand rows in L2, as in the matrix schedule below
+        const int W = n_waves - 1;
         std::vector<std::vector<int2>> bands(n_waves);
-        std::vector<int64_t> dealt(n_waves, 0);
-        std::vector<char> seen(n_waves);
         constexpr int SI = 4, SJ = 8;
+        auto tile_dist = [&](int cbi, int cbj) { return (int64_t)cbj * pair::P_BN - (int64_t)cbi * 2 * BM; };
+        struct Sup { uint64_t h; int sbi, sbj; };
+        std::vector<Sup> sups;
+        int64_t dealt0 = 0;
         for (int sbi = 0; sbi < ncbi; sbi += SI)
             for (int sbj = 0; sbj < ncbj; sbj += SJ) {
-                // whole supertiles are dealt to the shards (a band's share of one supertile stays on one GPU)
-                std::fill(seen.begin(), seen.end(), 0);
+                bool any0 = false, any1 = false;
                 for (int cbi = sbi; cbi < sbi + SI && cbi < ncbi; cbi++)
                     for (int cbj = sbj; cbj < sbj + SJ && cbj < ncbj; cbj++) {
-                        const int64_t d = (int64_t)cbj * pair::P_BN - (int64_t)cbi * 2 * BM;   // column distance of the tile
+                        const int64_t d = tile_dist(cbi, cbj);
                         if (d + pair::P_BN <= 0) continue;                                     // every column <= every row
-                        int w = 0;
-                        for (int64_t lim = 512; d >= lim; lim *= 2) w++;
-                        if (!seen[w]) { seen[w] = 1; dealt[w]++; }
-                        if ((dealt[w] - 1) % shard_count == shard_index) bands[w].push_back(make_int2(cbi, cbj));
+                        if (d < 512) any0 = true; else any1 = true;
                     }
+                if (any0) {     // wave 0: the diagonal band, whole supertile shares dealt to one shard
+                    const bool mine = dealt0++ % shard_count == shard_index;
+                    for (int cbi = sbi; cbi < sbi + SI && cbi < ncbi; cbi++)
+                        for (int cbj = sbj; cbj < sbj + SJ && cbj < ncbj; cbj++) {
+                            const int64_t d = tile_dist(cbi, cbj);
+                            if (d + pair::P_BN > 0 && d < 512 && mine) bands[0].push_back(make_int2(cbi, cbj));
+                        }
+                }
+                if (any1) sups.push_back({mix64(((uint64_t)sbi << 32) | (uint64_t)sbj), sbi, sbj});
             }
+        std::sort(sups.begin(), sups.end(), [](const Sup &x, const Sup &y) { return x.h < y.h; });
+        for (size_t q = 0; q < sups.size(); q++) {
+            // wave w (1..W) ends at the fraction 2^(w-W) of the shuffled supertiles
+            int w = 1;
+            while (w < W && (double)(q + 1) > (double)sups.size() * std::ldexp(1.0, w - W)) w++;
+            if ((int64_t)q % shard_count != shard_index) continue;
+            for (int cbi = sups[q].sbi; cbi < sups[q].sbi + SI && cbi < ncbi; cbi++)
+                for (int cbj = sups[q].sbj; cbj < sups[q].sbj + SJ && cbj < ncbj; cbj++) {
+                    const int64_t d = tile_dist(cbi, cbj);
+                    if (d >= 512) bands[w].push_back(make_int2(cbi, cbj));
+                }
+        }
         std::vector<int2> flat;
         h->band_off.assign(n_waves + 1, 0);
         for (int w = 0; w < n_waves; w++) {

@@ -87,7 +87,6 @@ def test_sims_bit_exact_both_triangles(ml100k, sim, user_based, tri, monkeypatch
 @pytest.mark.parametrize("count", [2, 3])
 def test_cyclic_row_shards_equal_full(ml100k, count, tri, monkeypatch):
     monkeypatch.setenv("RS_KNN_STREAM_TRI", tri)
-    monkeypatch.setenv("RS_KNN_HEAVY_MIN", "200")      # some rows of every shard in dense-row mode
     u, i, r = split(ml100k["u1_base"])
     ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
     base = {"sim": rs.Pearson, "userBased": False, "k": 40}
@@ -202,28 +201,6 @@ def test_concurrent_predict_on_one_handle(ml100k):
     [t.start() for t in ths]
     [t.join() for t in ths]
     assert bits_equal(np.concatenate(out), want)
-
-
-# ---- heavy-row mode of the exact sparse Fit (long rows are walked in 32-column sub-chunks with register
-# accumulators instead of one warp per 256-column chunk): every row (min 0), a mix (rows of >= 150
-# entries), both triangles; the row shard takes the plain path ----
-@pytest.mark.parametrize("heavy_min", ["0", "150"])
-@pytest.mark.parametrize("tri", ["upper", "lower"])
-@pytest.mark.parametrize("sim", ["cosine", "msd", "pearson"])
-def test_heavy_row_mode_bit_exact(ml100k, sim, tri, heavy_min, monkeypatch):
-    monkeypatch.setenv("RS_KNN_STREAM_TRI", tri)
-    monkeypatch.setenv("RS_KNN_HEAVY_MIN", heavy_min)
-    est, ref = fit_pair(ml100k["u2_base"], sim, "basic", False, extra={"simPath": "stream"})
-    got, want = est.Sims, ref.sims()
-    assert np.isnan(np.diag(got)).all()
-    assert bits_equal(got, want)
-    n = got.shape[0]
-    b, e = n // 4, n // 4 + 300
-    part = rs.NewKNN(rs.Parameters({"sim": SIMS[sim], "userBased": False, "simPath": "stream",
-                                    "rowBegin": b, "rowEnd": e}))
-    u, i, r = split(ml100k["u2_base"])
-    part.Fit(rs.NewTrainSet(rs.NewRawSet(u, i, r)))
-    assert bits_equal(part.Sims, want[b:e])
 
 
 # ---- arbitrary float64 ratings (continuous values, thousands of distinct ones): the stream path
@@ -632,6 +609,64 @@ def test_ml1m_shape_properties():
     sel = np.where((ii >= 1000) & (ii < 1256))[0][:2000]
     want = ref.predict_batch(test.Users[sel], test.Items[sel], n_threads=8)
     assert bits_equal(pred[sel], want)
+
+
+def test_ml20m_shape_config3_and_cyclic_shards():
+    """Full MovieLens-20M shape, the two gaps of the round-1 review: (a) BASELINE.json configs[2] —
+    KNNBaseline over PearsonBaseline similarities with ALS baselines — similarities AND predictions against
+    an oracle slab; (b) the multi-GPU form of the north-star workload — cyclic row shards, 2 and 3 shards on
+    one GPU, peer mirror — equal to the unsharded matrix and predictions."""
+    d = rs.core.synth_ratings(138_493, 26_744, 20_400_000, 0x5EED0003)
+    n_test = 400_000
+    train = rs.NewTrainSet(d.SubSet(np.arange(n_test, d.Length())))
+    test = d.SubSet(np.arange(n_test))
+    n = train.ItemCount
+    # ---- (a) config 3 ----
+    est = rs.NewKNNBaseLine(rs.Parameters({"sim": rs.PearsonBaseline, "userBased": False, "k": 40, "baseline": "als"}))
+    est.Fit(train)
+    r0, r1 = 9000, 9040
+    ots = ob.TrainSet(train.Users, train.Items, train.Ratings)
+    ref = ob.KNN(sim="pearson_baseline", knn_type="baseline", user_based=False, k=40, n_jobs=16,
+                 baseline="als").fit(ots, rows=(r0, r1))
+    assert bits_equal(est._h.sims_rows(r0, r1 - r0), ref.sims(copy=False)[r0:r1])
+    ii = train.convert_items(test.Items)
+    sel = np.where((ii >= r0) & (ii < r1))[0][:400]
+    assert len(sel) > 50
+    assert bits_equal(est.PredictBatch(test.Users[sel], test.Items[sel]),
+                      ref.predict_batch(test.Users[sel], test.Items[sel], n_threads=16))
+    est.Close()
+    del ref
+    # ---- (b) cyclic row shards of the north-star workload ----
+    base = {"sim": rs.Pearson, "userBased": False, "k": 40}
+    full = rs.NewKNNWithMean(rs.Parameters(base))
+    full.Fit(train)
+    want_pred = test.Predict(full)
+    probe = [0, 32, 4992, 13344, 26720]                          # block starts across the matrix
+    want_rows = {b: full._h.sims_rows(b, min(32, n - b)) for b in probe}
+    full.Close()
+    left = train.convert_items(test.Items)
+    for count in (2, 3):
+        shards = []
+        for q in range(count):
+            e = rs.NewKNNWithMean(rs.Parameters(dict(base, shardCount=count, shardIndex=q)))
+            e.Fit(train)
+            shards.append(e)
+        for e in shards:
+            e._h.synchronize()
+        for e in shards:
+            e._h.peer_import_local([x._h for x in shards])
+            e._h.mirror()
+        owner = rs.shard.route_pairs(left, count)
+        got = np.full(n_test, np.nan)
+        for q, e in enumerate(shards):
+            mine = np.flatnonzero(owner == q)
+            got[mine] = e.PredictBatch(test.Users[mine], test.Items[mine])
+            for b in probe:
+                if rs.core.cyclic_owner(b, count) == q:
+                    assert bits_equal(e._h.sims_rows(b, min(32, n - b)), want_rows[b]), (count, q, b)
+        assert bits_equal(got, want_pred), count
+        for e in shards:
+            e.Close()
 
 
 def test_ml20m_shape_properties():
