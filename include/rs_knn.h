@@ -75,8 +75,11 @@ enum rs_sim_path { RS_PATH_AUTO = 0, RS_PATH_TENSOR = 1, RS_PATH_STREAM = 2 };
  *   MATRIX: the dense similarity rows of this handle's shard (what core/knn.go:157,161
  *           keeps; required by Predict).
  *   TOPK  : only the per-row top-`topk` neighbour lists; the N x N matrix is never resident
- *           (BASELINE.json config 4).  The rows are produced slab by slab into a bounded
- *           work buffer and reduced to the lists by selection kernels. */
+ *           (BASELINE.json config 4).  With shard_count >= 1, Cosine / MSD on integer ratings and a
+ *           problem large enough for the CTA-pair tensor kernel, the lists are selected IN the
+ *           tensor kernel's epilogue (threshold compare, candidate append, merge between the waves
+ *           of the tile schedule): no similarity row is ever stored.  Otherwise the rows are produced
+ *           slab by slab into a bounded work buffer and reduced to the lists by selection kernels. */
 enum rs_store { RS_STORE_MATRIX = 0, RS_STORE_TOPK = 1 };
 
 typedef struct rs_knn rs_knn; /* opaque handle; one per estimator copy (core/eval.go:29-30) */

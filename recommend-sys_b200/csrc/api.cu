@@ -369,10 +369,10 @@ int32_t rs_knn_fit_device(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
     } else if (h->p.shard_count >= 1 && path == RS_PATH_TENSOR && rs_tensor_topk_fused(h)) {
         // top-k only, FUSED: the tensor kernel's epilogue tests every similarity against the current k-th
         // best of its two rows and appends the survivors to per-row candidate buffers; the buffers are merged
-        // into the running lists between the bands of the tile schedule (sim_tensor.cu).  No similarity row,
+        // into the running lists between the waves of the tile schedule (sim_tensor.cu).  No similarity row,
         // slab or transpose is ever written: the only N-proportional buffers are the lists (N x k) and the
         // candidate buffers (N x cap).  Every pair is computed once; a multi-GPU Fit deals the tiles of each
-        // band to the shards, every shard ends with PARTIAL lists for all rows (united after an all-gather).
+        // wave to the shards, every shard ends with PARTIAL lists for all rows (united after an all-gather).
         const int32_t k = h->p.topk > 0 ? h->p.topk : h->p.k;
         const int64_t n = n_left;
         h->cand_cap = 1792;                          // band 0 brings at most 2 * (512 + 256) entries per row

@@ -14,6 +14,13 @@ rep, obj, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
+# the report may hold several kernels: each section starts with a "Kernel Name" row; take the first whose
+# name contains the (demangled) kernel name given as the 5th argument, default = the 3rd argument up to "I"
+want = sys.argv[5] if len(sys.argv) > 5 else kname.split("IL")[0]
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+sec = next((i for i in starts if want in rows[i][1]), starts[0] if starts else 0)
+end = next((i for i in starts if i > sec), len(rows))
+rows = rows[sec:end]
 hdr_i = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
 hdr = rows[hdr_i]
 ie, ns, src = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
