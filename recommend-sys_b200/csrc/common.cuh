@@ -75,6 +75,7 @@ struct rs_knn {
     cudaStream_t stream = nullptr;
     cudaStream_t aux_stream = nullptr;   // read-backs of Fit statistics that must not wait for the similarity kernel
     cudaEvent_t ev_in = nullptr;         // the host inputs of rs_knn_fit have been consumed
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // heavy-row kernel on aux_stream beside the column walk
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr;
     rs_knn_profile prof{};
     // pending event pairs whose elapsed time has not been folded into prof yet
@@ -155,6 +156,8 @@ struct rs_knn {
     int64_t *l2r = nullptr;
     int32_t *perm_lr = nullptr, *perm_rl = nullptr, *perm_tmp = nullptr;  // CSR position -> input row (arena, valid until the next Fit)
     int32_t *row_order = nullptr;  // left rows sorted by descending length
+    int32_t *row_heavy = nullptr;  // heavy rows split off that order (sim_stream.cu: sim_stream_heavy_kernel)
+    int32_t n_heavy = 0;
     // int8 planes X^2, M, X of the left matrix, [3][k_pad / 256][n_pad][256] (tensor path)
     int8_t *planes = nullptr;
     int64_t tc_npad = 0, tc_kpad = 0;

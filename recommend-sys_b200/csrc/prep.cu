@@ -505,6 +505,47 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     return RS_OK;
 }
 
+// Heavy rows (sim_stream.cu: sim_stream_heavy_kernel): rows of >= min_len entries are split off the
+// longest-first order and processed by producer / consumer CTAs.  `order`: the rows to process, longest
+// first.  Writes h->row_order (the other rows, same order), h->row_heavy and the counts.
+struct HeavyPred {
+    const int64_t *l_ptr;
+    int64_t min_len;
+    bool negate;
+    __host__ __device__ bool operator()(const int32_t &i) const { return ((l_ptr[i + 1] - l_ptr[i]) >= min_len) != negate; }
+};
+
+static int32_t split_heavy_rows(rs_knn *h, int32_t *order, int64_t n_rows, bool allow) {
+    cudaStream_t st = h->stream;
+    // On ONE GPU the serial walk of a blockbuster row hides under the other rows' work; under cyclic sharding the
+    // per-GPU work shrinks and that walk becomes the critical path (profiles/r02_stream_notes.md).
+    int64_t min_len = h->cyc_R > 1 ? 8192 : -1;
+    if (const char *e = getenv("RS_KNN_HEAVY_MIN")) min_len = atoll(e);      // tests: 0 = every row
+    h->n_heavy = 0;
+    h->row_heavy = nullptr;
+    h->row_order = order;
+    h->n_work_rows = n_rows;
+    if (n_rows <= 0 || !allow || min_len < 0 || h->stream_jc != 256) return RS_OK;
+    int32_t *rest, *d_num;
+    RS_TRY(rs_alloc(h, &h->row_heavy, (size_t)n_rows));
+    RS_TRY(rs_alloc(h, &rest, (size_t)n_rows));
+    RS_TRY(rs_alloc(h, &d_num, 4));
+    HeavyPred yes{h->l_ptr, min_len, false}, no{h->l_ptr, min_len, true};
+    size_t need = 0;
+    RS_CUDA(cub::DeviceSelect::If(nullptr, need, order, h->row_heavy, d_num, (int)n_rows, yes, st));
+    void *tmp;
+    RS_TRY(rs_dev_alloc(h, &tmp, need + 256));
+    RS_CUDA(cub::DeviceSelect::If(tmp, need, order, h->row_heavy, d_num, (int)n_rows, yes, st));
+    RS_CUDA(cub::DeviceSelect::If(tmp, need, order, rest, d_num + 1, (int)n_rows, no, st));
+    int32_t cnt = 0;
+    RS_CUDA(cudaMemcpyAsync(&cnt, d_num, 4, cudaMemcpyDeviceToHost, st));
+    RS_CUDA(cudaStreamSynchronize(st));
+    h->n_heavy = cnt;
+    h->row_order = rest;
+    h->n_work_rows = n_rows - cnt;
+    return RS_OK;
+}
+
 int32_t rs_prep_rt(rs_knn *h) {
     cudaStream_t st = h->stream;
     h->n_chunks = (int32_t)(((int64_t)h->n_left + h->stream_jc - 1) / h->stream_jc);
@@ -555,11 +596,9 @@ int32_t rs_prep_rt(rs_knn *h) {
             void *tmp2;
             RS_TRY(rs_dev_alloc(h, &tmp2, need2 + 256));
             RS_CUDA(cub::DeviceSelect::If(tmp2, need2, sorted, owned, d_num, (int)h->n_left, pred, st));
-            h->row_order = owned;
-            h->n_work_rows = h->rows_local;
+            RS_TRY(split_heavy_rows(h, owned, h->rows_local, true));
         } else {
-            h->row_order = sorted;
-            h->n_work_rows = rows;
+            RS_TRY(split_heavy_rows(h, sorted, rows, h->row_begin == 0 && h->row_end == h->n_left));
         }
     }
     RS_CUDA(cudaGetLastError());

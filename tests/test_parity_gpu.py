@@ -87,6 +87,8 @@ def test_sims_bit_exact_both_triangles(ml100k, sim, user_based, tri, monkeypatch
 @pytest.mark.parametrize("count", [2, 3])
 def test_cyclic_row_shards_equal_full(ml100k, count, tri, monkeypatch):
     monkeypatch.setenv("RS_KNN_STREAM_TRI", tri)
+    monkeypatch.setenv("RS_KNN_STREAM_JC", "256")
+    monkeypatch.setenv("RS_KNN_HEAVY_MIN", "200")      # the longer rows of every shard take the heavy-row kernel
     u, i, r = split(ml100k["u1_base"])
     ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
     base = {"sim": rs.Pearson, "userBased": False, "k": 40}
@@ -201,6 +203,23 @@ def test_concurrent_predict_on_one_handle(ml100k):
     [t.start() for t in ths]
     [t.join() for t in ths]
     assert bits_equal(np.concatenate(out), want)
+
+
+# ---- heavy rows of the exact sparse Fit: producer / consumer CTAs (seven warps stage the entries' runs with
+# cp.async, one applies them in order) instead of one warp per (row, chunk): every row (min 0) and a mix
+# (rows of >= 150 entries), both triangles, all similarities ----
+@pytest.mark.parametrize("heavy_min", ["0", "150"])
+@pytest.mark.parametrize("tri", ["upper", "lower"])
+@pytest.mark.parametrize("sim", ["cosine", "msd", "pearson"])
+def test_heavy_row_mode_bit_exact(ml100k, sim, tri, heavy_min, monkeypatch):
+    monkeypatch.setenv("RS_KNN_STREAM_TRI", tri)
+    monkeypatch.setenv("RS_KNN_STREAM_JC", "256")       # the heavy kernel shares the 256-column chunk pointers
+    monkeypatch.setenv("RS_KNN_HEAVY_MIN", heavy_min)
+    for user_based in (True, False):
+        est, ref = fit_pair(ml100k["u2_base"], sim, "basic", user_based, extra={"simPath": "stream"})
+        got, want = est.Sims, ref.sims()
+        assert np.isnan(np.diag(got)).all()
+        assert bits_equal(got, want)
 
 
 # ---- arbitrary float64 ratings (continuous values, thousands of distinct ones): the stream path
