@@ -312,9 +312,10 @@ def run_ours(args, rank, world, local_rank):
     if shard and n_test:
         mine = (t_left >= rb) & (t_left < re)
     if cyc:
-        owner = route_pairs(t_left, world)
-        counts = np.bincount(owner, minlength=world).tolist()
-        mine = owner == rank
+        # every rank gets the full test set, answers the pairs whose left row it owns (+0.0 elsewhere) and an
+        # int64 SUM all-reduce of the bit patterns assembles the predictions: no routing, no re-ordering
+        own_cyc = route_pairs(t_left, world) == rank
+        n_mine_cyc = int(own_cyc.sum())
     if mine is not None:
         t_left, t_right = t_left[mine], t_right[mine]
     n_pred = len(t_left)
@@ -359,10 +360,12 @@ def run_ours(args, rank, world, local_rank):
                      d_rb.data_ptr() if d_rb is not None else 0, global_bias)
         if cyc:
             attach_peers_and_mirror(h)          # the exchange step: other triangle over NVLink
+        if cyc:
+            h.predict_batch_sharded_device(d_tl.data_ptr(), d_tr.data_ptr(), n_pred, d_out.data_ptr())
+            dist.all_reduce(d_out.view(torch.int64), op=dist.ReduceOp.SUM)
+            return d_out
         if n_pred:
             h.predict_batch_device(d_tl.data_ptr(), d_tr.data_ptr(), n_pred, d_out.data_ptr())
-        if cyc:
-            return allgather_predictions(d_out[:n_pred], counts)
         if shard:
             h.topk_device(k, d_tk_i.data_ptr(), d_tk_s.data_ptr())
             allgather_topk(d_tk_i, d_tk_s, n_left, k)
@@ -463,7 +466,7 @@ def run_ours(args, rank, world, local_rank):
         pairs_rank = pairs_full / (world if multi else 1)        # every pair once across the ranks
     red = torch.tensor([total_ms, e2e_s, prof["sim_kernel_ms"], prof["predict_kernel_ms"], prof["prep_ms"]],
                        dtype=torch.float64, device=dev)
-    units = torch.tensor([pairs_rank, float(n_pred)], dtype=torch.float64, device=dev)
+    units = torch.tensor([pairs_rank, float(n_mine_cyc if cyc else n_pred)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(units, op=dist.ReduceOp.SUM)
@@ -525,15 +528,17 @@ def run_ours(args, rank, world, local_rank):
     roof_pred = None
     if n_pred:
         deg_right = np.bincount(right, minlength=n_right)
-        cand = float(deg_right[t_right[t_right >= 0]].sum())
+        t_right_own = t_right[own_cyc] if cyc else t_right          # the pairs THIS rank's kernel answered
+        cand = float(deg_right[t_right_own[t_right_own >= 0]].sum())
         per_cand = 13 + (8 if knn_type != "basic" else 0)
-        pbytes = cand * per_cand + n_pred * 8.0
+        n_answered = n_mine_cyc if cyc else n_pred
+        pbytes = cand * per_cand + n_answered * 8.0
         pms = pred_ms / args.steps
         roof_pred = {"bound": "hbm", "achieved": pbytes / (pms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "frac": pbytes / (pms / 1e3) / 1e9 / hbm_peak, "traffic": None,
                      "kernel": "predict_select_kernel", "ms_per_launch": pms,
                      "bytes_per_candidate": per_cand,
-                     "candidates_per_prediction": cand / max(1, n_pred)}
+                     "candidates_per_prediction": cand / max(1, n_answered)}
     prof_file = ROOT / "profiles" / "traffic.json"
     if prof_file.exists():
         try:
@@ -550,7 +555,8 @@ def run_ours(args, rank, world, local_rank):
                    "one fold per GPU, no collective" if args.folds else
                    "symmetric slabs dealt in snake order + NCCL all-gather and union of partial neighbour lists" if sym else
                    "cyclic row shards: every pair once, other triangle pulled from peer memory over NVLink "
-                   "(CUDA IPC), test pairs routed to the owner of their left row, NCCL all-gather of predictions" if cyc else
+                   "(CUDA IPC), every shard answers the test pairs of its rows, NCCL all-reduce (int64 sum of the bit "
+                   "patterns) assembles the predictions" if cyc else
                    "contiguous row shards (full rows) + NCCL all-gather of neighbour lists")
     limiter = None
     if multi:
@@ -572,8 +578,8 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": parallelism},
         "clocks": clock_info,
         "e2e": {"value": pairs_all / e2e_s, "unit": "pairs/s", "ms_per_step": e2e_s * 1e3,
-                "h2d_bytes_per_step": int(len(left) * 16 / (world if cyc else 1) + (n_pred if cyc else test.Length()) * 8),
-                "d2h_bytes_per_step": int((test.Length() if cyc else n_pred) * 8 + (n_left * k * 12 if sym else 0)),
+                "h2d_bytes_per_step": int(len(left) * 16 / (world if cyc else 1) + test.Length() * 8),
+                "d2h_bytes_per_step": int(n_pred * 8 + (n_left * k * 12 if sym else 0)),
                 "predictions_per_sec": preds_all / e2e_s, "steps": e2e_steps, "statistic": "median step",
                 "ms_min": min(e2e_times) * 1e3, "ms_max": max(e2e_times) * 1e3},
         "gpu_launches": int(prof["total_launches"]),

@@ -244,6 +244,12 @@ int32_t rs_knn_set_k(rs_knn *h, int32_t k, int32_t min_k);
  *                         after every peer's Fit has finished (rs_knn_synchronize + a barrier) and
  *                         keeps the peers' matrices alive until it has finished.
  * Until rs_knn_mirror has run, Predict / sims_rows / topk on a cyclic shard fail with RS_ERR_INVALID. */
+/* Predict on a cyclic row shard for an all-reduce: the FULL test set goes to every shard; a pair whose left row
+ * another shard owns yields +0.0 (all bits zero) instead of NaN, and a cold-start pair (left = -1) is answered by
+ * shard (index % shard_count) only — so an integer SUM all-reduce of the 64-bit patterns over the shards assembles
+ * the complete prediction vector, bit for bit, with no routing and no re-ordering on the host. */
+int32_t rs_knn_predict_batch_sharded_device(rs_knn *h, const int32_t *d_left, const int32_t *d_right, int64_t n,
+                                            double *d_out);
 int32_t rs_knn_peer_export(rs_knn *h, unsigned char *handle64, int64_t *offset);
 int32_t rs_knn_peer_import(rs_knn *h, int32_t n_peers, const unsigned char *handles, const int64_t *offsets);
 int32_t rs_knn_peer_import_local(rs_knn *h, int32_t n_peers, rs_knn *const *peers);

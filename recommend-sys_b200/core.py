@@ -67,7 +67,7 @@ ABI_SYMBOLS = [
     "rs_knn_topk_device", "rs_knn_cosums", "rs_knn_means", "rs_knn_stddevs", "rs_knn_profile_get",
     "rs_knn_profile_reset", "rs_knn_synchronize", "rs_knn_trim_cache", "rs_baseline_als",
     "rs_knn_topk_union_device", "rs_knn_set_k", "rs_knn_peer_export", "rs_knn_peer_import",
-    "rs_knn_peer_import_local", "rs_knn_mirror",
+    "rs_knn_peer_import_local", "rs_knn_mirror", "rs_knn_predict_batch_sharded_device",
 ]
 
 _knn_lib = None
@@ -115,6 +115,7 @@ def knn_lib():
     L.rs_knn_peer_import.argtypes = [vp, i32, vp, vp]
     L.rs_knn_peer_import_local.argtypes = [vp, i32, vp]
     L.rs_knn_mirror.argtypes = [vp]
+    L.rs_knn_predict_batch_sharded_device.argtypes = [vp, vp, vp, i64, vp]
     _knn_lib = L
     return L
 
@@ -145,6 +146,8 @@ def host_lib():
     L.rs_host_load_ratings.restype = C.c_int64
     L.rs_host_load_ratings.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int64]
+    L.rs_host_route_pairs.restype = None
+    L.rs_host_route_pairs.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     L.rs_host_convert_dense.restype = None
     L.rs_host_convert_dense.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     _host_lib = L
@@ -508,6 +511,16 @@ def cyclic_owner(ids, count):
     return (np.asarray(ids) // CYC_B) % count
 
 
+def route_pairs_grouped(left_inner, count):
+    """(order, counts): the test pairs grouped by the cyclic shard that owns their left row (stable; unknown
+    left ids round-robin) — one counting-sort pass in librs_host.so."""
+    left_inner = np.ascontiguousarray(left_inner, dtype=np.int32)
+    order = np.empty(len(left_inner), dtype=np.int64)
+    counts = np.zeros(count, dtype=np.int64)
+    host_lib().rs_host_route_pairs(_ptr(left_inner), len(left_inner), count, CYC_B, _ptr(order), _ptr(counts))
+    return order, counts.tolist()
+
+
 # --------------------------------------------------------------------------------------------
 # device handle
 # --------------------------------------------------------------------------------------------
@@ -574,6 +587,9 @@ class _Handle:
 
     def predict_batch_device(self, d_left, d_right, n, d_out):
         _check(knn_lib().rs_knn_predict_batch_device(self.h, d_left, d_right, n, d_out))
+
+    def predict_batch_sharded_device(self, d_left, d_right, n, d_out):
+        _check(knn_lib().rs_knn_predict_batch_sharded_device(self.h, d_left, d_right, n, d_out))
 
     def predict_neighbors(self, left, right, cap=1024):
         ids = np.empty(cap, dtype=np.int32)

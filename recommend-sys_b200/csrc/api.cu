@@ -614,6 +614,27 @@ int32_t rs_knn_predict_batch_device(rs_knn *h, const int32_t *d_left, const int3
     return RS_OK;
 }
 
+int32_t rs_knn_predict_batch_sharded_device(rs_knn *h, const int32_t *d_left, const int32_t *d_right, int64_t n,
+                                            double *d_out) {
+    RS_ENTER(h);
+    RS_TRY(require_matrix(h, "rs_knn_predict_batch_sharded"));
+    if (h->cyc_R < 2) {
+        rs_set_error("rs_knn_predict_batch_sharded: the handle is not a cyclic row shard");
+        return RS_ERR_INVALID;
+    }
+    if (n == 0) return RS_OK;
+    if (!d_left || !d_right || !d_out || n < 0) {
+        rs_set_error("rs_knn_predict_batch_sharded: null argument");
+        return RS_ERR_INVALID;
+    }
+    if (h->pred_pending) RS_TRY(fold_profile(h));
+    RS_CUDA(cudaEventRecord(h->ev_d, h->stream));
+    RS_TRY(rs_predict_launch(h, d_left, d_right, n, d_out, nullptr, nullptr, nullptr, 0, 1));
+    RS_CUDA(cudaEventRecord(h->ev_e, h->stream));
+    h->pred_pending = true;
+    return RS_OK;
+}
+
 int32_t rs_knn_predict_batch(rs_knn *h, const int32_t *left, const int32_t *right, int64_t n, double *out) {
     RS_ENTER(h);
     RS_TRY(require_matrix(h, "rs_knn_predict_batch"));

@@ -45,13 +45,14 @@ int32_t rs_cached_malloc(int device, void **out, size_t bytes, size_t *got) {
     return RS_OK;
 }
 
-// Parked bytes are capped (RS_KNN_CACHE_BYTES, default 16 GiB per process): beyond the cap the
-// oldest parked blocks go back to the driver, so a co-resident allocator (torch, another library)
-// is not starved by arenas of estimators that no longer exist.
+// Parked bytes are capped (RS_KNN_CACHE_BYTES, default 96 GiB per process — one Netflix-shape arena is
+// 30 GB, and a 16 GiB cap made every e2e step re-allocate it: 499 -> 1050 ms): beyond the cap the oldest
+// parked blocks go back to the driver, so a co-resident allocator (torch, another library) is not
+// starved forever by arenas of estimators that no longer exist.
 static size_t cache_cap() {
     static size_t cap = [] {
         const char *e = getenv("RS_KNN_CACHE_BYTES");
-        return e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)16 << 30);
+        return e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)96 << 30);
     }();
     return cap;
 }

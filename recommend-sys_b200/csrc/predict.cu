@@ -52,6 +52,8 @@ struct PredArgs {
     double *nb_sims;
     int32_t *nb_count;
     int32_t nb_cap;
+    int32_t foreign_zero;   // cyclic shards: pairs of another shard's rows yield +0.0 (not NaN) and a cold-start pair is answered by
+                            // ONE shard, so that an integer all-reduce (sum) of the bit patterns assembles the full vector
     uint64_t *gstage;       // per-warp spill of the staged keys beyond the shared-memory capacity
     int64_t gcap;           // keys per warp in gstage
 };
@@ -171,12 +173,15 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
         const int64_t p = a.perm ? (int64_t)a.perm[w] : w;
         const int32_t l = a.left[p], r = a.right[p];
         if (a.nb_count && lane == 0) *a.nb_count = 0;
-        if (l < 0 || r < 0 || r >= a.n_right) {            // core/knn.go:89-91 (newID)
-            if (lane == 0) a.out[p] = a.global_mean;
-            continue;
+        if (l < a.row_begin || l >= a.row_end || (a.cyc_R > 1 && l >= 0 && !rs_cyc_owns(l, a.cyc_R, a.cyc_r))) {
+            if (l >= 0) {                                   // a known row of another shard
+                if (lane == 0) a.out[p] = a.foreign_zero ? 0.0 : nan_v;
+                continue;
+            }
         }
-        if (l < a.row_begin || l >= a.row_end || (a.cyc_R > 1 && !rs_cyc_owns(l, a.cyc_R, a.cyc_r))) {   // not in this shard
-            if (lane == 0) a.out[p] = nan_v;
+        if (l < 0 || r < 0 || r >= a.n_right) {            // core/knn.go:89-91 (newID)
+            const bool mine = !(a.foreign_zero && a.cyc_R > 1 && l < 0) || (int)(p % a.cyc_R) == a.cyc_r;
+            if (lane == 0) a.out[p] = mine ? a.global_mean : 0.0;
             continue;
         }
         const double *row = a.sims + (a.cyc_R > 1 ? rs_cyc_local(l, a.cyc_R) : l - a.row_begin) * a.ld_s;
@@ -896,7 +901,7 @@ static int32_t launch_select(const PredArgs &a, unsigned blocks, size_t smem, in
 }
 
 int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_right, int64_t n, double *d_out,
-                          int32_t *d_nb_ids, double *d_nb_sims, int32_t *d_nb_count, int32_t nb_cap) {
+                          int32_t *d_nb_ids, double *d_nb_sims, int32_t *d_nb_count, int32_t nb_cap, int32_t foreign_zero) {
     if (n <= 0) return RS_OK;
     if (h->p.k > PRED_CAP / 2) {
         rs_set_error("k=%d exceeds the %d neighbours the predict kernel supports", h->p.k, PRED_CAP / 2);
@@ -911,6 +916,7 @@ int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
     a.r_ptr = h->r_ptr; a.r_col = h->r_col; a.r_val = h->r_val;
     a.sims = h->sims; a.ld_s = h->ld_s; a.row_begin = h->row_begin; a.row_end = h->row_end;
     a.cyc_R = h->cyc_R; a.cyc_r = h->cyc_r;
+    a.foreign_zero = foreign_zero;
     a.means = h->means; a.stddevs = h->stddevs; a.bias = h->left_bias;
     a.global_mean = h->global_mean; a.n_right = h->n_right;
     a.k = h->p.k; a.min_k = h->p.min_k; a.knn_type = h->p.knn_type;

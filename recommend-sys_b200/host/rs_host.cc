@@ -165,6 +165,32 @@ void rs_host_convert_dense(const int32_t *table, int64_t n_table, const int64_t 
     }
 }
 
+// Routing of test pairs to the cyclic row shards of a multi-GPU Fit (csrc/common.cuh RS_CYC_B): the pair goes
+// to the shard that owns its left row, block b of `block` rows -> shard b % world; pairs with an unknown left id
+// (cold start, answered with GlobalMean by any shard) are spread round-robin.  One counting-sort pass:
+// order[] = pair indices grouped by shard (stable), counts[world].  4 M pairs: ~10 ms (numpy: 150 ms).
+void rs_host_route_pairs(const int32_t *left_inner, int64_t n, int32_t world, int32_t block, int64_t *order,
+                         int64_t *counts) {
+    // owner of every block of rows, by table (two integer divisions per pair cost more than the rest of the pass)
+    int32_t max_left = -1;
+    for (int64_t i = 0; i < n; i++) max_left = left_inner[i] > max_left ? left_inner[i] : max_left;
+    std::vector<uint8_t> own_of_row((size_t)(max_left + 1) + 1);
+    for (int32_t l = 0; l <= max_left; l++) own_of_row[(size_t)l] = (uint8_t)((l / block) % world);
+    std::vector<uint8_t> own((size_t)n);
+    std::vector<int64_t> off((size_t)world + 1, 0);
+    int32_t cold = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const int32_t l = left_inner[i];
+        uint8_t o;
+        if (l < 0) { o = (uint8_t)cold; cold = cold + 1 == world ? 0 : cold + 1; }
+        else o = own_of_row[(size_t)l];
+        own[(size_t)i] = o;
+        off[(size_t)o + 1]++;
+    }
+    for (int32_t r = 0; r < world; r++) { counts[r] = off[(size_t)r + 1]; off[(size_t)r + 1] += off[r]; }
+    for (int64_t i = 0; i < n; i++) order[off[own[(size_t)i]]++] = i;
+}
+
 // ---- on-disk neighbour lists and a rating loader that keeps half-stars ----
 // File format (little endian):  magic "RSKNNL01" | int64 n_rows | int32 k | int32 reserved |
 // uint64 checksum (FNV-1a 64 of the payload) | int32 idx[n_rows*k] | float64 sim[n_rows*k].

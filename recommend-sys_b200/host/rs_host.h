@@ -25,6 +25,10 @@ void rs_host_baseline_sgd(const int32_t *inner_user, const int32_t *inner_item, 
 
 /* Batch ConvertUserID / ConvertItemID (core/data.go:157-183) through a dense raw -> inner table
  * (table[raw] = inner id or -1; raw ids outside [0, n_table) are new ids = -1). */
+/* Routing of test pairs to the cyclic row shards of a multi-GPU Fit: order[] = pair indices grouped by owner
+ * shard (stable), counts[world]; owner = (left / block) % world, unknown left ids round-robin. */
+void rs_host_route_pairs(const int32_t *left_inner, int64_t n, int32_t world, int32_t block, int64_t *order,
+                         int64_t *counts);
 /* SURVEY.md §8 f-4.  Neighbour lists (int32 idx, float64 sim)[n_rows][k] on disk, checksummed; replaces
  * gob Save/Load (core/dump.go:11-36) for the one artefact of a top-k-only Fit.  load with idx == NULL
  * returns the header only.  0 ok, -1 io error, -2 not a neighbour-list file / checksum mismatch. */

@@ -209,25 +209,20 @@ class ShardedKNN:
         iu = k.Data.convert_users(userIDs)
         ii = k.Data.convert_items(itemIDs)
         left, right = (iu, ii) if k._userBased else (ii, iu)
-        owner = route_pairs(left, self.world)
-        parts = [np.flatnonzero(owner == r) for r in range(self.world)]     # (a stable argsort of 4 M keys costs 150 ms)
-        counts = [len(x) for x in parts]
-        mine = parts[self.rank]
+        import torch.distributed as dist
+
+        # every rank gets the FULL test set (32 MB at 4 M pairs — cheaper than routing it on the host); a shard
+        # answers the pairs whose left row it owns and leaves +0.0 elsewhere; an int64 SUM all-reduce of the bit
+        # patterns over NVLink assembles the vector exactly (x + 0 + ... + 0 in integer arithmetic)
         dev = torch.device("cuda", torch.cuda.current_device())
-        d_l = torch.from_numpy(np.ascontiguousarray(left[mine], dtype=np.int32)).to(dev)
-        d_r = torch.from_numpy(np.ascontiguousarray(right[mine], dtype=np.int32)).to(dev)
-        d_o = torch.empty(max(1, len(mine)), dtype=torch.float64, device=dev)
+        d_l = torch.from_numpy(np.ascontiguousarray(left, dtype=np.int32)).to(dev, non_blocking=True)
+        d_r = torch.from_numpy(np.ascontiguousarray(right, dtype=np.int32)).to(dev, non_blocking=True)
+        d_o = torch.empty(max(1, len(left)), dtype=torch.float64, device=dev)
         self._finish_fit()
-        if len(mine):
-            k._h.predict_batch_device(d_l.data_ptr(), d_r.data_ptr(), len(mine), d_o.data_ptr())
-        allp = allgather_predictions(d_o[: len(mine)], counts, group=self.group)
-        out = np.empty(len(left), dtype=np.float64)
-        allp = allp.cpu().numpy()
-        off = 0
-        for r in range(self.world):
-            out[parts[r]] = allp[off: off + counts[r]]
-            off += counts[r]
-        return out
+        if len(left):
+            k._h.predict_batch_sharded_device(d_l.data_ptr(), d_r.data_ptr(), len(left), d_o.data_ptr())
+            dist.all_reduce(d_o.view(torch.int64), op=dist.ReduceOp.SUM, group=self.group)
+        return d_o[: len(left)].cpu().numpy()
 
     def Predict(self, userID, itemID):
         import numpy as np

@@ -121,6 +121,22 @@ def test_cyclic_row_shards_equal_full(ml100k, count, tri, monkeypatch):
         assert np.isnan(est.PredictBatch(tu[other], ti[other])).all()     # rows of another shard: NaN
     assert bits_equal(got_pred, want_pred)
     assert sorted(np.concatenate([e._h.owned_rows() for e in shards]).tolist()) == list(range(want.shape[0]))
+    # the all-reduce form: every shard gets the FULL test set (plus cold-start pairs), answers its own pairs and
+    # leaves +0.0 elsewhere; the integer sum of the bit patterns over the shards is the complete vector
+    import torch
+
+    tu2 = np.concatenate([tu, [10 ** 9, 10 ** 9 + 1, 10 ** 9 + 2]])       # unknown users and items
+    ti2 = np.concatenate([ti, [int(ti[0]), 10 ** 9, int(ti[1])]])
+    want2 = full.PredictBatch(tu2, ti2)
+    d_l = torch.from_numpy(ts.convert_items(ti2).astype(np.int32)).cuda()
+    d_r = torch.from_numpy(ts.convert_users(tu2).astype(np.int32)).cuda()
+    acc = np.zeros(len(tu2), dtype=np.int64)
+    for est in shards:
+        d_o = torch.empty(len(tu2), dtype=torch.float64, device="cuda")
+        est._h.predict_batch_sharded_device(d_l.data_ptr(), d_r.data_ptr(), len(tu2), d_o.data_ptr())
+        est._h.synchronize()
+        acc += d_o.cpu().numpy().view(np.int64)
+    assert bits_equal(acc.view(np.float64), want2)
     for est in shards:
         est.Close()
 
