@@ -196,7 +196,10 @@ def cpu_sample_rows(n, nnz, budget_merge_steps):
     rows = int(budget_merge_steps / (2.0 * nnz))
     if rows >= n:
         return n
-    return max(64, rows // 64 * 64)
+    # at least 24 rows per host thread: the reference splits the rows statically over nJobs threads
+    # (core/knn.go:192-199) and a slab of a few rows per thread measures the imbalance, not the algorithm
+    floor = min(n, 24 * (os.cpu_count() or 1))
+    return max(floor, rows // 64 * 64)
 
 
 def run_reference(args, rank, world):

@@ -105,7 +105,8 @@ typedef struct rs_knn_params {
                           /*   computes ONE triangle of the rows it owns (every pair once across the       */
                           /*   shards, exact sparse path) and the other triangle is pulled from the peers'  */
                           /*   matrices over NVLink by rs_knn_mirror (after rs_knn_peer_import).  Predict   */
-                          /*   then serves the test pairs whose left row the handle owns.                  */
+                          /*   then serves the test pairs whose left row the handle owns (NaN for others;  */
+                          /*   rs_knn_predict_batch_sharded_device: +0.0 for others, for an all-reduce).   */
     int32_t shard_count;  /* RS_STORE_TOPK.  0 (default): the handle computes the full rows of             */
     int32_t shard_index;  /*   [row_begin,row_end) and keeps their lists.  >= 1: SYMMETRIC SLABS — the */
                           /*   left rows are cut into slabs dealt to the shards in snake order          */

@@ -52,6 +52,7 @@ struct PredArgs {
     double *nb_sims;
     int32_t *nb_count;
     int32_t nb_cap;
+    const long long *n_dev; // when set: only the first *n_dev positions of `perm` are processed (the shard's own pairs)
     int32_t foreign_zero;   // cyclic shards: pairs of another shard's rows yield +0.0 (not NaN) and a cold-start pair is answered by
                             // ONE shard, so that an integer all-reduce (sum) of the bit patterns assembles the full vector
     uint64_t *gstage;       // per-warp spill of the staged keys beyond the shared-memory capacity
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
     uint64_t *gbuf = a.gstage + ((size_t)blockIdx.x * SEL_WARPS + warp) * (size_t)a.gcap - scap;
     const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const int64_t n_eff = a.n_dev ? (int64_t)*a.n_dev : a.n;
 
     // Positions are handed out in order from one counter, so the predictions in flight are always
     // a contiguous window of the (row-grouped) order however unevenly long they take — with a
@@ -167,8 +169,8 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) predict_select_kernel(PredArgs
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(a.work, (unsigned long long)PRED_GRAB);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if ((int64_t)base >= a.n) break;
-        const int64_t w_end = (int64_t)base + PRED_GRAB < a.n ? (int64_t)base + PRED_GRAB : a.n;
+        if ((int64_t)base >= n_eff) break;
+        const int64_t w_end = (int64_t)base + PRED_GRAB < n_eff ? (int64_t)base + PRED_GRAB : n_eff;
     for (int64_t w = (int64_t)base; w < w_end; w++) {
         const int64_t p = a.perm ? (int64_t)a.perm[w] : w;
         const int32_t l = a.left[p], r = a.right[p];
@@ -887,6 +889,23 @@ __global__ void __launch_bounds__(SLOPE_WARPS * 32) slope_predict_kernel(
 
 }  // namespace
 
+// Sharded Predict: sort key that puts the shard's OWN pairs first, grouped by left row; foreign pairs (answered with
+// +0.0 by a memset) get the largest key and are never visited.  own = the left row belongs to the shard, or the pair is
+// a cold start (left = -1: GlobalMean) dealt to this shard by position.
+__global__ void own_key_kernel(const int32_t *__restrict__ left, int64_t n, int32_t count, int32_t index,
+                               int32_t *__restrict__ key, int32_t *__restrict__ iota, long long *__restrict__ n_own) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool own = false;
+    if (i < n) {
+        const int32_t l = left[i];
+        own = l < 0 ? (int)(i % count) == index : rs_cyc_owns(l, count, index);
+        key[i] = own ? l + 1 : 0x7fffffff;
+        iota[i] = (int32_t)i;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, own);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(reinterpret_cast<unsigned long long *>(n_own), (unsigned long long)__popc(m));
+}
+
 __global__ void iota_kernel(int32_t *out, int32_t n) {
     const int32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x < n) out[x] = x;
@@ -927,7 +946,31 @@ int32_t rs_predict_launch(rs_knn *h, const int32_t *d_left, const int32_t *d_rig
     // (MovieLens-20M item shape: 150 test pairs per row, 5.7 GB matrix).  Stable radix sort of
     // (left id, index) — CUB, plumbing — and the kernel walks the permutation.
     a.perm = nullptr;
-    if (n >= 65536 && (size_t)h->rows_local * (size_t)h->ld_s * 8 > ((size_t)64 << 20) &&
+    a.n_dev = nullptr;
+    if (foreign_zero && h->cyc_R > 1 && n >= 4096) {
+        // sharded Predict over the FULL test set: the foreign pairs are answered by a memset (+0.0) and the kernel
+        // only visits the shard's own pairs, found — and grouped by left row — by ONE radix sort whose key puts
+        // foreign pairs last (walking all positions to skip 7 of 8 cost 2.7 ms of a 4.8 ms launch at 8 shards)
+        void *keys_in, *keys_out, *iota, *perm, *tmp, *cnt;
+        RS_TRY(rs_scratch_get(h, 18, (size_t)n * 4, &keys_in));
+        RS_TRY(rs_scratch_get(h, 12, (size_t)n * 4, &keys_out));
+        RS_TRY(rs_scratch_get(h, 13, (size_t)n * 4, &iota));
+        RS_TRY(rs_scratch_get(h, 14, (size_t)n * 4, &perm));
+        RS_TRY(rs_scratch_get(h, 19, 8, &cnt));
+        size_t need = 0;
+        RS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, (int32_t *)keys_in, (int32_t *)keys_out, (int32_t *)iota,
+                                                (int32_t *)perm, (int)n, 0, 31, h->stream));
+        RS_TRY(rs_scratch_get(h, 15, need + 256, &tmp));
+        RS_CUDA(cudaMemsetAsync(cnt, 0, 8, h->stream));
+        RS_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n * 8, h->stream));
+        own_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_left, n, h->cyc_R, h->cyc_r, (int32_t *)keys_in,
+                                                                            (int32_t *)iota, (long long *)cnt);
+        RS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, need, (int32_t *)keys_in, (int32_t *)keys_out, (int32_t *)iota,
+                                                (int32_t *)perm, (int)n, 0, 31, h->stream));
+        a.perm = (const int32_t *)perm;
+        a.n_dev = (const long long *)cnt;
+        h->prof.total_launches += 1;
+    } else if (n >= 65536 && (size_t)h->rows_local * (size_t)h->ld_s * 8 > ((size_t)64 << 20) &&
         !getenv("RS_KNN_PRED_NOSORT")) {
         void *keys_out, *iota, *perm, *tmp;
         RS_TRY(rs_scratch_get(h, 12, (size_t)n * 4, &keys_out));

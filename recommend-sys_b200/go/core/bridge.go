@@ -183,6 +183,14 @@ func (d *deviceKNN) peerImportLocal(peers []*deviceKNN) {
 
 func (d *deviceKNN) mirror() { check(C.rs_knn_mirror(d.h)) }
 
+// predictBatchShardedDevice: every shard gets the FULL test set (device pointers), answers the pairs whose left
+// row it owns and leaves +0.0 elsewhere (a cold-start pair is answered by shard index % shardCount); an int64 SUM
+// all-reduce of the bit patterns over the shards (NCCL) then holds the complete prediction vector on every GPU.
+func (d *deviceKNN) predictBatchShardedDevice(dLeft, dRight unsafe.Pointer, n int, dOut unsafe.Pointer) {
+	check(C.rs_knn_predict_batch_sharded_device(d.h, (*C.int32_t)(dLeft), (*C.int32_t)(dRight), C.int64_t(n),
+		(*C.double)(dOut)))
+}
+
 func (d *deviceKNN) predictBatch(left, right []int32) []float64 {
 	out := make([]float64, len(left))
 	check(C.rs_knn_predict_batch(d.h, i32(left), i32(right), C.int64_t(len(left)), f64(out)))

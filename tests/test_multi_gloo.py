@@ -205,6 +205,14 @@ def _worker_cyclic(rank, world, port, out_dir):
     out[order] = gathered
     want = full.predict_batch(te[:, 0], te[:, 1])
     assert np.array_equal(np.nan_to_num(out), np.nan_to_num(want))
+    # the all-reduce form (ShardedKNN.PredictBatch): own pairs answered, +0.0 elsewhere, int64 sum of the bit patterns
+    part = np.zeros(len(te))
+    part[sel] = pred
+    acc = torch.from_numpy(part.view(np.int64).copy())
+    dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    got = acc.numpy().view(np.float64)
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~np.isnan(got)].view(np.int64),
+                                                                             want[~np.isnan(want)].view(np.int64))
     if rank == 0:
         (Path(out_dir) / "ok_cyc").write_text("ok")
     dist.barrier()
