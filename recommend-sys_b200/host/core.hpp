@@ -221,7 +221,11 @@ struct KNN : Estimator {
         p.row_begin = Params.GetInt("rowBegin", 0);
         p.row_end = Params.GetInt("rowEnd", 0);
         p.shrinkage = Params.GetFloat64("shrinkage", 0.0);
+        p.shard_count = Params.GetInt("shardCount", 0);      // one estimator per GPU: see rs_knn.h
+        p.shard_index = Params.GetInt("shardIndex", 0);
         rs_check(rs_knn_create(&p, &h_));
+        k_ = p.k;
+        minK_ = p.min_k;
         rs_check(rs_knn_fit(h_, left.data(), right.data(), t.Ratings.data(), (int64_t)t.Length(), nLeft_, nRight,
                             t.GlobalMean, lb, rb, gb));
         if (KNNType == "centered" || KNNType == "zscore") { Means.resize(nLeft_); rs_check(rs_knn_means(h_, Means.data())); }
@@ -235,6 +239,9 @@ struct KNN : Estimator {
             l[j] = userBased_ ? iu : ii;
             r[j] = userBased_ ? ii : iu;
         }
+        // core/knn.go:80-81 reads k / mink in Predict: SetParams after Fit takes effect here
+        const int k = Params.GetInt("k", 40), minK = Params.GetInt("mink", 1);
+        if (k != k_ || minK != minK_) { rs_check(rs_knn_set_k(h_, k, minK)); k_ = k; minK_ = minK; }
         std::vector<double> out(users.size());
         rs_check(rs_knn_predict_batch(h_, l.data(), r.data(), (int64_t)l.size(), out.data()));
         return out;
@@ -252,6 +259,7 @@ struct KNN : Estimator {
 
   private:
     rs_knn *h_ = nullptr;
+    int k_ = 40, minK_ = 1;   // what the handle currently holds
     bool userBased_ = true;
     int nLeft_ = 0;
 };
