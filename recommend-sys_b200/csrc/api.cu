@@ -55,6 +55,14 @@ void free_fit_state(rs_knn *h) {
     h->row_order = nullptr;
     h->row_heavy = nullptr;
     h->n_heavy = 0;
+    h->n_pop = h->pop_ld = 0;
+    h->pop_idx = h->pop_items = nullptr;
+    h->pop_dense = nullptr;
+    h->w_ptr = nullptr;
+    h->w_col = nullptr;
+    h->w_dev = nullptr;
+    h->row_all = nullptr;
+    h->n_all_rows = 0;
     h->planes = nullptr;
     h->row_cnt = h->row_sum = nullptr;
     h->sims = nullptr;

@@ -158,6 +158,20 @@ struct rs_knn {
     int32_t *row_order = nullptr;  // left rows sorted by descending length
     int32_t *row_heavy = nullptr;  // heavy rows split off that order (sim_stream.cu: sim_stream_heavy_kernel)
     int32_t n_heavy = 0;
+    // popular columns (sim_stream.cu: sim_pop_kernel): the n_pop longest rows, longest first.  Their ratings are
+    // taken out of the right CSR the column walk reads (walk CSR: w_ptr / w_col / w_dev, `cp` and `l2r` refer to
+    // it) and kept as a dense table pop_dense[n_right][pop_ld] instead (one byte per cell when every rating is a
+    // small integer, else the b-side double; 0 / NaN = no rating).
+    int32_t n_pop = 0, pop_ld = 0;
+    bool pop_u8 = false;
+    int32_t *pop_idx = nullptr;    // [n_left] index in the popular list or -1
+    int32_t *pop_items = nullptr;  // [pop_ld] row id (-1 beyond n_pop)
+    void *pop_dense = nullptr;
+    int64_t *w_ptr = nullptr;
+    int32_t *w_col = nullptr;
+    double *w_dev = nullptr;
+    int32_t *row_all = nullptr;    // every row of the shard, longest first (the dense pass visits them all)
+    int64_t n_all_rows = 0;
     // int8 planes X^2, M, X of the left matrix, [3][k_pad / 256][n_pad][256] (tensor path)
     int8_t *planes = nullptr;
     int64_t tc_npad = 0, tc_kpad = 0;

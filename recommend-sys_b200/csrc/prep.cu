@@ -236,6 +236,80 @@ __global__ void compose_l2r_kernel(const int32_t *__restrict__ perm_lr, const in
     if (e < n) l2r[e] = inv_rl[perm_lr[e]];
 }
 
+// ---- popular columns (sim_stream.cu: sim_pop_kernel) ----
+// n_pop = rows of at least min_len entries (len_sorted is descending), at most cap
+__global__ void pop_count_kernel(const int32_t *__restrict__ len_sorted, int32_t n, int64_t min_len, int32_t cap,
+                                 int32_t *__restrict__ out) {
+    int32_t lo = 0, hi = n;                                   // first position whose length is < min_len
+    while (lo < hi) {
+        const int32_t mid = (lo + hi) >> 1;
+        if ((int64_t)len_sorted[mid] >= min_len) lo = mid + 1; else hi = mid;
+    }
+    *out = lo < cap ? lo : cap;
+}
+// pop_idx[row] = position in the popular list (-1 elsewhere: the array is preset to 0xFF), pop_items = the list
+__global__ void pop_index_kernel(const int32_t *__restrict__ sorted, int32_t n_pop, int32_t pop_ld,
+                                 int32_t *__restrict__ pop_idx, int32_t *__restrict__ pop_items) {
+    const int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pop_ld) return;
+    if (p < n_pop) { const int32_t i = sorted[p]; pop_idx[i] = p; pop_items[p] = i; }
+    else pop_items[p] = -1;
+}
+// One warp per right row: its popular ratings go into the dense table (preset to "no rating"), the others are
+// counted (w_cnt[c]; the walk CSR's row pointers are the exclusive sums).
+template <typename DT>
+__global__ void pop_scatter_kernel(const int64_t *__restrict__ r_ptr, const int32_t *__restrict__ r_col,
+                                   const double *__restrict__ r_val, const double *__restrict__ r_dev,
+                                   int32_t n_right, const int32_t *__restrict__ pop_idx, int32_t pop_ld,
+                                   DT *__restrict__ dense, int64_t *__restrict__ w_cnt) {
+    const int32_t c = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c > n_right) return;
+    if (c == n_right) { if (lane == 0) w_cnt[c] = 0; return; }
+    int32_t light = 0;
+    for (int64_t x = r_ptr[c] + lane; x < r_ptr[c + 1]; x += 32) {
+        const int32_t p = pop_idx[r_col[x]];
+        if (p < 0) { light++; continue; }
+        if (sizeof(DT) == 1) dense[(int64_t)c * pop_ld + p] = (DT)((int)r_val[x] + RS_INT8_BIAS);            // the byte code of code_int8_kernel
+        else dense[(int64_t)c * pop_ld + p] = (DT)r_dev[x];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) light += __shfl_xor_sync(0xffffffffu, light, o);
+    if (lane == 0) w_cnt[c] = light;
+}
+// One warp per right row: the other ratings, compacted in order into the walk CSR; pos[x] = where the entry went.
+__global__ void pop_compact_kernel(const int64_t *__restrict__ r_ptr, const int32_t *__restrict__ r_col,
+                                   const double *__restrict__ r_dev, int32_t n_right,
+                                   const int32_t *__restrict__ pop_idx, const int64_t *__restrict__ w_ptr,
+                                   int32_t *__restrict__ w_col, double *__restrict__ w_dev, int64_t *__restrict__ pos) {
+    const int32_t c = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= n_right) return;
+    const int64_t b = r_ptr[c], e = r_ptr[c + 1];
+    int64_t out = w_ptr[c];
+    for (int64_t x0 = b; x0 < e; x0 += 32) {
+        const int64_t x = x0 + lane;
+        int32_t j = -1;
+        bool keep = false;
+        if (x < e) { j = r_col[x]; keep = pop_idx[j] < 0; }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (x < e) {
+            const int64_t o = out + __popc(m & ((1u << lane) - 1u));
+            if (keep) { w_col[o] = j; w_dev[o] = r_dev[x]; pos[x] = o; }
+            else pos[x] = -1;
+        }
+        out += __popc(m);
+    }
+}
+__global__ void pop_remap_l2r_kernel(int64_t *__restrict__ l2r, const int64_t *__restrict__ pos, int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) l2r[e] = pos[l2r[e]];      // -1 for the entries of popular rows, which are never walked
+}
+struct PopLight {
+    const int32_t *pop_idx;
+    __host__ __device__ bool operator()(const int32_t &i) const { return pop_idx[i] < 0; }
+};
+
 
 // planes[p][col / kblk][row][col % kblk]: p=0 rating^2, p=1 mask, p=2 rating (the order the MMAs of
 // sim_tensor.cu rely on: B planes adjacent in shared memory as X2 | M | X); int8, K-blocked so that
@@ -546,20 +620,96 @@ static int32_t split_heavy_rows(rs_knn *h, int32_t *order, int64_t n_rows, bool 
     return RS_OK;
 }
 
+// Popular columns: the rows of >= min_len entries (at most RS_POP_MAX, the longest).  `sorted`: ALL rows, longest
+// first; `len_sorted`: their lengths; `order` / n_rows: the rows of this shard, longest first.  Splits their
+// ratings off the right CSR (walk CSR + dense table, see rs_knn::pop_*), builds `cp` and re-targets `l2r` for the
+// walk CSR, and leaves the rows the column walk visits (the others, same order) in h->row_order.
+constexpr int RS_POP_MAX = 512;
+
+static int32_t split_popular(rs_knn *h, const int32_t *sorted, const int32_t *len_sorted, int32_t *order, int64_t n_rows,
+                             int64_t min_len) {
+    cudaStream_t st = h->stream;
+    int32_t *d_num;
+    RS_TRY(rs_alloc(h, &d_num, 4));
+    pop_count_kernel<<<1, 1, 0, st>>>(len_sorted, h->n_left, min_len, RS_POP_MAX, d_num);
+    int32_t n_pop = 0;
+    RS_CUDA(cudaMemcpyAsync(&n_pop, d_num, 4, cudaMemcpyDeviceToHost, st));
+    RS_CUDA(cudaStreamSynchronize(st));
+    h->prof.total_launches++;
+    if (n_pop < 2) return RS_OK;                              // nothing to split off
+    const int32_t nr = h->n_right;
+    h->n_pop = n_pop;
+    h->pop_ld = (n_pop + 31) / 32 * 32;
+    h->pop_u8 = h->rating_class == RS_CLASS_INT8;
+    RS_TRY(rs_alloc(h, &h->pop_idx, (size_t)h->n_left));
+    RS_TRY(rs_alloc(h, &h->pop_items, (size_t)h->pop_ld));
+    RS_CUDA(cudaMemsetAsync(h->pop_idx, 0xFF, (size_t)h->n_left * 4, st));
+    pop_index_kernel<<<blocks_for(h->pop_ld), T, 0, st>>>(sorted, n_pop, h->pop_ld, h->pop_idx, h->pop_items);
+    // dense table + walk CSR
+    const size_t cell = h->pop_u8 ? 1 : 8;
+    RS_TRY(rs_dev_alloc(h, &h->pop_dense, (size_t)nr * h->pop_ld * cell));
+    RS_CUDA(cudaMemsetAsync(h->pop_dense, h->pop_u8 ? 0 : 0xFF, (size_t)nr * h->pop_ld * cell, st));   // 0 / NaN = no rating
+    int64_t *w_cnt, *pos;
+    RS_TRY(rs_alloc(h, &w_cnt, (size_t)nr + 1));
+    RS_TRY(rs_alloc(h, &h->w_ptr, (size_t)nr + 1));
+    RS_TRY(rs_alloc(h, &h->w_col, (size_t)h->nnz));
+    RS_TRY(rs_alloc(h, &h->w_dev, (size_t)h->nnz));
+    RS_TRY(rs_alloc(h, &pos, (size_t)h->nnz));
+    if (h->pop_u8)
+        pop_scatter_kernel<uint8_t><<<blocks_for(((int64_t)nr + 1) * 32), T, 0, st>>>(
+            h->r_ptr, h->r_col, h->r_val, h->r_dev, nr, h->pop_idx, h->pop_ld, static_cast<uint8_t *>(h->pop_dense), w_cnt);
+    else
+        pop_scatter_kernel<double><<<blocks_for(((int64_t)nr + 1) * 32), T, 0, st>>>(
+            h->r_ptr, h->r_col, h->r_val, h->r_dev, nr, h->pop_idx, h->pop_ld, static_cast<double *>(h->pop_dense), w_cnt);
+    size_t need = 0;
+    RS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, w_cnt, h->w_ptr, nr + 1, st));
+    void *tmp;
+    RS_TRY(rs_dev_alloc(h, &tmp, need + 256));
+    RS_CUDA(cub::DeviceScan::ExclusiveSum(tmp, need, w_cnt, h->w_ptr, nr + 1, st));
+    pop_compact_kernel<<<blocks_for((int64_t)nr * 32), T, 0, st>>>(h->r_ptr, h->r_col, h->r_dev, nr, h->pop_idx, h->w_ptr,
+                                                                   h->w_col, h->w_dev, pos);
+    pop_remap_l2r_kernel<<<blocks_for(h->nnz), T, 0, st>>>(h->l2r, pos, h->nnz);
+    h->prof.total_launches += 5;
+    // the rows the column walk visits: the shard's rows that are not popular
+    h->row_all = order;
+    h->n_all_rows = n_rows;
+    int32_t *rest;
+    RS_TRY(rs_alloc(h, &rest, (size_t)(n_rows > 0 ? n_rows : 1)));
+    h->row_order = rest;
+    h->n_work_rows = 0;
+    if (n_rows > 0) {
+        PopLight light{h->pop_idx};
+        size_t need2 = 0;
+        RS_CUDA(cub::DeviceSelect::If(nullptr, need2, order, rest, d_num, (int)n_rows, light, st));
+        void *tmp2;
+        RS_TRY(rs_dev_alloc(h, &tmp2, need2 + 256));
+        RS_CUDA(cub::DeviceSelect::If(tmp2, need2, order, rest, d_num, (int)n_rows, light, st));
+        int32_t cnt = 0;
+        RS_CUDA(cudaMemcpyAsync(&cnt, d_num, 4, cudaMemcpyDeviceToHost, st));
+        RS_CUDA(cudaStreamSynchronize(st));
+        h->n_work_rows = cnt;
+    }
+    return RS_OK;
+}
+
 int32_t rs_prep_rt(rs_knn *h) {
     cudaStream_t st = h->stream;
     h->n_chunks = (int32_t)(((int64_t)h->n_left + h->stream_jc - 1) / h->stream_jc);
+    h->n_pop = 0;
     RS_TRY(rs_alloc(h, &h->r_dev, (size_t)h->nnz));
     RS_TRY(rs_alloc(h, &h->l2r, (size_t)h->nnz));
     RS_TRY(rs_alloc(h, &h->cp, (size_t)h->n_right * ((size_t)h->n_chunks + 1)));
     build_rdev_kernel<<<blocks_for((int64_t)h->n_right * 32), T, 0, st>>>(
         h->r_ptr, h->r_col, h->r_val, h->n_right, h->p.sim, h->pmeans, h->left_bias, h->right_bias, h->global_bias,
         h->r_dev);
-    build_cp_kernel<<<blocks_for((int64_t)h->n_right * 32), T, 0, st>>>(h->r_ptr, h->r_col, h->n_right, 0, h->n_chunks,
-                                                                         h->stream_jc, h->cp);
     invert_perm_kernel<<<blocks_for(h->nnz), T, 0, st>>>(h->perm_rl, h->nnz, h->perm_tmp);
     compose_l2r_kernel<<<blocks_for(h->nnz), T, 0, st>>>(h->perm_lr, h->perm_tmp, h->nnz, h->l2r);
     h->prof.total_launches += 4;
+    // chunk pointers of the CSR the column walk reads: the right CSR, or the walk CSR once popular columns are split off
+    auto build_cp = [&]() {
+        build_cp_kernel<<<blocks_for((int64_t)h->n_right * 32), T, 0, st>>>(
+            h->n_pop ? h->w_ptr : h->r_ptr, h->n_pop ? h->w_col : h->r_col, h->n_right, 0, h->n_chunks, h->stream_jc, h->cp);
+    };
     // rows of the shard ordered longest first (a stable descending sort of the row lengths keeps the
     // order deterministic): the longest work items start first
     {
@@ -575,6 +725,7 @@ int32_t rs_prep_rt(rs_knn *h) {
             // rows are produced slab by slab into a slab-sized buffer: keep the natural order
             h->row_order = ids;
             h->n_work_rows = -1;                 // the launcher takes [row_begin, row_end) of the natural order
+            build_cp();
             RS_CUDA(cudaGetLastError());
             return RS_OK;
         }
@@ -585,6 +736,16 @@ int32_t rs_prep_rt(rs_knn *h) {
         RS_TRY(rs_dev_alloc(h, &tmp, need));
         RS_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, need, len + rb, len_sorted + rb, ids + rb,
                                                           sorted, (int)rows, 0, 32, st));
+        // Full-matrix Fits (one GPU, or cyclic shards) compute one triangle and mirror the other: there the longest
+        // rows can be taken out of the column walk.  RS_KNN_POP=0 keeps them in it (under cyclic sharding as
+        // producer / consumer CTAs: split_heavy_rows); RS_KNN_HEAVY_MIN sets the length threshold (tests).
+        const bool full = h->row_begin == 0 && h->row_end == h->n_left;
+        int64_t min_len = 8192;
+        if (const char *e = getenv("RS_KNN_HEAVY_MIN")) min_len = atoll(e);
+        bool pop = full && min_len >= 0;
+        if (const char *e = getenv("RS_KNN_POP")) pop = pop && atoi(e) != 0;
+        int32_t *order = sorted;
+        int64_t n_order = rows;
         if (h->cyc_R > 1) {
             // cyclic shards: the owned rows picked out of the longest-first order
             int32_t *owned, *d_num;
@@ -596,10 +757,16 @@ int32_t rs_prep_rt(rs_knn *h) {
             void *tmp2;
             RS_TRY(rs_dev_alloc(h, &tmp2, need2 + 256));
             RS_CUDA(cub::DeviceSelect::If(tmp2, need2, sorted, owned, d_num, (int)h->n_left, pred, st));
-            RS_TRY(split_heavy_rows(h, owned, h->rows_local, true));
-        } else {
-            RS_TRY(split_heavy_rows(h, sorted, rows, h->row_begin == 0 && h->row_end == h->n_left));
+            order = owned;
+            n_order = h->rows_local;
         }
+        h->n_heavy = 0;
+        h->row_heavy = nullptr;
+        h->row_order = order;
+        h->n_work_rows = n_order;
+        if (pop) RS_TRY(split_popular(h, sorted, len_sorted, order, n_order, min_len));
+        else RS_TRY(split_heavy_rows(h, order, n_order, full));
+        build_cp();
     }
     RS_CUDA(cudaGetLastError());
     return RS_OK;

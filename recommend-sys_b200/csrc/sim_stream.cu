@@ -46,6 +46,7 @@ struct StreamArgs {
     int64_t n_rows;           // rows of row_order to walk
     int cyc_R;                // >= 2: cyclic row shards, the output row is rs_cyc_local(i)
     int symmetric;            // 0: full rows; 1: only columns j > i are computed; 2: only j < i (the mirror pass fills the rest)
+    const int32_t *pop_idx;   // popular columns (not in the CSR this walk reads; sim_pop_kernel writes their cells) or null
     unsigned long long *counter;
 };
 
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
             if (col >= a.n_left) break;
             if (SYM == 1 && col < i) continue;                                    // mirror pass writes it
             if (SYM == 2 && col > i) break;
+            if (a.pop_idx && a.pop_idx[col] >= 0) continue;                       // sim_pop_kernel writes it
             double s;
             if (SIM == RS_SIM_MSD) s = 1.0 / (acc[j] / acc[JC + j] + 1.0);        // core/sim.go:43
             else s = acc[2 * JC + j] / (sqrt(acc[j]) * sqrt(acc[JC + j]));        // core/sim.go:24 / :80
@@ -433,6 +435,147 @@ __global__ void __launch_bounds__(HV_WARPS * 32, 1) sim_stream_heavy_kernel(Stre
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Popular columns.  The column walk serialises a row's entries in ONE warp, so the few rows that a large part of
+// the right ids rated (78 k of 138 k on the MovieLens-20M shape) are chains of tens of thousands of dependent
+// steps, and as COLUMNS they fill the other rows' runs with most of the triples (the 312 longest of 26,744 rows
+// hold 34 % of the ratings and take part in 56 % of the co-rated triples).  rs_prep_rt takes their ratings out of
+// the CSR the walk reads and lays them out as a dense table D[right id][popular column]; this kernel computes
+// every pair with a popular column from it:
+//   work item = (row i, block of 32 popular columns), one warp; LANE = column, accumulators in registers;
+//   the warp walks row i's entries in ascending right id c — the reference's order (core/sim.go:14-22) —, each
+//   step is ONE coalesced load of D[c][block] (independent of the accumulators: 16 in flight) and, in the lanes
+//   whose column c rated, the reference's IEEE operations on the lane's own sums.
+// No lookups, no gathers, no shared-memory read-modify-writes, and no work item depends on another: a row of
+// 78 k entries is 10 items of 78 k pipelined steps.  Who computes which pair (the mirror passes below copy the
+// transposed cell): a popular column's pairs with every other row belong to THAT row; two popular rows: to the one
+// further down the popular list (the shorter one); two other rows: the triangle rule of the column walk.
+constexpr int PW = 8;       // warps per CTA
+constexpr int PU = 16;      // loads in flight per warp
+
+struct PopArgs {
+    const int32_t *rows;      // the shard's rows, longest first
+    int64_t n_rows;
+    const int32_t *pop_idx;   // [n_left] index in the popular list or -1
+    const int32_t *pop_items; // [32 * n_blk] row id, -1 beyond the list
+    int32_t n_blk, ld;        // blocks of 32 popular columns; row stride of the table
+    const void *dense;
+    unsigned long long *counter;
+};
+
+template <int SIM, bool SHRINK, typename DT>
+__global__ void __launch_bounds__(PW * 32) sim_pop_kernel(StreamArgs a, PopArgs pa) {
+    __shared__ double s_ra[PW][32];
+    __shared__ double s_rbias[PW][32];
+    __shared__ int32_t s_c[PW][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const DT *__restrict__ dense = static_cast<const DT *>(pa.dense);
+    const int64_t n_items = pa.n_rows * pa.n_blk;
+    const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
+
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(pa.counter, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if ((int64_t)item >= n_items) break;
+        const int32_t i = pa.rows[(int64_t)item / pa.n_blk];
+        const int b = (int)((int64_t)item % pa.n_blk);
+        const int pi = pa.pop_idx[i];
+        if (pi >= 0 && 32 * b > pi) continue;                 // a popular row: only the columns above it in the list
+        const int col = 32 * b + lane;
+        const int32_t hcol = pa.pop_items[col];
+        const bool want = hcol >= 0 && (pi < 0 || col < pi);
+        double bh = 0.0;                                      // what is subtracted from the column's ratings
+        if (want && SIM == RS_SIM_PEARSON) bh = a.pmeans[hcol];
+        if (want && SIM == RS_SIM_PEARSON_BASELINE) bh = a.global_bias + a.left_bias[hcol];
+        double ai = 0.0;
+        if (SIM == RS_SIM_PEARSON) ai = a.pmeans[i];
+        if (SIM == RS_SIM_PEARSON_BASELINE) ai = a.global_bias + a.left_bias[i];
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        const int64_t eb = a.l_ptr[i], ee = a.l_ptr[i + 1];
+
+        if (__any_sync(0xffffffffu, want)) {
+            for (int64_t x0 = eb; x0 < ee; x0 += 32) {
+                const int64_t e = x0 + lane;
+                int32_t c = 0;
+                double ra = 0.0, rbias = 0.0;
+                if (e < ee) {
+                    c = a.l_col[e];
+                    const double v = a.l_val[e];
+                    if (SIM == RS_SIM_PEARSON) ra = v - ai;                       // core/sim.go:73
+                    else if (SIM == RS_SIM_PEARSON_BASELINE) { rbias = a.right_bias[c]; const double bb = ai + rbias; ra = v - bb; }
+                    else ra = v;
+                }
+                __syncwarp();                                 // the previous batch has been read
+                s_c[warp][lane] = c;
+                s_ra[warp][lane] = ra;
+                if (SIM == RS_SIM_PEARSON_BASELINE) s_rbias[warp][lane] = rbias;
+                __syncwarp();
+                const int lim = (ee - x0) < 32 ? (int)(ee - x0) : 32;
+#pragma unroll
+                for (int u0 = 0; u0 < 32; u0 += PU) {
+                    if (u0 >= lim) break;
+                    DT d[PU];
+#pragma unroll
+                    for (int g = 0; g < PU; g++) {
+                        const int u = u0 + g;
+                        if constexpr (sizeof(DT) == 1) d[g] = (DT)0; else d[g] = (DT)nan_v;
+                        if (want && u < lim) d[g] = dense[(int64_t)s_c[warp][u] * pa.ld + col];
+                    }
+#pragma unroll
+                    for (int g = 0; g < PU; g++) {
+                        const int u = u0 + g;
+                        const bool rated = sizeof(DT) == 1 ? (d[g] != (DT)0) : (d[g] == d[g]);
+                        if (!rated) continue;
+                        const double ra_u = s_ra[warp][u];
+                        double rb;                                                // the b-side term, as build_rdev_kernel (prep.cu)
+                        if constexpr (sizeof(DT) == 1) {
+                            const double y = (double)((int)d[g] - RS_INT8_BIAS);
+                            if (SIM == RS_SIM_PEARSON) rb = y - bh;               // core/sim.go:74
+                            else if (SIM == RS_SIM_PEARSON_BASELINE) { const double bb = bh + s_rbias[warp][u]; rb = y - bb; }
+                            else rb = y;
+                        } else {
+                            rb = (double)d[g];
+                        }
+                        if (SIM == RS_SIM_MSD) {
+                            const double dd = ra_u - rb;
+                            acc0 += dd * dd;                                      // core/sim.go:37
+                            acc1 += 1.0;                                          // core/sim.go:38
+                        } else {
+                            const double raa_u = ra_u * ra_u;
+                            acc0 += raa_u;                                        // core/sim.go:19 / :75
+                            acc1 += rb * rb;                                      // core/sim.go:20 / :76
+                            acc2 += ra_u * rb;                                    // core/sim.go:21 / :77
+                            if (SHRINK) acc3 += 1.0;
+                        }
+                    }
+                }
+            }
+        }
+
+        if (hcol >= 0) {
+            double *out = a.sims + (a.cyc_R > 1 ? rs_cyc_local(i, a.cyc_R) : (int64_t)(i - a.row_begin)) * a.ld_s;
+            if (pi >= 0 && col == pi) {
+                out[hcol] = nan_v;                                                // diagonal stays NaN
+            } else if (want) {
+                double s;
+                if (SIM == RS_SIM_MSD) s = 1.0 / (acc0 / acc1 + 1.0);                          // core/sim.go:43
+                else s = acc2 / (sqrt(acc0) * sqrt(acc1));                                     // core/sim.go:24 / :80
+                if (SHRINK) s = (acc3 - 1.0) / (acc3 - 1.0 + a.shrinkage) * s;
+                out[hcol] = s;
+            }
+        }
+    }
+}
+
+// does row r's own pass (column walk or sim_pop_kernel) compute cell (r, c)?  pr / pc: their popular indices or -1
+__device__ __forceinline__ bool pop_owns(int64_t r, int64_t c, int pr, int pc, int lower) {
+    if (pc >= 0 && pr < 0) return true;
+    if (pr >= 0 && pc < 0) return false;
+    if (pr >= 0) return pc < pr;
+    return lower ? c < r : c > r;
+}
+
 // Mirror the computed upper block-triangle into the lower one: the three similarities are
 // bit-symmetric (sums and products commute), which is why the reference can write
 // Sims[j][i] = Sims[i][j] (core/knn.go:205-208).  32x32 tiles through shared memory,
@@ -486,6 +629,57 @@ __global__ void mirror_kernel(MirrorArgs a) {
     }
 }
 
+// The same two passes when popular columns were split off: which of the cells (r, c) / (c, r) was computed is
+// pop_owns(), cell by cell, so a pair of transposed tiles may exchange cells in both directions.
+__global__ void symmetrize_pop_kernel(double *__restrict__ s, int64_t ld, int32_t n, int lower,
+                                      const int32_t *__restrict__ pop_idx) {
+    __shared__ double ta[32][33], tb[32][33];
+    const int64_t bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;                                     // one block per unordered tile pair
+    const int64_t r0 = bi * 32, c0 = bj * 32;                // tile A = rows r0.., cols c0..; tile B = rows c0.., cols r0..
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int64_t ar = r0 + y, ac = c0 + threadIdx.x, br = c0 + y, bc = r0 + threadIdx.x;
+        ta[y][threadIdx.x] = (ar < n && ac < n) ? s[ar * ld + ac] : 0.0;
+        tb[y][threadIdx.x] = (br < n && bc < n) ? s[br * ld + bc] : 0.0;
+    }
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        int64_t r = r0 + y, c = c0 + threadIdx.x;            // a cell of A takes B's transposed cell (c, r)
+        if (r < n && c < n && r != c && !pop_owns(r, c, pop_idx[r], pop_idx[c], lower)) s[r * ld + c] = tb[threadIdx.x][y];
+        if (bi == bj) continue;
+        r = c0 + y; c = r0 + threadIdx.x;                    // a cell of B takes A's transposed cell
+        if (r < n && c < n && !pop_owns(r, c, pop_idx[r], pop_idx[c], lower)) s[r * ld + c] = ta[threadIdx.x][y];
+    }
+}
+
+__global__ void mirror_pop_kernel(MirrorArgs a, const int32_t *__restrict__ pop_idx) {
+    __shared__ double tile[32][33];
+    const int64_t bI = blockIdx.y;                           // own block (local index)
+    const int64_t gI = bI * a.count + a.index, gJ = blockIdx.x;
+    bool need[4];                                            // blockDim.y == 8: four cells per thread
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int y = threadIdx.y + 8 * k;
+        const int64_t r = gI * 32 + y, c = gJ * 32 + threadIdx.x;
+        need[k] = r < a.n && c < a.n && r != c && !pop_owns(r, c, pop_idx[r], pop_idx[c], a.lower);
+        any = any || need[k];
+    }
+    if (!__syncthreads_or(any)) return;                      // every cell of the tile is this shard's own work
+    const double *src = a.peer[gJ % a.count];
+    const int64_t sJ = (gJ / a.count) * RS_CYC_B;            // first local row of block gJ at its owner
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int64_t sr = gJ * 32 + y, sc = gI * 32 + threadIdx.x;   // global (row, col) of the source cell
+        tile[y][threadIdx.x] = (sr < a.n && sc < a.n) ? src[(sJ + y) * a.ld + sc] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int y = threadIdx.y + 8 * k;
+        if (need[k]) a.self[(bI * 32 + y) * a.ld + gJ * 32 + threadIdx.x] = tile[threadIdx.x][y];
+    }
+}
+
 }  // namespace
 
 template <int SIM, bool SHRINK, int SYM, int JC>
@@ -527,6 +721,32 @@ static int32_t launch_heavy(rs_knn *h, const StreamArgs &a, const HeavyArgs &hv)
     return RS_OK;
 }
 
+template <int SIM, bool SHRINK>
+static int32_t launch_pop(rs_knn *h, const StreamArgs &a, const PopArgs &pa) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int64_t items = pa.n_rows * pa.n_blk;
+    int64_t grid = (int64_t)sms * 4;                          // resident CTAs; warps pull work items from the counter
+    if (grid > (items + PW - 1) / PW) grid = (items + PW - 1) / PW;
+    // on the auxiliary stream, beside the column walk of the other columns
+    if (h->pop_u8) sim_pop_kernel<SIM, SHRINK, uint8_t><<<(unsigned)grid, PW * 32, 0, h->aux_stream>>>(a, pa);
+    else sim_pop_kernel<SIM, SHRINK, double><<<(unsigned)grid, PW * 32, 0, h->aux_stream>>>(a, pa);
+    h->prof.total_launches += 1;
+    return RS_OK;
+}
+
+static int32_t rs_pop_launch(rs_knn *h, const StreamArgs &a, const PopArgs &pa) {
+    switch (h->p.sim) {
+    case RS_SIM_COSINE: return launch_pop<RS_SIM_COSINE, false>(h, a, pa);
+    case RS_SIM_MSD: return launch_pop<RS_SIM_MSD, false>(h, a, pa);
+    case RS_SIM_PEARSON: return launch_pop<RS_SIM_PEARSON, false>(h, a, pa);
+    case RS_SIM_PEARSON_BASELINE:
+        return h->p.shrinkage > 0.0 ? launch_pop<RS_SIM_PEARSON_BASELINE, true>(h, a, pa)
+                                    : launch_pop<RS_SIM_PEARSON_BASELINE, false>(h, a, pa);
+    default: rs_set_error("unknown similarity %d", h->p.sim); return RS_ERR_INVALID;
+    }
+}
+
 static int32_t rs_heavy_rows_launch(rs_knn *h, const StreamArgs &a, const HeavyArgs &hv) {
     switch (h->p.sim) {
     case RS_SIM_COSINE: return launch_heavy<RS_SIM_COSINE, false>(h, a, hv);
@@ -556,9 +776,30 @@ int32_t rs_sim_stream_launch(rs_knn *h) {
     a.symmetric = h->force_sym ? 1 : ((h->row_begin == 0 && h->row_end == h->n_left) || cyc) ? (h->stream_lower ? 2 : 1) : 0;
     a.counter = reinterpret_cast<unsigned long long *>(h->d_flags + 2);
     RS_CUDA(cudaMemsetAsync(a.counter, 0, 8, h->stream));
+    // popular columns (rs_prep_rt split them off: the walk reads the CSR without them) run as a dense pass on the
+    // auxiliary stream beside the column walk
+    const bool pop = h->n_pop > 0;
+    if (pop) {
+        if (a.symmetric == 0 || h->force_sym) {
+            rs_set_error("popular columns were split off, but this Fit does not compute a triangle of the full matrix");
+            return RS_ERR_INVALID;
+        }
+        a.r_ptr = h->w_ptr; a.r_col = h->w_col; a.r_dev = h->w_dev; a.pop_idx = h->pop_idx;
+        PopArgs pa{};
+        pa.rows = h->row_all; pa.n_rows = h->n_all_rows;
+        pa.pop_idx = h->pop_idx; pa.pop_items = h->pop_items;
+        pa.n_blk = h->pop_ld / 32; pa.ld = h->pop_ld;
+        pa.dense = h->pop_dense;
+        pa.counter = reinterpret_cast<unsigned long long *>(h->d_flags + 12);
+        RS_CUDA(cudaMemsetAsync(pa.counter, 0, 8, h->stream));
+        RS_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+        RS_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+        if (pa.n_rows > 0) RS_TRY(rs_pop_launch(h, a, pa));
+        RS_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
+    }
     // heavy rows (rs_prep_rt split them off the order; JC = 256 only) run as producer / consumer CTAs on the
     // auxiliary stream beside the column walk of the other rows
-    const bool heavy = h->n_heavy > 0 && a.symmetric != 0 && !h->force_sym && h->stream_jc == HV_JC;
+    const bool heavy = !pop && h->n_heavy > 0 && a.symmetric != 0 && !h->force_sym && h->stream_jc == HV_JC;
     if (heavy) {
         HeavyArgs hv{};
         hv.rows = h->row_heavy; hv.n_rows = h->n_heavy;
@@ -570,7 +811,7 @@ int32_t rs_sim_stream_launch(rs_knn *h) {
         RS_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
     }
     if (a.n_rows <= 0) {
-        if (heavy) RS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        if (heavy || pop) RS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         return RS_OK;
     }
     int sms = 148;
@@ -588,7 +829,7 @@ int32_t rs_sim_stream_launch(rs_knn *h) {
         break;
     default: rs_set_error("unknown similarity %d", h->p.sim); return RS_ERR_INVALID;
     }
-    if (heavy) RS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    if (heavy || pop) RS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     h->prof.sim_launches++;
     h->prof.total_launches++;
     RS_CUDA(cudaGetLastError());
@@ -605,7 +846,8 @@ int32_t rs_mirror_launch(rs_knn *h) {
     const int64_t own = (nblk - h->cyc_r + h->cyc_R - 1) / h->cyc_R;
     if (own <= 0) return RS_OK;
     dim3 grid((unsigned)nblk, (unsigned)own), block(32, 8);
-    mirror_kernel<<<grid, block, 0, h->stream>>>(a);
+    if (h->n_pop > 0) mirror_pop_kernel<<<grid, block, 0, h->stream>>>(a, h->pop_idx);
+    else mirror_kernel<<<grid, block, 0, h->stream>>>(a);
     h->prof.total_launches++;
     RS_CUDA(cudaGetLastError());
     return RS_OK;
@@ -616,7 +858,8 @@ int32_t rs_symmetrize_launch(rs_knn *h) {
     if (!(h->row_begin == 0 && h->row_end == h->n_left)) return RS_OK;
     const unsigned t = (unsigned)((h->n_left + 31) / 32);
     dim3 grid(t, t), block(32, 8);
-    symmetrize_kernel<<<grid, block, 0, h->stream>>>(h->sims, h->ld_s, h->n_left, h->stream_lower ? 1 : 0);
+    if (h->n_pop > 0) symmetrize_pop_kernel<<<grid, block, 0, h->stream>>>(h->sims, h->ld_s, h->n_left, h->stream_lower ? 1 : 0, h->pop_idx);
+    else symmetrize_kernel<<<grid, block, 0, h->stream>>>(h->sims, h->ld_s, h->n_left, h->stream_lower ? 1 : 0);
     h->prof.total_launches++;
     RS_CUDA(cudaGetLastError());
     return RS_OK;

@@ -83,18 +83,23 @@ def test_sims_bit_exact_both_triangles(ml100k, sim, user_based, tri, monkeypatch
 
 # ---- cyclic row shards (the multi-GPU Fit + Predict): every shard computes one triangle of its rows,
 # the mirror step pulls the other one from the peers; here all shards live on one GPU ----
+@pytest.mark.parametrize("pop", ["1", "0"])
 @pytest.mark.parametrize("tri", ["upper", "lower"])
 @pytest.mark.parametrize("count", [2, 3])
-def test_cyclic_row_shards_equal_full(ml100k, count, tri, monkeypatch):
+def test_cyclic_row_shards_equal_full(ml100k, count, tri, pop, monkeypatch):
     monkeypatch.setenv("RS_KNN_STREAM_TRI", tri)
     monkeypatch.setenv("RS_KNN_STREAM_JC", "256")
-    monkeypatch.setenv("RS_KNN_HEAVY_MIN", "200")      # the longer rows of every shard take the heavy-row kernel
+    monkeypatch.setenv("RS_KNN_HEAVY_MIN", "200")      # the longer rows: popular columns (dense pass) / heavy-row kernel
+    monkeypatch.setenv("RS_KNN_POP", pop)
     u, i, r = split(ml100k["u1_base"])
     ts = rs.NewTrainSet(rs.NewRawSet(u, i, r))
     base = {"sim": rs.Pearson, "userBased": False, "k": 40}
     full = rs.NewKNNWithMean(rs.Parameters(base))
     full.Fit(ts)
     want = full.Sims
+    ref = ob.KNN(sim="pearson", knn_type="centered", user_based=False, k=40, n_jobs=8,
+                 tie_policy="canonical").fit(ob.TrainSet(u, i, r))
+    assert bits_equal(want, ref.sims())
     tu, ti, _ = split(ml100k["u1_test"])
     want_pred = full.PredictBatch(tu, ti)
     shards = []
@@ -221,21 +226,65 @@ def test_concurrent_predict_on_one_handle(ml100k):
     assert bits_equal(np.concatenate(out), want)
 
 
-# ---- heavy rows of the exact sparse Fit: producer / consumer CTAs (seven warps stage the entries' runs with
-# cp.async, one applies them in order) instead of one warp per (row, chunk): every row (min 0) and a mix
-# (rows of >= 150 entries), both triangles, all similarities ----
+# ---- the longest rows of the exact sparse Fit.  mode "pop" (default): their ratings leave the CSR the column walk
+# reads and every pair with one of them comes from the dense pass (sim_pop_kernel: lane = popular column, register
+# accumulators); mode "heavy": they stay in the walk as producer / consumer CTAs.  Every row (min 0: the 512
+# longest become popular columns) and a mix (rows of >= 150 entries), both triangles, all similarities ----
+@pytest.mark.parametrize("mode", ["pop", "heavy"])
 @pytest.mark.parametrize("heavy_min", ["0", "150"])
 @pytest.mark.parametrize("tri", ["upper", "lower"])
 @pytest.mark.parametrize("sim", ["cosine", "msd", "pearson"])
-def test_heavy_row_mode_bit_exact(ml100k, sim, tri, heavy_min, monkeypatch):
+def test_heavy_row_mode_bit_exact(ml100k, sim, tri, heavy_min, mode, monkeypatch):
     monkeypatch.setenv("RS_KNN_STREAM_TRI", tri)
     monkeypatch.setenv("RS_KNN_STREAM_JC", "256")       # the heavy kernel shares the 256-column chunk pointers
     monkeypatch.setenv("RS_KNN_HEAVY_MIN", heavy_min)
+    monkeypatch.setenv("RS_KNN_POP", "1" if mode == "pop" else "0")
     for user_based in (True, False):
         est, ref = fit_pair(ml100k["u2_base"], sim, "basic", user_based, extra={"simPath": "stream"})
         got, want = est.Sims, ref.sims()
         assert np.isnan(np.diag(got)).all()
         assert bits_equal(got, want)
+        assert bits_equal(got, got.T)
+
+
+# ---- popular columns with the other table type and the other similarities: continuous ratings (the dense table
+# holds the b-side doubles instead of one byte per cell), PearsonBaseline with and without shrinkage (the b-side
+# term depends on both biases), a threshold that makes EVERY row popular (no column walk at all), and the
+# predictions that read the mirrored cells ----
+@pytest.mark.parametrize("heavy_min", ["0", "60"])
+def test_popular_columns_tables_and_baseline(ml100k, heavy_min, monkeypatch):
+    monkeypatch.setenv("RS_KNN_HEAVY_MIN", heavy_min)
+    arr = ml100k["u3_base"]
+    u, i, r = split(arr)
+    rng = np.random.RandomState(11)
+    rc = r + rng.uniform(-0.49, 0.49, len(r))
+    for sim in ("cosine", "msd", "pearson"):
+        for user_based in (True, False):
+            ts = rs.NewTrainSet(rs.NewRawSet(u, i, rc))
+            est = rs.NewKNN(rs.Parameters({"sim": SIMS[sim], "userBased": user_based, "k": 40}))
+            est.Fit(ts)
+            ref = ob.KNN(sim=sim, knn_type="basic", user_based=user_based, k=40, n_jobs=8,
+                         tie_policy="canonical").fit(ob.TrainSet(u, i, rc))
+            assert bits_equal(est.Sims, ref.sims()), (sim, user_based)
+    tu, ti, _ = split(ml100k["u3_test"][:3000])
+    for ratings in (r, rc):
+        ts = rs.NewTrainSet(rs.NewRawSet(u, i, ratings))
+        ots = ob.TrainSet(u, i, ratings)
+        for shrink in (0.0, 100.0):
+            est = rs.NewKNNBaseLine(rs.Parameters({"sim": rs.PearsonBaseline, "userBased": False, "shrinkage": shrink}))
+            est.Fit(ts)
+            ref = ob.KNN(sim="pearson_baseline", knn_type="baseline", user_based=False, n_jobs=8,
+                         shrinkage=shrink).fit(ots)
+            assert bits_equal(est.Sims, ref.sims()), shrink
+            assert bits_equal(est.PredictBatch(tu, ti), ref.predict_batch(tu, ti))
+    # a matrix of fewer rows than the popular list can hold: every row is a popular column
+    sub = arr[arr[:, 1] <= 300]
+    su, si, sr = split(sub)
+    est = rs.NewKNNWithMean(rs.Parameters({"sim": rs.Pearson, "userBased": False, "k": 40}))
+    est.Fit(rs.NewTrainSet(rs.NewRawSet(su, si, sr)))
+    ref = ob.KNN(sim="pearson", knn_type="centered", user_based=False, k=40, n_jobs=8,
+                 tie_policy="canonical").fit(ob.TrainSet(su, si, sr))
+    assert bits_equal(est.Sims, ref.sims())
 
 
 # ---- arbitrary float64 ratings (continuous values, thousands of distinct ones): the stream path
@@ -737,6 +786,19 @@ def test_ml20m_shape_properties():
     sel = np.where((ii >= r0) & (ii < r1))[0][:500]
     assert len(sel) > 50
     assert bits_equal(pred[sel], ref.predict_batch(test.Users[sel], test.Items[sel], n_threads=16))
+    del ref
+    # the popular rows (first-appearance ids: the blockbusters are among the first rows): their pairs come from
+    # the dense pass and the mirror, not from the column walk — an oracle slab over them, and their transposes
+    cnt_items = np.bincount(train.innerItems, minlength=n)
+    assert (cnt_items[:256] >= 8192).sum() >= 8               # the slab below does hold popular rows
+    P0 = h.sims_rows(0, 256)
+    refp = ob.KNN(sim="pearson", knn_type="centered", user_based=False, n_jobs=16).fit(ots, rows=(0, 12))
+    assert bits_equal(P0[:12], refp.sims(copy=False)[0:12])
+    del refp
+    assert np.isnan(P0[np.arange(256), np.arange(256)]).all()
+    assert bits_equal(P0[:, :256], P0[:, :256].T)
+    assert bits_equal(P0[:, a0:a0 + m], A[:, :256].T)
+    assert bits_equal(P0[:, b0:b0 + m], B[:, :256].T)
     # the dense tensor path agrees bit for bit with the sparse replay on Cosine at this size
     cos_t = rs.NewKNN(rs.Parameters({"sim": rs.Cosine, "userBased": False, "simPath": "tensor"}))
     cos_t.Fit(train)

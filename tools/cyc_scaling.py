@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Per-shard time of the exact sparse Fit under cyclic row sharding, measured on ONE GPU: fits shard 0
 of `count` shards (no peers needed for the similarity kernel itself) and prints the kernel time.
-usage: tools/cyc_scaling.py [workload] [counts...]"""
+usage: [CYC_INDEX=i] [CYC_POP=1,0] tools/cyc_scaling.py [workload] [counts...]
+CYC_POP: the values of RS_KNN_POP to run (1: popular columns as a dense pass, 0: heavy rows in the walk)."""
+import os
 import sys
 from pathlib import Path
 
@@ -23,8 +25,9 @@ right = train.innerItems if user_based else train.innerUsers
 dev = torch.device("cuda", 0)
 d_left, d_right = torch.from_numpy(left).to(dev), torch.from_numpy(right).to(dev)
 d_rating = torch.from_numpy(train.Ratings).to(dev)
-for count in counts:
-    for index in sorted({0, count - 1}):
+for pop, count in [(p_, c_) for p_ in os.environ.get("CYC_POP", "1").split(",") for c_ in counts]:
+    os.environ["RS_KNN_POP"] = pop
+    for index in ([int(os.environ["CYC_INDEX"])] if "CYC_INDEX" in os.environ else sorted({0, count - 1})):
         h = rs.core._Handle(sim=sim, knn_type=knn_type, k=k, device=0, shard_count=count if count > 1 else 0,
                             shard_index=index, sim_path="stream")
         ms = []
@@ -34,5 +37,5 @@ for count in counts:
                          train.GlobalMean)
             p = h.profile()
             ms.append(p["sim_kernel_ms"])
-        print(f"{wl} shards={count} index={index} sim_ms={min(ms[1:]):.2f} prep_ms={p['prep_ms']:.2f}", flush=True)
+        print(f"{wl} pop={pop} shards={count} index={index} sim_ms={min(ms[1:]):.2f} prep_ms={p['prep_ms']:.2f}", flush=True)
         h.close()
