@@ -66,6 +66,180 @@ __device__ __forceinline__ void stream_update(double *acc, int j, double ra, dou
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Popular columns.  The column walk below serialises a row's entries in ONE warp, so the few rows that a large
+// part of the right ids rated (78 k of 138 k on the MovieLens-20M shape) are chains of tens of thousands of
+// dependent steps, and as COLUMNS they fill the other rows' runs with most of the triples (the 312 longest of
+// 26,744 rows hold 34 % of the ratings and take part in 56 % of the co-rated triples).  rs_prep_rt takes their
+// ratings out of the CSR the walk reads and lays them out as a dense table D[right id][popular column]; every
+// pair with a popular column is computed from it by a second kind of work item of the same kernel:
+//   (row i, block of 32 popular columns), one warp; LANE = column, accumulators in registers; the warp walks
+//   row i's entries in ascending right id c — the reference's order (core/sim.go:14-22) —, each step is ONE
+//   coalesced load of D[c][block] (independent of the accumulators: 16 or 8 in flight) and, in the lanes whose column c
+//   rated, the reference's IEEE operations on the lane's own sums.
+// No lookups, no gathers, no shared-memory read-modify-writes, and no item depends on another: a row of 78 k
+// entries is 10 items of 78 k pipelined steps.  Who computes which pair (the mirror passes copy the transposed
+// cell): a popular column's pairs with every other row belong to THAT row; two popular rows: to the one further
+// down the popular list (the shorter one); two other rows: the triangle rule of the column walk.
+
+struct PopArgs {
+    const int32_t *rows;      // the shard's rows, longest first: the popular ones come first
+    int64_t n_rows;
+    const int32_t *pop_idx;   // [n_left] index in the popular list or -1
+    const int32_t *pop_items; // [32 * n_blk] row id, -1 beyond the list
+    int32_t n_blk, ld;        // blocks of 32 popular columns; row stride of the table
+    const void *dense;
+    int64_t n_first;          // dense items of the shard's popular rows: they open the work queue (longest chains)
+    int32_t skip;             // profiling only (RS_KNN_STREAM_SKIP, results are wrong): 1 popular rows' dense items, 2 walk items, 4 other rows' dense items
+};
+
+__device__ __forceinline__ void pop_cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void pop_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void pop_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One dense item.  `scratch`: 3 KB of the warp's shared memory (its accumulator area): per batch of 32 entries the
+// a-side terms {ra, ra^2} [32][2], the right rows' biases [32], the right ids [32], and — byte table — two buffers
+// of 32 x 32 table bytes filled by cp.async one batch ahead (two 16-byte copies per lane and batch; the right ids
+// are loaded two batches ahead), so the chain of a long row is bound by its own arithmetic, not by memory latency.
+// The per-entry arithmetic is branch-free: every lane computes its b-side term and products, only the three
+// additions are predicated on "this column was rated" — the unrolled entries overlap in the FP64 pipe.
+template <int SIM, bool SHRINK, typename DT>
+__device__ __forceinline__ void pop_item(const StreamArgs &a, const PopArgs &pa, int64_t item, double *scratch, int lane) {
+    constexpr bool U8 = sizeof(DT) == 1;
+    double2 *s_a = reinterpret_cast<double2 *>(scratch);                          // {ra, ra * ra}
+    double *s_rbias = scratch + 64;
+    int32_t *s_c = reinterpret_cast<int32_t *>(scratch + 96);
+    uint8_t *s_d = reinterpret_cast<uint8_t *>(scratch + 112);                    // [2][32][32]
+    const DT *__restrict__ dense = static_cast<const DT *>(pa.dense);
+    const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
+    const int32_t i = pa.rows[item / pa.n_blk];
+    const int b = (int)(item % pa.n_blk);
+    const int pi = pa.pop_idx[i];
+    if (pi >= 0 && 32 * b > pi) return;                       // a popular row: only the columns above it in the list
+    const int col = 32 * b + lane;
+    const int32_t hcol = pa.pop_items[col];
+    const bool want = hcol >= 0 && (pi < 0 || col < pi);
+    double bh = 0.0;                                          // what is subtracted from the column's ratings
+    if (want && SIM == RS_SIM_PEARSON) bh = a.pmeans[hcol];
+    if (want && SIM == RS_SIM_PEARSON_BASELINE) bh = a.global_bias + a.left_bias[hcol];
+    double ai = 0.0;
+    if (SIM == RS_SIM_PEARSON) ai = a.pmeans[i];
+    if (SIM == RS_SIM_PEARSON_BASELINE) ai = a.global_bias + a.left_bias[i];
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    const int64_t eb = a.l_ptr[i], ee = a.l_ptr[i + 1];
+
+    // the reference's operations on the lane's sums for one entry; `rated` predicates the additions only
+    auto apply = [&](bool rated, double rb, const double2 aa, double rbias_u) {
+        (void)rbias_u;
+        if (SIM == RS_SIM_MSD) {
+            const double dd = aa.x - rb;
+            const double t = dd * dd;
+            if (rated) { acc0 += t; acc1 += 1.0; }                                // core/sim.go:37-38
+        } else {
+            const double t1 = rb * rb, t2 = aa.x * rb;
+            if (rated) {
+                acc0 += aa.y;                                                     // core/sim.go:19 / :75
+                acc1 += t1;                                                       // core/sim.go:20 / :76
+                acc2 += t2;                                                       // core/sim.go:21 / :77
+                if (SHRINK) acc3 += 1.0;
+            }
+        }
+    };
+
+    if (__any_sync(0xffffffffu, want)) {
+        // batch k: entries [eb + 32 k, ...); (c, v) in registers for batches k and k + 1, loads of k + 2 in flight
+        int32_t c_0 = 0, c_1 = 0;
+        double v_0 = 0.0, v_1 = 0.0;
+        if (eb + lane < ee) { c_0 = a.l_col[eb + lane]; v_0 = a.l_val[eb + lane]; }
+        if (eb + 32 + lane < ee) { c_1 = a.l_col[eb + 32 + lane]; v_1 = a.l_val[eb + 32 + lane]; }
+        // copies of one batch: piece p = lane, lane + 32 is half (p & 1) of entry p >> 1
+        auto issue = [&](int32_t c_l, int64_t x0, int buf) {
+            if constexpr (U8) {
+#pragma unroll
+                for (int h2 = 0; h2 < 2; h2++) {
+                    const int p = lane + 32 * h2, u = p >> 1;
+                    const int32_t c_u = __shfl_sync(0xffffffffu, c_l, u);
+                    if (x0 + u < ee)
+                        pop_cp_async16(s_d + buf * 1024 + 32 * u + 16 * (p & 1),
+                                       reinterpret_cast<const uint8_t *>(dense) + (int64_t)c_u * pa.ld + 32 * b + 16 * (p & 1));
+                }
+            }
+            pop_commit();
+        };
+        __syncwarp();
+        issue(c_0, eb, 0);
+        int buf = 0;
+        for (int64_t x0 = eb; x0 < ee; x0 += 32, buf ^= 1) {
+            const int32_t c = c_0;
+            const double v = v_0;
+            c_0 = c_1; v_0 = v_1;
+            c_1 = 0; v_1 = 0.0;
+            if (x0 + 64 + lane < ee) { c_1 = a.l_col[x0 + 64 + lane]; v_1 = a.l_val[x0 + 64 + lane]; }
+            double ra = 0.0, rbias = 0.0;
+            if (x0 + lane < ee) {
+                if (SIM == RS_SIM_PEARSON) ra = v - ai;                           // core/sim.go:73
+                else if (SIM == RS_SIM_PEARSON_BASELINE) { rbias = a.right_bias[c]; const double bb = ai + rbias; ra = v - bb; }
+                else ra = v;
+            }
+            s_a[lane] = make_double2(ra, ra * ra);                                // core/sim.go:19 / :75
+            if (SIM == RS_SIM_PEARSON_BASELINE) s_rbias[lane] = rbias;
+            if (!U8) s_c[lane] = c;
+            issue(c_0, x0 + 32, buf ^ 1);                     // the next batch, into the buffer the previous one left
+            pop_wait<1>();                                    // this batch has landed (this lane's copies) ...
+            __syncwarp();                                     // ... and every lane's; the staged terms are visible
+            const int lim = (ee - x0) < 32 ? (int)(ee - x0) : 32;
+            if constexpr (U8) {
+                const uint8_t *sd = s_d + buf * 1024 + lane;
+#pragma unroll 8
+                for (int u = 0; u < lim; u++) {
+                    const int code = want ? (int)sd[32 * u] : 0;
+                    // code -> rating without a conversion: 2^52 + 2^51 + code as a double, minus 2^52 + 2^51 + bias (exact)
+                    const double y = __hiloint2double(0x43380000, code) - (6755399441055744.0 + (double)RS_INT8_BIAS);
+                    const double2 aa = s_a[u];
+                    double rb;                                                    // the b-side term, as build_rdev_kernel (prep.cu)
+                    double rbias_u = 0.0;
+                    if (SIM == RS_SIM_PEARSON) rb = y - bh;                       // core/sim.go:74
+                    else if (SIM == RS_SIM_PEARSON_BASELINE) { rbias_u = s_rbias[u]; const double bb = bh + rbias_u; rb = y - bb; }
+                    else rb = y;
+                    apply(code != 0, rb, aa, rbias_u);
+                }
+            } else {
+                constexpr int PU = 8;                                             // table loads in flight
+                for (int u0 = 0; u0 < lim; u0 += PU) {
+                    double d[PU];
+#pragma unroll
+                    for (int g = 0; g < PU; g++) {
+                        d[g] = nan_v;
+                        if (want && u0 + g < lim) d[g] = dense[(int64_t)s_c[u0 + g] * pa.ld + col];
+                    }
+#pragma unroll
+                    for (int g = 0; g < PU; g++) {
+                        const int u = (u0 + g) & 31;
+                        apply(d[g] == d[g], d[g], s_a[u], 0.0);
+                    }
+                }
+            }
+            __syncwarp();                                     // the batch has been read: its buffer and the staged terms are free
+        }
+        pop_wait<0>();
+    }
+
+    if (hcol >= 0) {
+        double *out = a.sims + (a.cyc_R > 1 ? rs_cyc_local(i, a.cyc_R) : (int64_t)(i - a.row_begin)) * a.ld_s;
+        if (pi >= 0 && col == pi) {
+            out[hcol] = nan_v;                                                    // diagonal stays NaN
+        } else if (want) {
+            double s;
+            if (SIM == RS_SIM_MSD) s = 1.0 / (acc0 / acc1 + 1.0);                              // core/sim.go:43
+            else s = acc2 / (sqrt(acc0) * sqrt(acc1));                                         // core/sim.go:24 / :80
+            if (SHRINK) s = (acc3 - 1.0) / (acc3 - 1.0 + a.shrinkage) * s;
+            out[hcol] = s;
+        }
+    }
+}
+
 // SYM = 1: the full matrix is being computed, only columns j > i are visited (the run starts right
 // after i's own position in c's list) and the mirror pass fills j < i.  SYM = 2: only columns j < i
 // (the run ends at i's own position).  Which triangle is cheaper depends on how the row lengths
@@ -76,8 +250,10 @@ __device__ __forceinline__ void stream_update(double *acc, int j, double ra, dou
 // Indices into the right CSR are kept in 32 bits inside the loop (nnz < 2^32 is checked at launch)
 // and the per-entry a-side terms are staged in shared memory, which halves the instructions per
 // column against the first version of this kernel (profiles/r01_stream_notes.md).
-template <int SIM, bool SHRINK, int SYM, int JC>
-__global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
+// POP = 1 / 2: popular columns were split off (table of bytes / of doubles): the queue holds the dense items of the
+// shard's popular rows (the longest chains) first, then the column-walk items, then the dense items of the other rows.
+template <int SIM, bool SHRINK, int SYM, int JC, int POP>
+__global__ void __launch_bounds__(SW * 32, 4) sim_stream_kernel(StreamArgs a, PopArgs pa) {
     constexpr int NACC = SHRINK ? 4 : 3;
     extern __shared__ double s_acc_all[];                    // [SW][NACC][JC] accumulators, then [SW][32] a-side terms
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -93,7 +269,20 @@ __global__ void __launch_bounds__(SW * 32) sim_stream_kernel(StreamArgs a) {
         unsigned long long item = 0;
         if (lane == 0) item = atomicAdd(a.counter, 1ull);
         item = __shfl_sync(0xffffffffu, item, 0);
-        if ((int64_t)item >= n_items) break;
+        if (POP) {
+            int64_t d = (int64_t)item;
+            if (d >= pa.n_first) d = d >= pa.n_first + n_items ? d - n_items : -1;
+            if (d >= pa.n_rows * pa.n_blk) break;
+            if (pa.skip && ((d >= 0 && d < pa.n_first && (pa.skip & 1)) || (d < 0 && (pa.skip & 2)) || (d >= pa.n_first && (pa.skip & 4)))) continue;
+            if (d >= 0) {
+                __syncwarp();
+                if (POP == 1) pop_item<SIM, SHRINK, uint8_t>(a, pa, d, acc, lane);
+                else pop_item<SIM, SHRINK, double>(a, pa, d, acc, lane);
+                __syncwarp();
+                continue;
+            }
+            item -= (unsigned long long)pa.n_first;
+        } else if ((int64_t)item >= n_items) break;
         // items are ordered longest row first, so the critical path starts early
         const int64_t q = (int64_t)item % Q;
         const int32_t i = a.row_order[(int64_t)item / Q];
@@ -435,139 +624,6 @@ __global__ void __launch_bounds__(HV_WARPS * 32, 1) sim_stream_heavy_kernel(Stre
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Popular columns.  The column walk serialises a row's entries in ONE warp, so the few rows that a large part of
-// the right ids rated (78 k of 138 k on the MovieLens-20M shape) are chains of tens of thousands of dependent
-// steps, and as COLUMNS they fill the other rows' runs with most of the triples (the 312 longest of 26,744 rows
-// hold 34 % of the ratings and take part in 56 % of the co-rated triples).  rs_prep_rt takes their ratings out of
-// the CSR the walk reads and lays them out as a dense table D[right id][popular column]; this kernel computes
-// every pair with a popular column from it:
-//   work item = (row i, block of 32 popular columns), one warp; LANE = column, accumulators in registers;
-//   the warp walks row i's entries in ascending right id c — the reference's order (core/sim.go:14-22) —, each
-//   step is ONE coalesced load of D[c][block] (independent of the accumulators: 16 in flight) and, in the lanes
-//   whose column c rated, the reference's IEEE operations on the lane's own sums.
-// No lookups, no gathers, no shared-memory read-modify-writes, and no work item depends on another: a row of
-// 78 k entries is 10 items of 78 k pipelined steps.  Who computes which pair (the mirror passes below copy the
-// transposed cell): a popular column's pairs with every other row belong to THAT row; two popular rows: to the one
-// further down the popular list (the shorter one); two other rows: the triangle rule of the column walk.
-constexpr int PW = 8;       // warps per CTA
-constexpr int PU = 16;      // loads in flight per warp
-
-struct PopArgs {
-    const int32_t *rows;      // the shard's rows, longest first
-    int64_t n_rows;
-    const int32_t *pop_idx;   // [n_left] index in the popular list or -1
-    const int32_t *pop_items; // [32 * n_blk] row id, -1 beyond the list
-    int32_t n_blk, ld;        // blocks of 32 popular columns; row stride of the table
-    const void *dense;
-    unsigned long long *counter;
-};
-
-template <int SIM, bool SHRINK, typename DT>
-__global__ void __launch_bounds__(PW * 32) sim_pop_kernel(StreamArgs a, PopArgs pa) {
-    __shared__ double s_ra[PW][32];
-    __shared__ double s_rbias[PW][32];
-    __shared__ int32_t s_c[PW][32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const DT *__restrict__ dense = static_cast<const DT *>(pa.dense);
-    const int64_t n_items = pa.n_rows * pa.n_blk;
-    const double nan_v = __longlong_as_double(0x7ff8000000000001ll);
-
-    for (;;) {
-        unsigned long long item = 0;
-        if (lane == 0) item = atomicAdd(pa.counter, 1ull);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if ((int64_t)item >= n_items) break;
-        const int32_t i = pa.rows[(int64_t)item / pa.n_blk];
-        const int b = (int)((int64_t)item % pa.n_blk);
-        const int pi = pa.pop_idx[i];
-        if (pi >= 0 && 32 * b > pi) continue;                 // a popular row: only the columns above it in the list
-        const int col = 32 * b + lane;
-        const int32_t hcol = pa.pop_items[col];
-        const bool want = hcol >= 0 && (pi < 0 || col < pi);
-        double bh = 0.0;                                      // what is subtracted from the column's ratings
-        if (want && SIM == RS_SIM_PEARSON) bh = a.pmeans[hcol];
-        if (want && SIM == RS_SIM_PEARSON_BASELINE) bh = a.global_bias + a.left_bias[hcol];
-        double ai = 0.0;
-        if (SIM == RS_SIM_PEARSON) ai = a.pmeans[i];
-        if (SIM == RS_SIM_PEARSON_BASELINE) ai = a.global_bias + a.left_bias[i];
-        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-        const int64_t eb = a.l_ptr[i], ee = a.l_ptr[i + 1];
-
-        if (__any_sync(0xffffffffu, want)) {
-            for (int64_t x0 = eb; x0 < ee; x0 += 32) {
-                const int64_t e = x0 + lane;
-                int32_t c = 0;
-                double ra = 0.0, rbias = 0.0;
-                if (e < ee) {
-                    c = a.l_col[e];
-                    const double v = a.l_val[e];
-                    if (SIM == RS_SIM_PEARSON) ra = v - ai;                       // core/sim.go:73
-                    else if (SIM == RS_SIM_PEARSON_BASELINE) { rbias = a.right_bias[c]; const double bb = ai + rbias; ra = v - bb; }
-                    else ra = v;
-                }
-                __syncwarp();                                 // the previous batch has been read
-                s_c[warp][lane] = c;
-                s_ra[warp][lane] = ra;
-                if (SIM == RS_SIM_PEARSON_BASELINE) s_rbias[warp][lane] = rbias;
-                __syncwarp();
-                const int lim = (ee - x0) < 32 ? (int)(ee - x0) : 32;
-#pragma unroll
-                for (int u0 = 0; u0 < 32; u0 += PU) {
-                    if (u0 >= lim) break;
-                    DT d[PU];
-#pragma unroll
-                    for (int g = 0; g < PU; g++) {
-                        const int u = u0 + g;
-                        if constexpr (sizeof(DT) == 1) d[g] = (DT)0; else d[g] = (DT)nan_v;
-                        if (want && u < lim) d[g] = dense[(int64_t)s_c[warp][u] * pa.ld + col];
-                    }
-#pragma unroll
-                    for (int g = 0; g < PU; g++) {
-                        const int u = u0 + g;
-                        const bool rated = sizeof(DT) == 1 ? (d[g] != (DT)0) : (d[g] == d[g]);
-                        if (!rated) continue;
-                        const double ra_u = s_ra[warp][u];
-                        double rb;                                                // the b-side term, as build_rdev_kernel (prep.cu)
-                        if constexpr (sizeof(DT) == 1) {
-                            const double y = (double)((int)d[g] - RS_INT8_BIAS);
-                            if (SIM == RS_SIM_PEARSON) rb = y - bh;               // core/sim.go:74
-                            else if (SIM == RS_SIM_PEARSON_BASELINE) { const double bb = bh + s_rbias[warp][u]; rb = y - bb; }
-                            else rb = y;
-                        } else {
-                            rb = (double)d[g];
-                        }
-                        if (SIM == RS_SIM_MSD) {
-                            const double dd = ra_u - rb;
-                            acc0 += dd * dd;                                      // core/sim.go:37
-                            acc1 += 1.0;                                          // core/sim.go:38
-                        } else {
-                            const double raa_u = ra_u * ra_u;
-                            acc0 += raa_u;                                        // core/sim.go:19 / :75
-                            acc1 += rb * rb;                                      // core/sim.go:20 / :76
-                            acc2 += ra_u * rb;                                    // core/sim.go:21 / :77
-                            if (SHRINK) acc3 += 1.0;
-                        }
-                    }
-                }
-            }
-        }
-
-        if (hcol >= 0) {
-            double *out = a.sims + (a.cyc_R > 1 ? rs_cyc_local(i, a.cyc_R) : (int64_t)(i - a.row_begin)) * a.ld_s;
-            if (pi >= 0 && col == pi) {
-                out[hcol] = nan_v;                                                // diagonal stays NaN
-            } else if (want) {
-                double s;
-                if (SIM == RS_SIM_MSD) s = 1.0 / (acc0 / acc1 + 1.0);                          // core/sim.go:43
-                else s = acc2 / (sqrt(acc0) * sqrt(acc1));                                     // core/sim.go:24 / :80
-                if (SHRINK) s = (acc3 - 1.0) / (acc3 - 1.0 + a.shrinkage) * s;
-                out[hcol] = s;
-            }
-        }
-    }
-}
-
 // does row r's own pass (column walk or sim_pop_kernel) compute cell (r, c)?  pr / pc: their popular indices or -1
 __device__ __forceinline__ bool pop_owns(int64_t r, int64_t c, int pr, int pc, int lower) {
     if (pc >= 0 && pr < 0) return true;
@@ -682,27 +738,35 @@ __global__ void mirror_pop_kernel(MirrorArgs a, const int32_t *__restrict__ pop_
 
 }  // namespace
 
-template <int SIM, bool SHRINK, int SYM, int JC>
-static int32_t launch_stream_jc(rs_knn *h, const StreamArgs &s, int grid) {
+template <int SIM, bool SHRINK, int SYM, int JC, int POP>
+static int32_t launch_stream_pop(rs_knn *h, const StreamArgs &s, const PopArgs &pa, int grid) {
     const int smem = SW * ((SHRINK ? 4 : 3) * JC + 32) * (int)sizeof(double);
-    auto kern = sim_stream_kernel<SIM, SHRINK, SYM, JC>;
+    auto kern = sim_stream_kernel<SIM, SHRINK, SYM, JC, POP>;
     RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, SW * 32, smem, h->stream>>>(s);
+    kern<<<grid, SW * 32, smem, h->stream>>>(s, pa);
     return RS_OK;
 }
+template <int SIM, bool SHRINK, int SYM, int JC>
+static int32_t launch_stream_jc(rs_knn *h, const StreamArgs &s, const PopArgs &pa, int grid) {
+    if (SYM != 0 && s.pop_idx) {                              // popular columns exist only where a triangle is computed
+        if (h->pop_u8) return launch_stream_pop<SIM, SHRINK, SYM ? SYM : 1, JC, 1>(h, s, pa, grid);
+        return launch_stream_pop<SIM, SHRINK, SYM ? SYM : 1, JC, 2>(h, s, pa, grid);
+    }
+    return launch_stream_pop<SIM, SHRINK, SYM, JC, 0>(h, s, pa, grid);
+}
 template <int SIM, bool SHRINK, int SYM>
-static int32_t launch_stream_sym(rs_knn *h, const StreamArgs &s, int grid) {
-    if (h->stream_jc == 128) return launch_stream_jc<SIM, SHRINK, SYM, 128>(h, s, grid);
-    return launch_stream_jc<SIM, SHRINK, SYM, 256>(h, s, grid);
+static int32_t launch_stream_sym(rs_knn *h, const StreamArgs &s, const PopArgs &pa, int grid) {
+    if (h->stream_jc == 128) return launch_stream_jc<SIM, SHRINK, SYM, 128>(h, s, pa, grid);
+    return launch_stream_jc<SIM, SHRINK, SYM, 256>(h, s, pa, grid);
 }
 template <int SIM, bool SHRINK>
-static int32_t launch_stream(rs_knn *h, const StreamArgs &s, int grid) {
+static int32_t launch_stream(rs_knn *h, const StreamArgs &s, const PopArgs &pa, int grid) {
     if (h->nnz >= (int64_t)0xffffffffll) {
         rs_set_error("stream path indexes the ratings with 32 bits (nnz=%lld)", (long long)h->nnz);
         return RS_ERR_UNSUPPORTED;
     }
-    if (s.symmetric == 2) return launch_stream_sym<SIM, SHRINK, 2>(h, s, grid);
-    return s.symmetric ? launch_stream_sym<SIM, SHRINK, 1>(h, s, grid) : launch_stream_sym<SIM, SHRINK, 0>(h, s, grid);
+    if (s.symmetric == 2) return launch_stream_sym<SIM, SHRINK, 2>(h, s, pa, grid);
+    return s.symmetric ? launch_stream_sym<SIM, SHRINK, 1>(h, s, pa, grid) : launch_stream_sym<SIM, SHRINK, 0>(h, s, pa, grid);
 }
 
 template <int SIM, bool SHRINK>
@@ -719,32 +783,6 @@ static int32_t launch_heavy(rs_knn *h, const StreamArgs &a, const HeavyArgs &hv)
     kern<<<(unsigned)grid, HV_WARPS * 32, smem, h->aux_stream>>>(a, hv);
     h->prof.total_launches += 1;
     return RS_OK;
-}
-
-template <int SIM, bool SHRINK>
-static int32_t launch_pop(rs_knn *h, const StreamArgs &a, const PopArgs &pa) {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    const int64_t items = pa.n_rows * pa.n_blk;
-    int64_t grid = (int64_t)sms * 4;                          // resident CTAs; warps pull work items from the counter
-    if (grid > (items + PW - 1) / PW) grid = (items + PW - 1) / PW;
-    // on the auxiliary stream, beside the column walk of the other columns
-    if (h->pop_u8) sim_pop_kernel<SIM, SHRINK, uint8_t><<<(unsigned)grid, PW * 32, 0, h->aux_stream>>>(a, pa);
-    else sim_pop_kernel<SIM, SHRINK, double><<<(unsigned)grid, PW * 32, 0, h->aux_stream>>>(a, pa);
-    h->prof.total_launches += 1;
-    return RS_OK;
-}
-
-static int32_t rs_pop_launch(rs_knn *h, const StreamArgs &a, const PopArgs &pa) {
-    switch (h->p.sim) {
-    case RS_SIM_COSINE: return launch_pop<RS_SIM_COSINE, false>(h, a, pa);
-    case RS_SIM_MSD: return launch_pop<RS_SIM_MSD, false>(h, a, pa);
-    case RS_SIM_PEARSON: return launch_pop<RS_SIM_PEARSON, false>(h, a, pa);
-    case RS_SIM_PEARSON_BASELINE:
-        return h->p.shrinkage > 0.0 ? launch_pop<RS_SIM_PEARSON_BASELINE, true>(h, a, pa)
-                                    : launch_pop<RS_SIM_PEARSON_BASELINE, false>(h, a, pa);
-    default: rs_set_error("unknown similarity %d", h->p.sim); return RS_ERR_INVALID;
-    }
 }
 
 static int32_t rs_heavy_rows_launch(rs_knn *h, const StreamArgs &a, const HeavyArgs &hv) {
@@ -776,26 +814,22 @@ int32_t rs_sim_stream_launch(rs_knn *h) {
     a.symmetric = h->force_sym ? 1 : ((h->row_begin == 0 && h->row_end == h->n_left) || cyc) ? (h->stream_lower ? 2 : 1) : 0;
     a.counter = reinterpret_cast<unsigned long long *>(h->d_flags + 2);
     RS_CUDA(cudaMemsetAsync(a.counter, 0, 8, h->stream));
-    // popular columns (rs_prep_rt split them off: the walk reads the CSR without them) run as a dense pass on the
-    // auxiliary stream beside the column walk
+    // popular columns (rs_prep_rt split them off: the walk reads the CSR without them): their pairs are dense work
+    // items of the same kernel
     const bool pop = h->n_pop > 0;
+    PopArgs pa{};
     if (pop) {
         if (a.symmetric == 0 || h->force_sym) {
             rs_set_error("popular columns were split off, but this Fit does not compute a triangle of the full matrix");
             return RS_ERR_INVALID;
         }
         a.r_ptr = h->w_ptr; a.r_col = h->w_col; a.r_dev = h->w_dev; a.pop_idx = h->pop_idx;
-        PopArgs pa{};
         pa.rows = h->row_all; pa.n_rows = h->n_all_rows;
         pa.pop_idx = h->pop_idx; pa.pop_items = h->pop_items;
         pa.n_blk = h->pop_ld / 32; pa.ld = h->pop_ld;
         pa.dense = h->pop_dense;
-        pa.counter = reinterpret_cast<unsigned long long *>(h->d_flags + 12);
-        RS_CUDA(cudaMemsetAsync(pa.counter, 0, 8, h->stream));
-        RS_CUDA(cudaEventRecord(h->ev_fork, h->stream));
-        RS_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
-        if (pa.n_rows > 0) RS_TRY(rs_pop_launch(h, a, pa));
-        RS_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
+        pa.n_first = (h->n_all_rows - a.n_rows) * pa.n_blk;
+        if (const char *e = getenv("RS_KNN_STREAM_SKIP")) pa.skip = atoi(e);
     }
     // heavy rows (rs_prep_rt split them off the order; JC = 256 only) run as producer / consumer CTAs on the
     // auxiliary stream beside the column walk of the other rows
@@ -810,26 +844,26 @@ int32_t rs_sim_stream_launch(rs_knn *h) {
         RS_TRY(rs_heavy_rows_launch(h, a, hv));
         RS_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
     }
-    if (a.n_rows <= 0) {
-        if (heavy || pop) RS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    if (a.n_rows <= 0 && !(pop && pa.n_rows > 0)) {
+        if (heavy) RS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         return RS_OK;
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    const int64_t items = a.n_rows * (int64_t)h->n_chunks;
+    const int64_t items = a.n_rows * (int64_t)h->n_chunks + (pop ? pa.n_rows * pa.n_blk : 0);
     int64_t grid = (int64_t)sms * 4;          // resident CTAs; warps pull work items from the counter
     if (grid > (items + SW - 1) / SW) grid = (items + SW - 1) / SW;
     switch (h->p.sim) {
-    case RS_SIM_COSINE: RS_TRY((launch_stream<RS_SIM_COSINE, false>(h, a, (int)grid))); break;
-    case RS_SIM_MSD: RS_TRY((launch_stream<RS_SIM_MSD, false>(h, a, (int)grid))); break;
-    case RS_SIM_PEARSON: RS_TRY((launch_stream<RS_SIM_PEARSON, false>(h, a, (int)grid))); break;
+    case RS_SIM_COSINE: RS_TRY((launch_stream<RS_SIM_COSINE, false>(h, a, pa, (int)grid))); break;
+    case RS_SIM_MSD: RS_TRY((launch_stream<RS_SIM_MSD, false>(h, a, pa, (int)grid))); break;
+    case RS_SIM_PEARSON: RS_TRY((launch_stream<RS_SIM_PEARSON, false>(h, a, pa, (int)grid))); break;
     case RS_SIM_PEARSON_BASELINE:
-        if (h->p.shrinkage > 0.0) RS_TRY((launch_stream<RS_SIM_PEARSON_BASELINE, true>(h, a, (int)grid)));
-        else RS_TRY((launch_stream<RS_SIM_PEARSON_BASELINE, false>(h, a, (int)grid)));
+        if (h->p.shrinkage > 0.0) RS_TRY((launch_stream<RS_SIM_PEARSON_BASELINE, true>(h, a, pa, (int)grid)));
+        else RS_TRY((launch_stream<RS_SIM_PEARSON_BASELINE, false>(h, a, pa, (int)grid)));
         break;
     default: rs_set_error("unknown similarity %d", h->p.sim); return RS_ERR_INVALID;
     }
-    if (heavy || pop) RS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    if (heavy) RS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     h->prof.sim_launches++;
     h->prof.total_launches++;
     RS_CUDA(cudaGetLastError());
