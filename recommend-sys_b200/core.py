@@ -67,7 +67,8 @@ ABI_SYMBOLS = [
     "rs_knn_topk_device", "rs_knn_cosums", "rs_knn_means", "rs_knn_stddevs", "rs_knn_profile_get",
     "rs_knn_profile_reset", "rs_knn_synchronize", "rs_knn_trim_cache", "rs_baseline_als",
     "rs_knn_topk_union_device", "rs_knn_set_k", "rs_knn_peer_export", "rs_knn_peer_import",
-    "rs_knn_peer_import_local", "rs_knn_mirror", "rs_knn_predict_batch_sharded_device",
+    "rs_knn_peer_import_local", "rs_knn_mirror", "rs_knn_predict_batch_sharded_device", "rs_knn_host_alloc",
+    "rs_knn_host_free",
 ]
 
 _knn_lib = None
@@ -116,6 +117,8 @@ def knn_lib():
     L.rs_knn_peer_import_local.argtypes = [vp, i32, vp]
     L.rs_knn_mirror.argtypes = [vp]
     L.rs_knn_predict_batch_sharded_device.argtypes = [vp, vp, vp, i64, vp]
+    L.rs_knn_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.rs_knn_host_free.argtypes = [vp]
     _knn_lib = L
     return L
 
@@ -150,6 +153,8 @@ def host_lib():
     L.rs_host_route_pairs.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     L.rs_host_convert_dense.restype = None
     L.rs_host_convert_dense.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+    L.rs_host_convert_dense_mt.restype = None
+    L.rs_host_convert_dense_mt.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]
     _host_lib = L
     return L
 
@@ -364,19 +369,50 @@ class TrainSet(DataSet):
         self._maps()
         return self._imap.get(int(itemID), newID)
 
-    def convert_users(self, raw):
+    def convert_users(self, raw, out=None):
         """Vectorised ConvertUserID for a batch (newID = -1 for unseen ids)."""
         if self._ulook is None:
             self._ulook = _lookup_table(self.Users, self.innerUsers)
-        return _convert(self._ulook, raw)
+        return _convert(self._ulook, raw, out)
 
-    def convert_items(self, raw):
+    def convert_items(self, raw, out=None):
         if self._ilook is None:
             self._ilook = _lookup_table(self.Items, self.innerItems)
-        return _convert(self._ilook, raw)
+        return _convert(self._ilook, raw, out)
 
     def RatingRange(self):
         return float(self.Ratings.min()), float(self.Ratings.max())
+
+
+class _HostBlock:
+    """A page-locked host block of rs_knn_host_alloc; goes back to the library's cache with the last array on it."""
+
+    def __init__(self, nbytes):
+        p = C.c_void_p()
+        _check(knn_lib().rs_knn_host_alloc(max(1, nbytes), C.byref(p)))
+        self.ptr = p.value
+
+    def __del__(self):
+        try:
+            knn_lib().rs_knn_host_free(self.ptr)
+        except Exception:      # interpreter shutdown
+            pass
+
+
+def pinned_empty(n, dtype):
+    """An uninitialised numpy array of n elements in page-locked host memory (full-speed, asynchronous copies to and
+    from the device); ordinary memory if no CUDA device can provide it."""
+    dtype = np.dtype(dtype)
+    nbytes = int(n) * dtype.itemsize
+    if nbytes == 0:
+        return np.empty(0, dtype=dtype)
+    try:
+        blk = _HostBlock(nbytes)
+    except (RsError, RuntimeError):
+        return np.empty(n, dtype=dtype)
+    buf = (C.c_char * nbytes).from_address(blk.ptr)
+    buf._blk = blk                      # the array's base keeps the block alive
+    return np.frombuffer(buf, dtype=dtype, count=int(n))
 
 
 def _lookup_table(known_raw, known_inner):
@@ -391,17 +427,27 @@ def _lookup_table(known_raw, known_inner):
     return ("sorted", uniq, np.ascontiguousarray(known_inner[first]))
 
 
-def _convert(table, raw):
+def host_threads():
+    """Host threads one process may use for the id conversion: its share of the cores when several ranks
+    (one per GPU) run on the box."""
+    world = int(os.environ.get("LOCAL_WORLD_SIZE") or os.environ.get("WORLD_SIZE") or 1)
+    return max(1, min(8, (os.cpu_count() or 1) // max(1, world)))
+
+
+def _convert(table, raw, out=None):
+    """Inner ids of `raw` (newID where unknown).  `out`: an int32 array to fill (e.g. pinned staging memory)."""
     raw = np.ascontiguousarray(raw, dtype=np.int64)
+    if out is None:
+        out = np.empty(len(raw), dtype=np.int32)
+    assert out.dtype == np.int32 and out.flags.c_contiguous and len(out) == len(raw)
     if table[0] == "dense":
         dense = table[1]
-        out = np.empty(len(raw), dtype=np.int32)
-        host_lib().rs_host_convert_dense(_ptr(dense), len(dense) - 1, _ptr(raw), len(raw), _ptr(out))
+        host_lib().rs_host_convert_dense_mt(_ptr(dense), len(dense) - 1, _ptr(raw), len(raw), _ptr(out), host_threads())
         return out
     _, uniq, inner = table
     pos = np.clip(np.searchsorted(uniq, raw), 0, len(uniq) - 1)
-    out = np.where(uniq[pos] == raw, inner[pos], newID).astype(np.int32)
-    return np.ascontiguousarray(out)
+    out[:] = np.where(uniq[pos] == raw, inner[pos], newID)
+    return out
 
 
 def NewTrainSet(rowSet: DataSet) -> TrainSet:
@@ -581,7 +627,7 @@ class _Handle:
     def predict_batch(self, left, right):
         left = np.ascontiguousarray(left, dtype=np.int32)
         right = np.ascontiguousarray(right, dtype=np.int32)
-        out = np.empty(len(left), dtype=np.float64)
+        out = pinned_empty(len(left), np.float64) if len(left) >= 1 << 16 else np.empty(len(left), dtype=np.float64)
         _check(knn_lib().rs_knn_predict_batch(self.h, _ptr(left), _ptr(right), len(left), _ptr(out)))
         return out
 
@@ -832,8 +878,11 @@ class KNN(Base):
 
     def PredictBatch(self, userIDs, itemIDs):
         """BatchPredictor: the whole of DataSet.Predict (core/data.go:98-105) in one device call."""
-        iu = self.Data.convert_users(userIDs)
-        ii = self.Data.convert_items(itemIDs)
+        # large batches: the inner ids are written into page-locked staging memory (and the predictions come back
+        # into it): both copies of rs_knn_predict_batch then run at full PCIe speed
+        big = len(userIDs) >= 1 << 16
+        iu = self.Data.convert_users(userIDs, out=pinned_empty(len(userIDs), np.int32) if big else None)
+        ii = self.Data.convert_items(itemIDs, out=pinned_empty(len(itemIDs), np.int32) if big else None)
         left, right = (iu, ii) if self._userBased else (ii, iu)
         # core/knn.go:80-81 reads k / mink in Predict: SetParams after Fit takes effect here
         k, mink = self.Params.GetInt("k", 40), self.Params.GetInt("mink", 1)

@@ -901,8 +901,48 @@ int32_t rs_knn_profile_get(rs_knn *h, rs_knn_profile *out) {
     return RS_OK;
 }
 
+// ---- page-locked host blocks, cached per process ----
+namespace {
+struct HostBlock { void *p; size_t bytes; bool used; };
+std::mutex g_host_mu;
+std::vector<HostBlock> g_host;
+}  // namespace
+
+int32_t rs_knn_host_alloc(size_t bytes, void **out) {
+    if (!out) { rs_set_error("rs_knn_host_alloc: null argument"); return RS_ERR_INVALID; }
+    if (bytes == 0) bytes = 1;
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    HostBlock *best = nullptr;
+    for (auto &b : g_host)                                   // the smallest free block that fits without wasting half of it
+        if (!b.used && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096 && (!best || b.bytes < best->bytes)) best = &b;
+    if (best) { best->used = true; *out = best->p; return RS_OK; }
+    void *p = nullptr;
+    RS_CUDA(cudaHostAlloc(&p, bytes, cudaHostAllocPortable));
+    g_host.push_back({p, bytes, true});
+    *out = p;
+    return RS_OK;
+}
+
+int32_t rs_knn_host_free(void *p) {
+    if (!p) return RS_OK;
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    for (auto &b : g_host)
+        if (b.p == p && b.used) { b.used = false; return RS_OK; }
+    rs_set_error("rs_knn_host_free: not a block of rs_knn_host_alloc");
+    return RS_ERR_INVALID;
+}
+
 int32_t rs_knn_trim_cache(void) {
     rs_cache_trim();
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        size_t kept = 0;
+        for (auto &b : g_host) {
+            if (b.used) g_host[kept++] = b;
+            else cudaFreeHost(b.p);
+        }
+        g_host.resize(kept);
+    }
     std::lock_guard<std::mutex> lk(g_ipc_mu);
     int cur = 0;
     cudaGetDevice(&cur);

@@ -7,6 +7,7 @@
 #include <string>
 #include <cstring>
 #include <unordered_map>
+#include <thread>
 #include <vector>
 
 extern "C" {
@@ -158,11 +159,32 @@ double rs_host_mean_seq(const double *x, int64_t n) {
     return sum / (double)n;
 }
 
-void rs_host_convert_dense(const int32_t *table, int64_t n_table, const int64_t *raw, int64_t n, int32_t *inner_out) {
-    for (int64_t x = 0; x < n; x++) {
+static void convert_dense_range(const int32_t *table, int64_t n_table, const int64_t *raw, int64_t x0, int64_t x1,
+                                int32_t *inner_out) {
+    for (int64_t x = x0; x < x1; x++) {
         const int64_t r = raw[x];
         inner_out[x] = (r >= 0 && r < n_table) ? table[r] : -1;     // -1 = newID (core/data.go:129)
     }
+}
+
+void rs_host_convert_dense(const int32_t *table, int64_t n_table, const int64_t *raw, int64_t n, int32_t *inner_out) {
+    convert_dense_range(table, n_table, raw, 0, n, inner_out);
+}
+
+// The same over `threads` host threads (a test set of 4 M pairs: 6.5 ms per id column on one core — under a
+// Fit sharded over 8 GPUs that is longer than the similarity kernel it is meant to hide behind).
+void rs_host_convert_dense_mt(const int32_t *table, int64_t n_table, const int64_t *raw, int64_t n, int32_t *inner_out,
+                              int32_t threads) {
+    if (threads > 16) threads = 16;
+    if (threads < 2 || n < (int64_t)1 << 18) { convert_dense_range(table, n_table, raw, 0, n, inner_out); return; }
+    std::vector<std::thread> pool;
+    const int64_t per = (n + threads - 1) / threads;
+    for (int32_t t = 1; t < threads; t++) {
+        const int64_t x0 = per * t < n ? per * t : n, x1 = per * (t + 1) < n ? per * (t + 1) : n;
+        pool.emplace_back(convert_dense_range, table, n_table, raw, x0, x1, inner_out);
+    }
+    convert_dense_range(table, n_table, raw, 0, per < n ? per : n, inner_out);
+    for (auto &th : pool) th.join();
 }
 
 // Routing of test pairs to the cyclic row shards of a multi-GPU Fit (csrc/common.cuh RS_CYC_B): the pair goes

@@ -41,6 +41,9 @@ int64_t rs_host_load_ratings(const char *path, const char *sep, int32_t float_ra
 /* TrainSet.GlobalMean (core/data.go:134): sequential sum / n. */
 double rs_host_mean_seq(const double *x, int64_t n);
 void rs_host_convert_dense(const int32_t *table, int64_t n_table, const int64_t *raw, int64_t n, int32_t *inner_out);
+/* the same on `threads` host threads (large test sets; the conversion runs beside the similarity kernel) */
+void rs_host_convert_dense_mt(const int32_t *table, int64_t n_table, const int64_t *raw, int64_t n, int32_t *inner_out,
+                              int32_t threads);
 
 /* Deterministic synthetic rating matrices of the BASELINE.json shapes:
  * unique (user,item) pairs, heavy-tailed degrees, integer ratings 1..5 with a MovieLens-like

@@ -204,25 +204,34 @@ class ShardedKNN:
     def PredictBatch(self, userIDs, itemIDs):
         import numpy as np
         import torch
-
-        k = self.knn
-        iu = k.Data.convert_users(userIDs)
-        ii = k.Data.convert_items(itemIDs)
-        left, right = (iu, ii) if k._userBased else (ii, iu)
         import torch.distributed as dist
 
-        # every rank gets the FULL test set (32 MB at 4 M pairs — cheaper than routing it on the host); a shard
-        # answers the pairs whose left row it owns and leaves +0.0 elsewhere; an int64 SUM all-reduce of the bit
-        # patterns over NVLink assembles the vector exactly (x + 0 + ... + 0 in integer arithmetic)
+        k = self.knn
+        n = len(userIDs)
+        if n == 0:
+            self._finish_fit()
+            return np.empty(0, dtype=np.float64)
+        # Inner ids are written straight into pinned staging memory (torch's caching host allocator: no
+        # cudaHostAlloc after the first call) by the threaded host conversion, which runs beside the similarity
+        # kernel (Fit has returned, the kernel has not).  Every rank gets the FULL test set (32 MB at 4 M pairs —
+        # cheaper than routing it on the host); a shard answers the pairs whose left row it owns and leaves +0.0
+        # elsewhere; an int64 SUM all-reduce of the bit patterns over NVLink assembles the vector exactly
+        # (x + 0 + ... + 0 in integer arithmetic).
         dev = torch.device("cuda", torch.cuda.current_device())
-        d_l = torch.from_numpy(np.ascontiguousarray(left, dtype=np.int32)).to(dev, non_blocking=True)
-        d_r = torch.from_numpy(np.ascontiguousarray(right, dtype=np.int32)).to(dev, non_blocking=True)
-        d_o = torch.empty(max(1, len(left)), dtype=torch.float64, device=dev)
+        p_l = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        p_r = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        k.Data.convert_users(userIDs, out=(p_l if k._userBased else p_r).numpy())
+        k.Data.convert_items(itemIDs, out=(p_r if k._userBased else p_l).numpy())
+        d_l = p_l.to(dev, non_blocking=True)
+        d_r = p_r.to(dev, non_blocking=True)
+        d_o = torch.empty(n, dtype=torch.float64, device=dev)
         self._finish_fit()
-        if len(left):
-            k._h.predict_batch_sharded_device(d_l.data_ptr(), d_r.data_ptr(), len(left), d_o.data_ptr())
-            dist.all_reduce(d_o.view(torch.int64), op=dist.ReduceOp.SUM, group=self.group)
-        return d_o[: len(left)].cpu().numpy()
+        k._h.predict_batch_sharded_device(d_l.data_ptr(), d_r.data_ptr(), n, d_o.data_ptr())
+        dist.all_reduce(d_o.view(torch.int64), op=dist.ReduceOp.SUM, group=self.group)
+        out = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        out.copy_(d_o, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out.numpy()
 
     def Predict(self, userID, itemID):
         import numpy as np

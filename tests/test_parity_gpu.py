@@ -226,6 +226,34 @@ def test_concurrent_predict_on_one_handle(ml100k):
     assert bits_equal(np.concatenate(out), want)
 
 
+# ---- page-locked staging of large batches (rs_knn_host_alloc): same predictions as the pageable path, blocks are
+# cached and reused ----
+def test_pinned_staging_of_large_batches(ml100k):
+    import ctypes as C
+
+    L = rs.core.knn_lib()
+    p, q = C.c_void_p(), C.c_void_p()
+    assert L.rs_knn_host_alloc(1 << 20, C.byref(p)) == 0 and p.value
+    assert L.rs_knn_host_free(p) == 0
+    assert L.rs_knn_host_alloc(1 << 20, C.byref(q)) == 0 and q.value == p.value      # reused
+    assert L.rs_knn_host_free(q) == 0
+    assert L.rs_knn_host_free(C.c_void_p(12345)) != 0
+    arr = rs.core.pinned_empty(1000, np.float64)
+    arr[:] = np.arange(1000)
+    assert arr.base is not None and arr.sum() == 499500.0
+    u, i, r = split(ml100k["u1_base"])
+    est = rs.NewKNNWithMean(rs.Parameters({"sim": rs.Pearson, "userBased": False, "k": 40}))
+    est.Fit(rs.NewTrainSet(rs.NewRawSet(u, i, r)))
+    tu, ti, _ = split(ml100k["u1_test"])
+    small = np.concatenate([est.PredictBatch(tu[x:x + 5000], ti[x:x + 5000]) for x in range(0, len(tu), 5000)])
+    big_u, big_i = np.tile(tu, 4), np.tile(ti, 4)                                    # 80,000 pairs: the pinned path
+    assert len(big_u) >= 1 << 16
+    big = est.PredictBatch(big_u, big_i)
+    assert bits_equal(big, np.tile(small, 4))
+    del big, arr
+    assert L.rs_knn_trim_cache() == 0
+
+
 # ---- the longest rows of the exact sparse Fit.  mode "pop" (default): their ratings leave the CSR the column walk
 # reads and every pair with one of them comes from the dense pass (sim_pop_kernel: lane = popular column, register
 # accumulators); mode "heavy": they stay in the walk as producer / consumer CTAs.  Every row (min 0: the 512
