@@ -46,25 +46,32 @@ inline unsigned blocks_for(int64_t n, int t = T) { return (unsigned)((n + t - 1)
 
 enum { FLAG_BAD_ID = 1, FLAG_NOT_INT8 = 2, FLAG_DUP = 4, FLAG_NAN = 8 };
 
+// (the per-row counts are NOT taken here: 40 M atomic increments were the largest kernel of the ML-20M prep,
+// 1.0 ms; the row pointers come out of the sorted key sequences instead, ptr_from_sorted_kernel)
 __global__ void iota_validate_kernel(const int32_t *__restrict__ left, const int32_t *__restrict__ right,
                                      const double *__restrict__ rating, int64_t nnz, int32_t n_left,
-                                     int32_t n_right, int32_t *__restrict__ idx, int32_t *__restrict__ lcount,
-                                     int32_t *__restrict__ rcount, int32_t *__restrict__ flags) {
+                                     int32_t n_right, int32_t *__restrict__ idx, int32_t *__restrict__ flags) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnz) return;
     idx[i] = (int32_t)i;
     int32_t l = left[i], r = right[i];
     int f = 0;
-    if (l < 0 || l >= n_left || r < 0 || r >= n_right) {
-        f |= FLAG_BAD_ID;
-    } else {
-        atomicAdd(&lcount[l], 1);
-        atomicAdd(&rcount[r], 1);
-    }
+    if (l < 0 || l >= n_left || r < 0 || r >= n_right) f |= FLAG_BAD_ID;
     double v = rating[i];
     if (v != v) f |= FLAG_NAN;
     if (!(v == rint(v) && fabs(v) <= 11.0)) f |= FLAG_NOT_INT8;
     if (f) atomicOr(flags, f);
+}
+
+// CSR row pointers from the ascending key sequence of a sort: ptr[k] = first position whose key is >= k
+// (k = 0 .. n_rows; empty rows included).  The entry that opens a new key closes every pointer in between.
+__global__ void ptr_from_sorted_kernel(const int32_t *__restrict__ keys, int64_t nnz, int32_t n_rows,
+                                       int64_t *__restrict__ ptr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nnz) return;
+    const int32_t cur = i < nnz ? keys[i] : n_rows;           // sentinel after the last entry
+    const int32_t prev = i > 0 ? keys[i - 1] : -1;
+    for (int32_t k = prev + 1; k <= cur; k++) ptr[k] = i;
 }
 
 __global__ void gather_keys_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ perm, int64_t n,
@@ -73,25 +80,24 @@ __global__ void gather_keys_kernel(const int32_t *__restrict__ src, const int32_
     if (i < n) out[i] = src[perm[i]];
 }
 
-__global__ void widen_kernel(const int32_t *__restrict__ in, int64_t n, int64_t *__restrict__ out) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = in[i];
-}
-
 // entries of the (major, minor)-sorted permutation -> CSR column / value arrays
-__global__ void gather_csr_kernel(const int32_t *__restrict__ perm, const int32_t *__restrict__ major,
-                                  const int32_t *__restrict__ minor, const double *__restrict__ rating,
-                                  int64_t nnz, int32_t *__restrict__ col, double *__restrict__ val,
-                                  int32_t *__restrict__ flags) {
+__global__ void gather_csr_kernel(const int32_t *__restrict__ perm, const int32_t *__restrict__ minor,
+                                  const double *__restrict__ rating, int64_t nnz, int32_t *__restrict__ col,
+                                  double *__restrict__ val) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnz) return;
     int32_t p = perm[i];
     col[i] = minor[p];
     val[i] = rating[p];
-    if (i > 0 && flags) {
-        int32_t q = perm[i - 1];
-        if (major[p] == major[q] && minor[p] == minor[q]) atomicOr(flags, FLAG_DUP);
-    }
+}
+
+// duplicate (left, right) pairs are adjacent in a CSR: `row` = the sorted major keys the last sort left behind,
+// `col` = the gathered minor ids (both read coalesced; the check used to re-gather three ids per entry)
+__global__ void dup_check_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col, int64_t nnz,
+                                 int32_t *__restrict__ flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 || i >= nnz) return;
+    if (row[i] == row[i - 1] && col[i] == col[i - 1]) atomicOr(flags, FLAG_DUP);
 }
 
 __global__ void gather_val_kernel(const int32_t *__restrict__ perm, const double *__restrict__ rating, int64_t nnz,
@@ -364,14 +370,15 @@ int bits_for(int32_t n) {
 
 // sum over right rows of cnt*(cnt-1)/2 = co-rated triples (i < j, common right id): the work of the
 // stream path, used by the Fit path model (api.cu)
-__global__ void triples_kernel(const int32_t *__restrict__ rcount, int32_t nr, unsigned long long *out,
+__global__ void triples_kernel(const int64_t *__restrict__ r_ptr, int32_t nr, unsigned long long *out,
                                int32_t *max_len) {
     unsigned long long acc = 0;
     int32_t mx = 0;
     for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nr; c += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long n = (unsigned long long)rcount[c];
+        const int32_t cnt = (int32_t)(r_ptr[c + 1] - r_ptr[c]);
+        const unsigned long long n = (unsigned long long)cnt;
         acc += n * (n - (n ? 1 : 0)) / 2;
-        mx = rcount[c] > mx ? rcount[c] : mx;
+        mx = cnt > mx ? cnt : mx;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const int32_t v = __shfl_xor_sync(0xffffffffu, mx, o); mx = v > mx ? v : mx; }
@@ -383,12 +390,12 @@ __global__ void triples_kernel(const int32_t *__restrict__ rcount, int32_t nr, u
 
 // (entry, chunk) lookups the stream kernel performs when it computes the upper (j > i) or the lower
 // (j < i) triangle: row i pays one lookup per entry and per column chunk it visits.
-__global__ void incidence_kernel(const int32_t *__restrict__ lcount, int32_t nl, int32_t jc,
+__global__ void incidence_kernel(const int64_t *__restrict__ l_ptr, int32_t nl, int32_t jc,
                                  unsigned long long *out) {
     unsigned long long up = 0, lo = 0;
     const long long q_all = (nl + jc - 1) / jc;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nl; i += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long d = (unsigned long long)lcount[i];
+        const unsigned long long d = (unsigned long long)(l_ptr[i + 1] - l_ptr[i]);
         const long long q = i / jc;
         up += d * (unsigned long long)(q_all - q);
         lo += d * (unsigned long long)(q + 1);
@@ -431,7 +438,7 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
         return RS_ERR_UNSUPPORTED;
     }
     SortTmp tmp;
-    int32_t *idx, *keys_a, *keys_b, *perm_l, *perm_r, *perm_lr, *perm_rl, *lcount, *rcount;
+    int32_t *idx, *keys_a, *keys_b, *perm_l, *perm_r, *perm_lr, *perm_rl;
     RS_TRY(rs_alloc(h, &idx, nnz));
     RS_TRY(rs_alloc(h, &keys_a, nnz));
     RS_TRY(rs_alloc(h, &keys_b, nnz));
@@ -439,29 +446,17 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     RS_TRY(rs_alloc(h, &perm_r, nnz));
     RS_TRY(rs_alloc(h, &perm_lr, nnz));
     RS_TRY(rs_alloc(h, &perm_rl, nnz));
-    RS_TRY(rs_alloc(h, &lcount, (size_t)nl + 1));
-    RS_TRY(rs_alloc(h, &rcount, (size_t)nr + 1));
     RS_TRY(rs_alloc(h, &h->d_flags, 16));
-    RS_CUDA(cudaMemsetAsync(lcount, 0, ((size_t)nl + 1) * 4, st));
-    RS_CUDA(cudaMemsetAsync(rcount, 0, ((size_t)nr + 1) * 4, st));
+    RS_TRY(rs_alloc(h, &h->l_ptr, (size_t)nl + 1));
+    RS_TRY(rs_alloc(h, &h->r_ptr, (size_t)nr + 1));
     RS_CUDA(cudaMemsetAsync(h->d_flags, 0, 64, st));
 
-    iota_validate_kernel<<<blocks_for(nnz), T, 0, st>>>(d_left, d_right, d_rating, nnz, nl, nr, idx, lcount,
-                                                       rcount, h->d_flags);
-    triples_kernel<<<148, T, 0, st>>>(rcount, nr, reinterpret_cast<unsigned long long *>(h->d_flags + 6), h->d_flags + 15);
+    iota_validate_kernel<<<blocks_for(nnz), T, 0, st>>>(d_left, d_right, d_rating, nnz, nl, nr, idx, h->d_flags);
     h->stream_jc = rs_stream_jc(nl);
-    incidence_kernel<<<148, T, 0, st>>>(lcount, nl, h->stream_jc, reinterpret_cast<unsigned long long *>(h->d_flags + 8));
-    h->prof.total_launches += 3;
+    h->prof.total_launches += 1;
     int32_t flags = 0;
-    int32_t fl8[16] = {0};
-    RS_CUDA(cudaMemcpyAsync(fl8, h->d_flags, 64, cudaMemcpyDeviceToHost, st));
+    RS_CUDA(cudaMemcpyAsync(&flags, h->d_flags, 4, cudaMemcpyDeviceToHost, st));
     RS_CUDA(cudaStreamSynchronize(st));
-    flags = fl8[0];
-    { unsigned long long t; memcpy(&t, fl8 + 6, 8); h->triples = (double)t; }
-    h->max_right_len = fl8[15];
-    { unsigned long long t[2]; memcpy(t, fl8 + 8, 16); h->inc_upper = (double)t[0]; h->inc_lower = (double)t[1]; }
-    h->stream_lower = h->inc_lower < h->inc_upper;
-    if (const char *e = getenv("RS_KNN_STREAM_TRI")) h->stream_lower = !strcmp(e, "lower");   // tests: force a triangle
     if (flags & FLAG_BAD_ID) {
         rs_set_error("rating rows contain inner ids outside [0,n_left) x [0,n_right)");
         return RS_ERR_INVALID;
@@ -479,9 +474,18 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     const bool need_dataset_order = h->rating_class != RS_CLASS_INT8 || h->p.knn_type == RS_KNN_ZSCORE;
     if (need_dataset_order) RS_SORT_PAIRS(d_left, keys_a, idx, perm_l, nnz, lb);
     RS_SORT_PAIRS(d_right, keys_a, idx, perm_r, nnz, rb);
+    // keys_a = the right ids in ascending order: the right CSR's row pointers, and from them the co-rated
+    // triples and the longest right row (read back with the duplicate flag at the end)
+    ptr_from_sorted_kernel<<<blocks_for(nnz + 1), T, 0, st>>>(keys_a, nnz, nr, h->r_ptr);
+    triples_kernel<<<148, T, 0, st>>>(h->r_ptr, nr, reinterpret_cast<unsigned long long *>(h->d_flags + 6), h->d_flags + 15);
     // (left, right asc): stable sort by left of the right-sorted sequence
     gather_keys_kernel<<<blocks_for(nnz), T, 0, st>>>(d_left, perm_r, nnz, keys_a);
     RS_SORT_PAIRS(keys_a, keys_b, perm_r, perm_lr, nnz, lb);
+    // keys_b = the left ids in ascending order: the left CSR's row pointers, and the (entry, chunk) lookups of
+    // the two triangles of a stream Fit
+    ptr_from_sorted_kernel<<<blocks_for(nnz + 1), T, 0, st>>>(keys_b, nnz, nl, h->l_ptr);
+    incidence_kernel<<<148, T, 0, st>>>(h->l_ptr, nl, h->stream_jc, reinterpret_cast<unsigned long long *>(h->d_flags + 8));
+    h->prof.total_launches += 4;
     // (right, left asc): stable sort by right of the (left, right asc) sequence
     gather_keys_kernel<<<blocks_for(nnz), T, 0, st>>>(d_right, perm_lr, nnz, keys_a);
     RS_SORT_PAIRS(keys_a, keys_b, perm_lr, perm_rl, nnz, rb);
@@ -497,34 +501,16 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
     h->perm_rl = perm_rl;
     h->perm_tmp = keys_b;
 
-    // row pointers
-    RS_TRY(rs_alloc(h, &h->l_ptr, (size_t)nl + 1));
-    RS_TRY(rs_alloc(h, &h->r_ptr, (size_t)nr + 1));
-    {
-        int64_t *wide;
-        size_t mx = (size_t)(nl > nr ? nl : nr) + 1;
-        RS_TRY(rs_alloc(h, &wide, mx));
-        size_t need = 0;
-        RS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, wide, h->l_ptr, (int)mx, st));
-        if (need > tmp.bytes) { RS_TRY(rs_dev_alloc(h, &tmp.p, need)); tmp.bytes = need; }
-        widen_kernel<<<blocks_for(nl + 1), T, 0, st>>>(lcount, nl + 1, wide);
-        RS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp.bytes, wide, h->l_ptr, nl + 1, st));
-        widen_kernel<<<blocks_for(nr + 1), T, 0, st>>>(rcount, nr + 1, wide);
-        RS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp.bytes, wide, h->r_ptr, nr + 1, st));
-        h->prof.total_launches += 2;
-    }
-
     RS_TRY(rs_alloc(h, &h->l_col, nnz));
     RS_TRY(rs_alloc(h, &h->l_val, nnz));
     RS_TRY(rs_alloc(h, &h->ld_val, nnz));
     RS_TRY(rs_alloc(h, &h->r_col, nnz));
     RS_TRY(rs_alloc(h, &h->r_val, nnz));
-    gather_csr_kernel<<<blocks_for(nnz), T, 0, st>>>(perm_lr, d_left, d_right, d_rating, nnz, h->l_col, h->l_val,
-                                                    h->d_flags);
-    gather_csr_kernel<<<blocks_for(nnz), T, 0, st>>>(perm_rl, d_right, d_left, d_rating, nnz, h->r_col, h->r_val,
-                                                    nullptr);
+    gather_csr_kernel<<<blocks_for(nnz), T, 0, st>>>(perm_lr, d_right, d_rating, nnz, h->l_col, h->l_val);
+    gather_csr_kernel<<<blocks_for(nnz), T, 0, st>>>(perm_rl, d_left, d_rating, nnz, h->r_col, h->r_val);
+    dup_check_kernel<<<blocks_for(nnz), T, 0, st>>>(keys_b, h->r_col, nnz, h->d_flags);   // keys_b: the right ids, sorted
     if (need_dataset_order) gather_val_kernel<<<blocks_for(nnz), T, 0, st>>>(perm_l, d_rating, nnz, h->ld_val);
-    h->prof.total_launches += need_dataset_order ? 3 : 2;
+    h->prof.total_launches += need_dataset_order ? 4 : 3;
 
     // byte codes (rating + 12) of the integer class: operands of the tensor path and of the exact
     // integer row sums.  Any other float64 rating set runs on the stream path, which reads the
@@ -568,8 +554,15 @@ int32_t rs_prep_build(rs_knn *h, const int32_t *d_left, const int32_t *d_right, 
         RS_CUDA(cudaMemcpyAsync(h->right_bias, d_right_bias, (size_t)nr * 8, cudaMemcpyDeviceToDevice, st));
     }
 
-    RS_CUDA(cudaMemcpyAsync(&flags, h->d_flags, 4, cudaMemcpyDeviceToHost, st));
+    int32_t fl8[16] = {0};
+    RS_CUDA(cudaMemcpyAsync(fl8, h->d_flags, 64, cudaMemcpyDeviceToHost, st));
     RS_CUDA(cudaStreamSynchronize(st));
+    flags = fl8[0];
+    { unsigned long long t; memcpy(&t, fl8 + 6, 8); h->triples = (double)t; }
+    h->max_right_len = fl8[15];
+    { unsigned long long t[2]; memcpy(t, fl8 + 8, 16); h->inc_upper = (double)t[0]; h->inc_lower = (double)t[1]; }
+    h->stream_lower = h->inc_lower < h->inc_upper;
+    if (const char *e = getenv("RS_KNN_STREAM_TRI")) h->stream_lower = !strcmp(e, "lower");   // tests: force a triangle
     if (flags & FLAG_DUP) {
         rs_set_error("duplicate (left,right) rating pairs are not supported (the reference's merge-join "
                      "double-counts them)");
