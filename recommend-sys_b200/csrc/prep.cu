@@ -624,7 +624,9 @@ static int32_t split_popular(rs_knn *h, const int32_t *sorted, const int32_t *le
     cudaStream_t st = h->stream;
     int32_t *d_num;
     RS_TRY(rs_alloc(h, &d_num, 4));
-    pop_count_kernel<<<1, 1, 0, st>>>(len_sorted, h->n_left, min_len, RS_POP_MAX, d_num);
+    int32_t cap = RS_POP_MAX;
+    if (const char *e = getenv("RS_KNN_POP_MAX")) { cap = atoi(e); cap = cap < 2 ? 2 : (cap > 2048 ? 2048 : cap); }   // experiments
+    pop_count_kernel<<<1, 1, 0, st>>>(len_sorted, h->n_left, min_len, cap, d_num);
     int32_t n_pop = 0;
     RS_CUDA(cudaMemcpyAsync(&n_pop, d_num, 4, cudaMemcpyDeviceToHost, st));
     RS_CUDA(cudaStreamSynchronize(st));

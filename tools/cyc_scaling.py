@@ -25,8 +25,13 @@ right = train.innerItems if user_based else train.innerUsers
 dev = torch.device("cuda", 0)
 d_left, d_right = torch.from_numpy(left).to(dev), torch.from_numpy(right).to(dev)
 d_rating = torch.from_numpy(train.Ratings).to(dev)
-for pop, count in [(p_, c_) for p_ in os.environ.get("CYC_POP", "1").split(",") for c_ in counts]:
+# CYC_SWEEP="min:max,min:max,...": popular-column thresholds (RS_KNN_HEAVY_MIN : RS_KNN_POP_MAX) to run in one process
+sweep = [x.split(":") for x in os.environ["CYC_SWEEP"].split(",")] if "CYC_SWEEP" in os.environ else [None]
+for sw, pop, count in [(s_, p_, c_) for s_ in sweep for p_ in os.environ.get("CYC_POP", "1").split(",") for c_ in counts]:
     os.environ["RS_KNN_POP"] = pop
+    if sw:
+        os.environ["RS_KNN_HEAVY_MIN"], os.environ["RS_KNN_POP_MAX"] = sw
+        print("threshold", sw, end=" ")
     for index in ([int(os.environ["CYC_INDEX"])] if "CYC_INDEX" in os.environ else sorted({0, count - 1})):
         h = rs.core._Handle(sim=sim, knn_type=knn_type, k=k, device=0, shard_count=count if count > 1 else 0,
                             shard_index=index, sim_path="stream")
