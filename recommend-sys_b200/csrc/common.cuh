@@ -166,6 +166,7 @@ struct rs_knn {
     bool pop_u8 = false;
     int32_t *pop_idx = nullptr;    // [n_left] index in the popular list or -1
     int32_t *pop_items = nullptr;  // [pop_ld] row id (-1 beyond n_pop)
+    uint8_t *pop_blk = nullptr;    // [ceil(n_left / 32)] the block of 32 rows holds a popular row
     void *pop_dense = nullptr;
     int64_t *w_ptr = nullptr;
     int32_t *w_col = nullptr;

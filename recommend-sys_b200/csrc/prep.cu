@@ -255,10 +255,11 @@ __global__ void pop_count_kernel(const int32_t *__restrict__ len_sorted, int32_t
 }
 // pop_idx[row] = position in the popular list (-1 elsewhere: the array is preset to 0xFF), pop_items = the list
 __global__ void pop_index_kernel(const int32_t *__restrict__ sorted, int32_t n_pop, int32_t pop_ld,
-                                 int32_t *__restrict__ pop_idx, int32_t *__restrict__ pop_items) {
+                                 int32_t *__restrict__ pop_idx, int32_t *__restrict__ pop_items,
+                                 uint8_t *__restrict__ pop_blk) {
     const int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= pop_ld) return;
-    if (p < n_pop) { const int32_t i = sorted[p]; pop_idx[i] = p; pop_items[p] = i; }
+    if (p < n_pop) { const int32_t i = sorted[p]; pop_idx[i] = p; pop_items[p] = i; pop_blk[i >> 5] = 1; }
     else pop_items[p] = -1;
 }
 // One warp per right row: its popular ratings go into the dense table (preset to "no rating"), the others are
@@ -638,8 +639,10 @@ static int32_t split_popular(rs_knn *h, const int32_t *sorted, const int32_t *le
     h->pop_u8 = h->rating_class == RS_CLASS_INT8;
     RS_TRY(rs_alloc(h, &h->pop_idx, (size_t)h->n_left));
     RS_TRY(rs_alloc(h, &h->pop_items, (size_t)h->pop_ld));
+    RS_TRY(rs_alloc(h, &h->pop_blk, ((size_t)h->n_left + 31) / 32 + 1));
     RS_CUDA(cudaMemsetAsync(h->pop_idx, 0xFF, (size_t)h->n_left * 4, st));
-    pop_index_kernel<<<blocks_for(h->pop_ld), T, 0, st>>>(sorted, n_pop, h->pop_ld, h->pop_idx, h->pop_items);
+    RS_CUDA(cudaMemsetAsync(h->pop_blk, 0, ((size_t)h->n_left + 31) / 32 + 1, st));
+    pop_index_kernel<<<blocks_for(h->pop_ld), T, 0, st>>>(sorted, n_pop, h->pop_ld, h->pop_idx, h->pop_items, h->pop_blk);
     // dense table + walk CSR
     const size_t cell = h->pop_u8 ? 1 : 8;
     RS_TRY(rs_dev_alloc(h, &h->pop_dense, (size_t)nr * h->pop_ld * cell));

@@ -688,10 +688,26 @@ __global__ void mirror_kernel(MirrorArgs a) {
 // The same two passes when popular columns were split off: which of the cells (r, c) / (c, r) was computed is
 // pop_owns(), cell by cell, so a pair of transposed tiles may exchange cells in both directions.
 __global__ void symmetrize_pop_kernel(double *__restrict__ s, int64_t ld, int32_t n, int lower,
-                                      const int32_t *__restrict__ pop_idx) {
+                                      const int32_t *__restrict__ pop_idx, const uint8_t *__restrict__ pop_blk) {
     __shared__ double ta[32][33], tb[32][33];
     const int64_t bi = blockIdx.y, bj = blockIdx.x;
     if (bj > bi) return;                                     // one block per unordered tile pair
+    if (!(pop_blk[bi] | pop_blk[bj])) {
+        // neither block of 32 rows holds a popular row (most of the matrix): the plain triangle rule of
+        // symmetrize_kernel, one tile read and one written
+        const int64_t di = lower ? bj : bi, dj = lower ? bi : bj;     // destination tile (rows di, cols dj)
+        const int64_t r0 = di * 32, c0 = dj * 32;
+        for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+            const int64_t sr = c0 + y, sc = r0 + threadIdx.x;         // source = transposed position
+            ta[y][threadIdx.x] = (sr < n && sc < n) ? s[sr * ld + sc] : 0.0;
+        }
+        __syncthreads();
+        for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+            const int64_t r = r0 + y, c = c0 + threadIdx.x;
+            if (r < n && c < n && (lower ? c > r : c < r)) s[r * ld + c] = ta[threadIdx.x][y];
+        }
+        return;
+    }
     const int64_t r0 = bi * 32, c0 = bj * 32;                // tile A = rows r0.., cols c0..; tile B = rows c0.., cols r0..
     for (int y = threadIdx.y; y < 32; y += blockDim.y) {
         const int64_t ar = r0 + y, ac = c0 + threadIdx.x, br = c0 + y, bc = r0 + threadIdx.x;
@@ -892,7 +908,7 @@ int32_t rs_symmetrize_launch(rs_knn *h) {
     if (!(h->row_begin == 0 && h->row_end == h->n_left)) return RS_OK;
     const unsigned t = (unsigned)((h->n_left + 31) / 32);
     dim3 grid(t, t), block(32, 8);
-    if (h->n_pop > 0) symmetrize_pop_kernel<<<grid, block, 0, h->stream>>>(h->sims, h->ld_s, h->n_left, h->stream_lower ? 1 : 0, h->pop_idx);
+    if (h->n_pop > 0) symmetrize_pop_kernel<<<grid, block, 0, h->stream>>>(h->sims, h->ld_s, h->n_left, h->stream_lower ? 1 : 0, h->pop_idx, h->pop_blk);
     else symmetrize_kernel<<<grid, block, 0, h->stream>>>(h->sims, h->ld_s, h->n_left, h->stream_lower ? 1 : 0);
     h->prof.total_launches++;
     RS_CUDA(cudaGetLastError());
