@@ -153,3 +153,29 @@ def test_loader_reference_semantics_and_half_stars(tmp_path):
     assert d.Users.tolist() == [196, 186] and d.Items.tolist() == [242, 302] and d.Ratings.tolist() == [3.0, 3.0]
     with pytest.raises(OSError):
         rs.LoadDataFromFile(tmp_path / "nope")
+
+
+def test_threaded_id_conversion_equals_serial():
+    """rs_host_convert_dense_mt (the batch form of ConvertUserID / ConvertItemID, core/data.go:110-122): any number of
+    host threads gives the serial result, unknown and negative ids become newID = -1, and a caller-provided output
+    array (pinned staging memory on the GPU box) is filled in place."""
+    rng = np.random.RandomState(5)
+    known = rng.permutation(50_000)[:30_000].astype(np.int64)
+    d = rs.NewRawSet(known, known[::-1].copy(), np.ones(len(known)))
+    ts = rs.NewTrainSet(d)
+    raw = rng.randint(-5, 60_000, size=700_000).astype(np.int64)
+    want = np.array([ts.ConvertUserID(int(x)) for x in raw[:2000]], dtype=np.int32)
+    got = ts.convert_users(raw)
+    assert got.dtype == np.int32 and np.array_equal(got[:2000], want)
+    assert (got[raw < 0] == -1).all() and (got[raw >= 50_000] == -1).all()
+    table = ts._ulook[1]
+    L = rs.core.host_lib()
+    for threads in (1, 2, 3, 7, 64):
+        out = np.full(len(raw), 123, dtype=np.int32)
+        L.rs_host_convert_dense_mt(rs.core._ptr(table), len(table) - 1, rs.core._ptr(raw), len(raw), rs.core._ptr(out), threads)
+        assert np.array_equal(out, got), threads
+    out = np.empty(len(raw), dtype=np.int32)
+    assert ts.convert_users(raw, out=out) is out and np.array_equal(out, got)
+    small = ts.convert_items(raw[:10])              # below the threading threshold
+    assert np.array_equal(small, np.array([ts.ConvertItemID(int(x)) for x in raw[:10]], dtype=np.int32))
+    assert rs.core.host_threads() >= 1
