@@ -16,6 +16,11 @@
 //
 // Bound: shared-memory RMW bandwidth (6 accesses per triple, random banks) and L2 reads of
 // 12 B per triple; see DESIGN.md and profiles/.
+//
+// The longest rows ("popular columns") are taken out of that walk: their pairs are dense work items of the same
+// kernel and queue (pop_item below: lane = column, accumulators in registers), see the comment there.  The
+// producer / consumer kernel further down (sim_stream_heavy_kernel) is the earlier treatment of those rows, kept
+// behind RS_KNN_POP=0 and by the tests.
 #include <cstdlib>
 #include <cstring>
 
