@@ -197,6 +197,21 @@ func (d *deviceKNN) predictBatch(left, right []int32) []float64 {
 	return out
 }
 
+// pinnedInt32 / pinnedFloat64: page-locked host memory of the library's per-process cache (rs_knn_host_alloc) viewed
+// as a Go slice, for callers that stage large batches themselves: copies from and to such memory run at full PCIe
+// speed.  The memory is C memory (no Go pointers in it); release returns the block to the cache.
+func pinnedInt32(n int) (s []int32, release func()) {
+	var p unsafe.Pointer
+	check(C.rs_knn_host_alloc(C.size_t(n*4), &p))
+	return unsafe.Slice((*int32)(p), n), func() { C.rs_knn_host_free(p) }
+}
+
+func pinnedFloat64(n int) (s []float64, release func()) {
+	var p unsafe.Pointer
+	check(C.rs_knn_host_alloc(C.size_t(n*8), &p))
+	return unsafe.Slice((*float64)(p), n), func() { C.rs_knn_host_free(p) }
+}
+
 func (d *deviceKNN) simsRows(row0, nrows, n int) []float64 {
 	out := make([]float64, nrows*n)
 	check(C.rs_knn_sims_rows(d.h, C.int64_t(row0), C.int64_t(nrows), f64(out)))
